@@ -1,0 +1,2 @@
+/* Minimal htslib stand-in for building the oracle (test infrastructure only). */
+#include "shim_all.h"
