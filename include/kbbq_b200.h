@@ -1,0 +1,173 @@
+/*
+ * kbbq_b200.h -- C ABI of the B200-native kbbq recalibration hot path.
+ *
+ * The reference (adamjorr/kbbq) has no plugin/FFI layer: its operator API for this path is the C++ surface of
+ * libkbbq.a that main() drives (src/kbbq/kbbq.cc:264-457).  This header is what a maintainer's replacement pass
+ * drivers bind instead of the CPU loops; each entry point names the reference interface it stands in for.
+ * Plain pointers and sizes only; every function returns 0 on success or a negative KBBQ_E* code, never throws.
+ * Caller owns host buffers; the library owns device memory.  One host thread drives one context (one GPU).
+ *
+ * Table layouts (dense, row-major; R = n_rg, C = max_cycle given to kbbq_ctx_create, 94 = KBBQ_MAXQ+1):
+ *   counts (uint64 {errors,total} pairs):  rg[R][2]  q[R][94][2]  cycle[R][94][2][C][2]  dinuc[R][94][16][2]
+ *   model  (int32):                        meanq[R] rgdq[R] qdq[R][94] cydq[R][94][2][C] didq[R][94][16]
+ * They are covariateutils::CCovariateData / dq_t (covariateutils.hh:21-34,157-172) without the lazy vector growth.
+ */
+#ifndef KBBQ_B200_H
+#define KBBQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KBBQ_OK 0
+#define KBBQ_EINVAL (-1)    /* bad argument (std::invalid_argument in the reference) */
+#define KBBQ_ENOMEM (-2)    /* host or device allocation failed (std::bad_alloc) */
+#define KBBQ_ECUDA (-3)     /* a CUDA call failed; see kbbq_last_error() */
+#define KBBQ_ESTATE (-4)    /* call out of order (e.g. a pass before its filter exists) */
+#define KBBQ_ERANGE (-5)    /* read longer than KBBQ_MAX_READ_LEN, rg >= n_rg, ... */
+
+#define KBBQ_FILTER_SAMPLED 0 /* `subsampled` in kbbq.cc:265 */
+#define KBBQ_FILTER_TRUSTED 1 /* `trusted`    in kbbq.cc:266 */
+#define KBBQ_DEFAULT_BLOOM_SEED 0xA5A5A5A55A5A5A5AULL /* bloom.hh:389 */
+#define KBBQ_ABI_MAX_READ_LEN 512
+
+typedef struct kbbq_ctx kbbq_ctx;       /* one GPU: stream, filters, count tables, model tables */
+typedef struct kbbq_dbatch kbbq_dbatch; /* a read batch resident in device memory */
+
+/* Geometry of a pattern-blocked Bloom filter: what bloom::Bloom's constructor derives (bloom.cc:12-24,
+ * bloom.hh:36-45, bloom_filter.hpp:108-160 and 467-528). */
+typedef struct kbbq_bloom_geom {
+    uint64_t projected;
+    double fpr;
+    uint64_t seed;
+    uint32_t optimal_k;
+    uint64_t optimal_table_size;
+    uint64_t random_seed;
+    uint64_t table_bits;
+    uint64_t n_blocks;
+    uint32_t n_salts;
+    uint32_t salts[128];
+} kbbq_bloom_geom;
+
+/* A batch of reads in packed form, host memory (pinned memory makes the upload asynchronous).
+ * Read r occupies words [word_off[r], word_off[r+1]); base i of it is bits [2*(i%32), +2) of
+ * bases[word_off[r] + i/32] (A=0 C=1 G=2 T=3), bit i%32 of nmask[...] marks a non-ACGT base (the reference's
+ * seq_nt16_int >= 4, bloom.hh:351), and its quality is qual[32*word_off[r] + i] (phred, no +33).  Unused bits and
+ * bytes are zero.  This replaces the per-record CReadData (readutils.hh:44-74) that the reference's pass drivers
+ * pull from htsiter::HTSFile::get() (htsiter.hh:40-49). */
+typedef struct kbbq_batch {
+    uint32_t n_reads;
+    uint32_t max_len;
+    uint64_t n_words;
+    const uint64_t* bases;    /* [n_words] */
+    const uint32_t* nmask;    /* [n_words] */
+    const uint8_t* qual;      /* [32*n_words] */
+    const uint32_t* word_off; /* [n_reads+1] */
+    const uint32_t* len;      /* [n_reads] */
+    const uint16_t* rg;       /* [n_reads] dense read-group id, CReadData::get_rg_int() (readutils.hh:62) */
+    const uint8_t* second;    /* [n_reads] CReadData::second */
+} kbbq_batch;
+
+const char* kbbq_last_error(void);
+int kbbq_device_count(void);
+
+/* ---- host-only helpers (no GPU needed) ------------------------------------------------------------------------ */
+/* bloom::Bloom ctor geometry; KBBQ_EINVAL where the reference throws (bloom.cc:18-21) */
+int kbbq_bloom_geometry(uint64_t projected, double fpr, uint64_t seed, kbbq_bloom_geom* out);
+/* pattern table of pattern_blocked_bf (bloom.hh:189-231): patterns[65536*8] */
+int kbbq_bloom_patterns(const kbbq_bloom_geom* g, uint64_t* patterns);
+/* Bloom::fprate() = pattern_blocked_bf::effective_fpp (bloom.hh:318-330,399) */
+double kbbq_effective_fpp(uint64_t table_bits, uint64_t inserted, uint32_t n_salts);
+/* bloom::calculate_phit (bloom.cc:190-195) chained into covariateutils::calculate_thresholds (covariateutils.hh:71-85),
+ * exactly as kbbq.cc:304-313; thresholds[k+1] */
+int kbbq_thresholds_from_fpr(double fpr, long double alpha, int k, int* thresholds);
+/* minion::Random::Seed(uint32) state (minion.hpp:355-375) advanced by `skip` draws */
+int kbbq_rng_state(uint32_t seed, uint64_t skip, uint64_t state[4]);
+/* CCovariateData::get_dqs (covariateutils.cc:204-230) on dense tables */
+int kbbq_fit_model_host(int n_rg, int max_cycle, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc,
+                        const uint64_t* dic, int32_t* meanq, int32_t* rgdq, int32_t* qdq, int32_t* cydq, int32_t* didq);
+/* Pack ASCII reads (seq[total], off[n+1], qual[total] phred) into the kbbq_batch layout.  Two-call protocol:
+ * kbbq_pack_size gives n_words; the caller allocates; kbbq_pack_reads fills.  Returns KBBQ_ERANGE for a read longer
+ * than KBBQ_ABI_MAX_READ_LEN. */
+int kbbq_pack_size(uint64_t n, const uint64_t* off, uint64_t* n_words, uint32_t* max_len);
+int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint8_t* qual, uint64_t* bases,
+                    uint32_t* nmask, uint8_t* qual_out, uint32_t* word_off, uint32_t* len, int n_threads);
+
+/* ---- context ---------------------------------------------------------------------------------------------------- */
+int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out);
+void kbbq_ctx_destroy(kbbq_ctx* ctx);
+int kbbq_sync(kbbq_ctx* ctx);
+/* the CUDA stream (cudaStream_t) all of this context's work is issued on */
+void* kbbq_stream(kbbq_ctx* ctx);
+/* device time of the most recent pass call in ms (CUDA events on the context's stream); syncs */
+int kbbq_last_pass_ms(kbbq_ctx* ctx, float* ms);
+/* kernels launched by this context so far */
+uint64_t kbbq_launch_count(kbbq_ctx* ctx);
+
+/* ---- filters: bloom::Bloom (bloom.hh:385-402) in HBM -------------------------------------------------------------- */
+int kbbq_bloom_create(kbbq_ctx* ctx, int which, uint64_t projected, double fpr, uint64_t seed);
+int kbbq_bloom_info(kbbq_ctx* ctx, int which, kbbq_bloom_geom* out);
+int kbbq_bloom_clear(kbbq_ctx* ctx, int which);
+/* Bloom::inserted_elements() */
+int kbbq_bloom_inserted(kbbq_ctx* ctx, int which, uint64_t* inserted);
+/* bit array as the reference holds it in bit_table_ (bloom.hh:33): words[table_bits/64]; either pointer may be NULL */
+int kbbq_bloom_download(kbbq_ctx* ctx, int which, uint64_t* words, uint64_t* inserted);
+int kbbq_bloom_upload(kbbq_ctx* ctx, int which, const uint64_t* words, uint64_t inserted);
+/* Bloom::insert / Bloom::query on raw 64-bit keys (bloom.hh:395-398 with a valid Kmer); hits[n] receives 0/1 */
+int kbbq_bloom_insert_keys(kbbq_ctx* ctx, int which, const uint64_t* keys, uint64_t n);
+int kbbq_bloom_query_keys(kbbq_ctx* ctx, int which, const uint64_t* keys, uint64_t n, uint8_t* hits);
+/* Bloom::fprate() from the device-side insert counter */
+int kbbq_bloom_fprate(kbbq_ctx* ctx, int which, double* fpr);
+/* device pointers for collectives (bit array: table_bits/8 bytes; counter: one uint64) */
+void* kbbq_bloom_device_words(kbbq_ctx* ctx, int which);
+void* kbbq_bloom_device_counter(kbbq_ctx* ctx, int which);
+/* words |= other (other: device pointer to an equally sized bit array, e.g. a peer GPU's mapped filter) */
+int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other_device_words, uint64_t first_word, uint64_t n_words);
+
+/* ---- batches -------------------------------------------------------------------------------------------------------- */
+int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
+void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b);
+/* number of k-mer slots of the batch = sum over reads of max(0, len-k+1): the draws pass 1 consumes */
+uint64_t kbbq_batch_slots(const kbbq_dbatch* b);
+
+/* ---- passes (each is asynchronous on the context's stream unless a host output pointer is given) ------------------ */
+/* htsiter::KmerSubsampler(file,k,alpha,seed) (htsiter.hh:143): seeds the sampling stream, position 0 */
+int kbbq_sampler_seed(kbbq_ctx* ctx, uint32_t seed, double alpha);
+/* position of the sampling stream in draws; set it when batches are dealt to several GPUs */
+int kbbq_sampler_seek(kbbq_ctx* ctx, uint64_t slot_ordinal);
+/* recalibrateutils::subsample_kmers (recalibrateutils.cc:7-13) over one batch; advances the stream by the batch's slots */
+int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* b);
+/* thresholds[k+1] for pass 2 (kbbq.cc:313) */
+int kbbq_set_thresholds(kbbq_ctx* ctx, const int* thresholds);
+/* fprate -> phit -> thresholds from the sampled filter's own counter, as kbbq.cc:304-313; also installs them */
+int kbbq_compute_thresholds(kbbq_ctx* ctx, long double alpha, int* thresholds_out /* may be NULL */);
+/* recalibrateutils::find_trusted_kmers (recalibrateutils.cc:15-40) over one batch.  err_bits (host, may be NULL)
+ * receives CReadData::errors after infer_read_errors as bit i%32 of err_bits[word_off[r] + i/32]. */
+int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* b, uint32_t* err_bits);
+/* recalibrateutils::get_covariatedata (recalibrateutils.cc:42-89) over one batch: get_errors + consume_read.
+ * err_bits as above (CReadData::errors after get_errors). */
+int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* b, uint32_t* err_bits);
+/* --fixed mode (kbbq.cc:367-378): error flags supplied by the caller, then CCovariateData::consume_read */
+int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* err_bits);
+int kbbq_covariates_reset(kbbq_ctx* ctx);
+int kbbq_covariates_download(kbbq_ctx* ctx, uint64_t* rgc, uint64_t* qc, uint64_t* cyc, uint64_t* dic);
+/* device pointer + size in uint64 words of the four count tables laid out back to back (for a sum all-reduce) */
+void* kbbq_covariates_device(kbbq_ctx* ctx, uint64_t* n_words);
+/* CCovariateData::get_dqs (covariateutils.cc:204-230) on the context's tables; installs the lookup tables.
+ * Output pointers may be NULL. */
+int kbbq_fit_model(kbbq_ctx* ctx, int32_t* meanq, int32_t* rgdq, int32_t* qdq, int32_t* cydq, int32_t* didq);
+int kbbq_set_model(kbbq_ctx* ctx, const int32_t* meanq, const int32_t* rgdq, const int32_t* qdq, const int32_t* cydq,
+                   const int32_t* didq);
+/* recalibrateutils::recalibrate_and_write's compute half = CReadData::recalibrate (readutils.cc:572-595) over one batch.
+ * qual_out (host, may be NULL) has the layout of kbbq_batch.qual. */
+int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* b, uint8_t* qual_out);
+/* device pointer to the batch's recalibrated qualities (valid after kbbq_pass4_recalibrate) */
+void* kbbq_batch_device_newqual(kbbq_dbatch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,809 @@
+// kbbq_capi.cu -- implementation of include/kbbq_b200.h: contexts, device memory, kernel launches.
+// No CPU fallback lives here: every pass entry point launches the sm_100a kernels or fails with KBBQ_ECUDA.
+#include "../../include/kbbq_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kbbq_host.h"
+#include "kbbq_kernels.cuh"
+
+using namespace kbbq;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA,                          \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                                 \
+    } while (0)
+
+struct Filter {
+    bool exists = false;
+    host::BloomGeom geom{};
+    unsigned long long* d_words = nullptr;
+    unsigned long long* d_patterns = nullptr;
+    unsigned long long* d_inserted = nullptr;
+    BloomView view() const {
+        BloomView v;
+        v.words = d_words;
+        v.patterns = d_patterns;
+        v.inserted = d_inserted;
+        v.n_blocks = geom.n_blocks;
+        v.fastmod_m = geom.n_blocks > 1 ? (~0ull / geom.n_blocks) + 1 : 0;
+        v.salt0 = geom.salts[0];
+        v.salt1 = geom.salts[1];
+        return v;
+    }
+};
+
+}  // namespace
+
+struct kbbq_ctx {
+    int device = 0;
+    int k = 32;
+    int n_rg = 1;
+    int max_cycle = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint64_t launches = 0;
+    Filter filt[2];
+    // sampler
+    bool sampler_seeded = false;
+    uint64_t sampler_state0[4] = {0, 0, 0, 0};  // state right after Seed()
+    uint64_t sampler_pos = 0;
+    double alpha = 0;
+    unsigned long long* d_jump = nullptr;  // 26 matrices: 2^(10+b) steps
+    // thresholds
+    bool have_thresholds = false;
+    int* d_thresholds = nullptr;
+    // count tables (one allocation, four tables back to back)
+    unsigned long long* d_counts = nullptr;
+    size_t n_rgc = 0, n_qc = 0, n_cyc = 0, n_dic = 0;
+    // model lookup tables
+    bool have_model = false;
+    int16_t* d_base = nullptr;
+    int8_t* d_cy = nullptr;
+    int8_t* d_di = nullptr;
+    unsigned int* d_work = nullptr;
+
+    CountView counts() const {
+        CountView c;
+        c.rgc = d_counts;
+        c.qc = d_counts + n_rgc;
+        c.cyc = d_counts + n_rgc + n_qc;
+        c.dic = d_counts + n_rgc + n_qc + n_cyc;
+        c.max_cycle = max_cycle;
+        return c;
+    }
+    size_t n_counts() const { return n_rgc + n_qc + n_cyc + n_dic; }
+};
+
+struct kbbq_dbatch {
+    uint32_t n_reads = 0;
+    uint32_t max_len = 0;
+    uint64_t n_words = 0;
+    uint64_t n_slots = 0;
+    int k = 0;
+    unsigned long long* d_bases = nullptr;
+    uint32_t* d_nmask = nullptr;
+    uint8_t* d_qual = nullptr;
+    uint32_t* d_word_off = nullptr;
+    uint32_t* d_len = nullptr;
+    uint16_t* d_rg = nullptr;
+    uint8_t* d_second = nullptr;
+    unsigned long long* d_slot_off = nullptr;
+    uint32_t* d_sample_bits = nullptr;
+    uint32_t* d_err_bits = nullptr;
+    uint8_t* d_newqual = nullptr;
+    BatchView view() const {
+        BatchView v;
+        v.bases = d_bases;
+        v.nmask = d_nmask;
+        v.qual = d_qual;
+        v.word_off = d_word_off;
+        v.len = d_len;
+        v.rg = d_rg;
+        v.second = d_second;
+        v.slot_off = d_slot_off;
+        v.n_reads = n_reads;
+        return v;
+    }
+};
+
+namespace {
+
+int use(kbbq_ctx* ctx) {
+    if (!ctx) return fail(KBBQ_EINVAL, "null context");
+    CU(cudaSetDevice(ctx->device));
+    return KBBQ_OK;
+}
+
+void pass_begin(kbbq_ctx* ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
+void pass_end(kbbq_ctx* ctx) {
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    ctx->timed = true;
+}
+
+// one warp per read; enough blocks to fill every SM's 64 warp slots, no more than the reads need
+int read_grid(const kbbq_ctx* ctx, uint32_t n_reads) {
+    const long long need = ((long long)n_reads + KBBQ_WARPS_PER_BLOCK - 1) / KBBQ_WARPS_PER_BLOCK;
+    const long long full = (long long)ctx->sm_count * (64 / KBBQ_WARPS_PER_BLOCK);
+    return (int)std::max(1ll, std::min(need, full));
+}
+
+int check_launch(kbbq_ctx* ctx, const char* what) {
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return KBBQ_OK;
+}
+
+int filter_ok(kbbq_ctx* ctx, int which) {
+    if (which != KBBQ_FILTER_SAMPLED && which != KBBQ_FILTER_TRUSTED) return fail(KBBQ_EINVAL, "filter id must be 0 or 1");
+    if (!ctx->filt[which].exists) return fail(KBBQ_ESTATE, "filter has not been created");
+    return KBBQ_OK;
+}
+
+void geom_to_c(const host::BloomGeom& g, kbbq_bloom_geom* o) {
+    o->projected = g.projected; o->fpr = g.fpr; o->seed = g.seed; o->optimal_k = g.optimal_k;
+    o->optimal_table_size = g.optimal_table_size; o->random_seed = g.random_seed; o->table_bits = g.table_bits;
+    o->n_blocks = g.n_blocks; o->n_salts = g.n_salts;
+    std::memset(o->salts, 0, sizeof o->salts);
+    std::memcpy(o->salts, g.salts, sizeof(uint32_t) * g.n_salts);
+}
+void geom_from_c(const kbbq_bloom_geom* o, host::BloomGeom& g) {
+    g.projected = o->projected; g.fpr = o->fpr; g.seed = o->seed; g.optimal_k = o->optimal_k;
+    g.optimal_table_size = o->optimal_table_size; g.random_seed = o->random_seed; g.table_bits = o->table_bits;
+    g.n_blocks = o->n_blocks; g.n_salts = o->n_salts;
+    std::memcpy(g.salts, o->salts, sizeof g.salts);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* kbbq_last_error(void) { return g_err.c_str(); }
+
+int kbbq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ---- host-only helpers ---------------------------------------------------------------------------------------------
+int kbbq_bloom_geometry(uint64_t projected, double fpr, uint64_t seed, kbbq_bloom_geom* out) {
+    if (!out) return fail(KBBQ_EINVAL, "null output");
+    host::BloomGeom g;
+    if (!host::bloom_geometry(projected, fpr, seed, g))
+        return fail(KBBQ_EINVAL, "Error: Invalid bloom filter parameters. Adjust parameters and try again.");
+    geom_to_c(g, out);
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_patterns(const kbbq_bloom_geom* g, uint64_t* patterns) {
+    if (!g || !patterns) return fail(KBBQ_EINVAL, "null argument");
+    host::BloomGeom hg;
+    geom_from_c(g, hg);
+    host::bloom_patterns(hg, patterns);
+    return KBBQ_OK;
+}
+
+double kbbq_effective_fpp(uint64_t table_bits, uint64_t inserted, uint32_t n_salts) {
+    return host::effective_fpp(table_bits, inserted, n_salts);
+}
+
+int kbbq_thresholds_from_fpr(double fpr, long double alpha, int k, int* thresholds) {
+    if (!thresholds || k < 1 || k > KBBQ_MAX_K) return fail(KBBQ_EINVAL, "k must be in 1..32");
+    host::calculate_thresholds(k, host::calculate_phit(fpr, alpha), thresholds);
+    return KBBQ_OK;
+}
+
+int kbbq_rng_state(uint32_t seed, uint64_t skip, uint64_t state[4]) {
+    host::Xoshiro256ss r;
+    r.seed(seed);
+    host::rng_advance(r.s, skip);
+    std::memcpy(state, r.s, 32);
+    return KBBQ_OK;
+}
+
+int kbbq_fit_model_host(int n_rg, int max_cycle, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc,
+                        const uint64_t* dic, int32_t* meanq, int32_t* rgdq, int32_t* qdq, int32_t* cydq, int32_t* didq) {
+    if (n_rg < 1 || max_cycle < 1) return fail(KBBQ_EINVAL, "bad table extents");
+    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    host::fit_model(n_rg, max_cycle, rgc, qc, cyc, dic, meanq, rgdq, qdq, cydq, didq, nt);
+    return KBBQ_OK;
+}
+
+int kbbq_pack_size(uint64_t n, const uint64_t* off, uint64_t* n_words, uint32_t* max_len) {
+    uint64_t words = 0;
+    uint32_t ml = 0;
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint64_t len = off[r + 1] - off[r];
+        if (len > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
+        words += (len + 31) / 32;
+        ml = std::max<uint32_t>(ml, (uint32_t)len);
+    }
+    if (words > 0xFFFFFFFFull) return fail(KBBQ_ERANGE, "batch too large: split it");
+    *n_words = words;
+    if (max_len) *max_len = ml;
+    return KBBQ_OK;
+}
+
+int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint8_t* qual, uint64_t* bases,
+                    uint32_t* nmask, uint8_t* qual_out, uint32_t* word_off, uint32_t* len, int n_threads) {
+    uint64_t words = 0;
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint64_t l = off[r + 1] - off[r];
+        if (l > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
+        word_off[r] = (uint32_t)words;
+        len[r] = (uint32_t)l;
+        words += (l + 31) / 32;
+    }
+    word_off[n] = (uint32_t)words;
+    unsigned char code[256];
+    for (int c = 0; c < 256; ++c) code[c] = (unsigned char)host::nt4((unsigned char)c);
+    bool bad_q = false;
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t r = lo; r < hi; ++r) {
+            const char* s = seq + off[r];
+            const uint8_t* q = qual + off[r];
+            const uint32_t l = len[r], wo = word_off[r];
+            for (uint32_t w = 0; w * 32 < l; ++w) {
+                uint64_t bw = 0;
+                uint32_t nw = 0;
+                const uint32_t cnt = std::min<uint32_t>(32, l - w * 32);
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    const unsigned c = code[(unsigned char)s[w * 32 + i]];
+                    if (c < 4) bw |= (uint64_t)c << (2 * i);
+                    else nw |= 1u << i;
+                    const uint8_t qq = q[w * 32 + i];
+                    if (qq > KBBQ_MAXQ) bad_q = true;
+                    qual_out[(size_t)(wo + w) * 32 + i] = qq;
+                }
+                for (uint32_t i = cnt; i < 32; ++i) qual_out[(size_t)(wo + w) * 32 + i] = 0;
+                bases[wo + w] = bw;
+                nmask[wo + w] = nw;
+            }
+        }
+    };
+    if (n_threads <= 1 || n < 4096) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        const uint64_t per = (n + n_threads - 1) / n_threads;
+        for (int t = 0; t < n_threads; ++t) {
+            const uint64_t lo = std::min<uint64_t>(n, (uint64_t)t * per), hi = std::min<uint64_t>(n, lo + per);
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto& t : th) t.join();
+    }
+    if (bad_q) return fail(KBBQ_ERANGE, "quality above 93: outside the model's table range");
+    return KBBQ_OK;
+}
+
+// ---- context -------------------------------------------------------------------------------------------------------
+int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) {
+    if (!out) return fail(KBBQ_EINVAL, "null output");
+    if (k < 1 || k > KBBQ_MAX_K) return fail(KBBQ_EINVAL, "Error: k must be <= 32 and > 0.");
+    if (n_rg < 1 || n_rg > 65535) return fail(KBBQ_EINVAL, "n_rg out of range");
+    if (max_cycle < 1 || max_cycle > KBBQ_MAX_READ_LEN) return fail(KBBQ_EINVAL, "max_cycle out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(KBBQ_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(KBBQ_EINVAL, "no such device");
+    CU(cudaSetDevice(device));
+    kbbq_ctx* c = new (std::nothrow) kbbq_ctx();
+    if (!c) return fail(KBBQ_ENOMEM, "out of host memory");
+    c->device = device;
+    c->k = k;
+    c->n_rg = n_rg;
+    c->max_cycle = max_cycle;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    c->n_rgc = (size_t)n_rg * 2;
+    c->n_qc = (size_t)n_rg * KBBQ_NQ * 2;
+    c->n_cyc = (size_t)n_rg * KBBQ_NQ * 2 * max_cycle * 2;
+    c->n_dic = (size_t)n_rg * KBBQ_NQ * 16 * 2;
+    CU(cudaMalloc(&c->d_counts, c->n_counts() * 8));
+    CU(cudaMemsetAsync(c->d_counts, 0, c->n_counts() * 8, c->stream));
+    CU(cudaMalloc(&c->d_thresholds, sizeof(int) * (KBBQ_MAX_K + 1)));
+    CU(cudaMalloc(&c->d_base, sizeof(int16_t) * (size_t)n_rg * KBBQ_NQ));
+    CU(cudaMalloc(&c->d_cy, (size_t)n_rg * KBBQ_NQ * 2 * max_cycle));
+    CU(cudaMalloc(&c->d_di, (size_t)n_rg * KBBQ_NQ * 16));
+    CU(cudaMalloc(&c->d_work, sizeof(unsigned int)));
+    *out = c;
+    return KBBQ_OK;
+}
+
+void kbbq_ctx_destroy(kbbq_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& f : c->filt) {
+        cudaFree(f.d_words);
+        cudaFree(f.d_patterns);
+        cudaFree(f.d_inserted);
+    }
+    cudaFree(c->d_jump);
+    cudaFree(c->d_thresholds);
+    cudaFree(c->d_counts);
+    cudaFree(c->d_base);
+    cudaFree(c->d_cy);
+    cudaFree(c->d_di);
+    cudaFree(c->d_work);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int kbbq_sync(kbbq_ctx* ctx) {
+    if (int rc = use(ctx)) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
+void* kbbq_stream(kbbq_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int kbbq_last_pass_ms(kbbq_ctx* ctx, float* ms) {
+    if (int rc = use(ctx)) return rc;
+    if (!ctx->timed) return fail(KBBQ_ESTATE, "no pass has run");
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return KBBQ_OK;
+}
+
+uint64_t kbbq_launch_count(kbbq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- filters -------------------------------------------------------------------------------------------------------
+int kbbq_bloom_create(kbbq_ctx* ctx, int which, uint64_t projected, double fpr, uint64_t seed) {
+    if (int rc = use(ctx)) return rc;
+    if (which != 0 && which != 1) return fail(KBBQ_EINVAL, "filter id must be 0 or 1");
+    host::BloomGeom g;
+    if (!host::bloom_geometry(projected, fpr, seed, g))
+        return fail(KBBQ_EINVAL, "Error: Invalid bloom filter parameters. Adjust parameters and try again.");
+    Filter& f = ctx->filt[which];
+    if (f.exists) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(f.d_words);
+        cudaFree(f.d_patterns);
+        cudaFree(f.d_inserted);
+        f = Filter();
+    }
+    f.geom = g;
+    CU(cudaMalloc(&f.d_words, g.table_bits / 8));
+    CU(cudaMalloc(&f.d_patterns, (size_t)KBBQ_NUM_PATTERNS * 64));
+    CU(cudaMalloc(&f.d_inserted, 8));
+    CU(cudaMemsetAsync(f.d_words, 0, g.table_bits / 8, ctx->stream));
+    CU(cudaMemsetAsync(f.d_inserted, 0, 8, ctx->stream));
+    std::vector<uint64_t> pat((size_t)KBBQ_NUM_PATTERNS * 8);
+    host::bloom_patterns(g, pat.data());
+    CU(cudaMemcpyAsync(f.d_patterns, pat.data(), pat.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    f.exists = true;
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_info(kbbq_ctx* ctx, int which, kbbq_bloom_geom* out) {
+    if (!ctx || !out) return fail(KBBQ_EINVAL, "null argument");
+    if (int rc = filter_ok(ctx, which)) return rc;
+    geom_to_c(ctx->filt[which].geom, out);
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_clear(kbbq_ctx* ctx, int which) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    CU(cudaMemsetAsync(f.d_words, 0, f.geom.table_bits / 8, ctx->stream));
+    CU(cudaMemsetAsync(f.d_inserted, 0, 8, ctx->stream));
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_inserted(kbbq_ctx* ctx, int which, uint64_t* inserted) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    CU(cudaMemcpyAsync(inserted, ctx->filt[which].d_inserted, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_download(kbbq_ctx* ctx, int which, uint64_t* words, uint64_t* inserted) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    if (words) CU(cudaMemcpyAsync(words, f.d_words, f.geom.table_bits / 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (inserted) CU(cudaMemcpyAsync(inserted, f.d_inserted, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_upload(kbbq_ctx* ctx, int which, const uint64_t* words, uint64_t inserted) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    if (words) CU(cudaMemcpyAsync(f.d_words, words, f.geom.table_bits / 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(f.d_inserted, &inserted, 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_insert_keys(kbbq_ctx* ctx, int which, const uint64_t* keys, uint64_t n) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    if (n == 0) return KBBQ_OK;
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, n * 8));
+    CU(cudaMemcpyAsync(d, keys, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    bloom_insert_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->filt[which].view(), d, n);
+    int rc = check_launch(ctx, "bloom_insert_keys_kernel");
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    return rc;
+}
+
+int kbbq_bloom_query_keys(kbbq_ctx* ctx, int which, const uint64_t* keys, uint64_t n, uint8_t* hits) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    if (n == 0) return KBBQ_OK;
+    unsigned long long* d = nullptr;
+    uint8_t* dh = nullptr;
+    CU(cudaMalloc(&d, n * 8));
+    CU(cudaMalloc(&dh, n));
+    CU(cudaMemcpyAsync(d, keys, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    bloom_query_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->filt[which].view(), d, n, dh);
+    int rc = check_launch(ctx, "bloom_query_keys_kernel");
+    if (rc == KBBQ_OK) {
+        cudaMemcpyAsync(hits, dh, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(KBBQ_ECUDA, "query sync failed");
+    }
+    cudaFree(d);
+    cudaFree(dh);
+    return rc;
+}
+
+int kbbq_bloom_fprate(kbbq_ctx* ctx, int which, double* fpr) {
+    uint64_t ins = 0;
+    if (int rc = kbbq_bloom_inserted(ctx, which, &ins)) return rc;
+    const host::BloomGeom& g = ctx->filt[which].geom;
+    *fpr = host::effective_fpp(g.table_bits, ins, g.n_salts);
+    return KBBQ_OK;
+}
+
+void* kbbq_bloom_device_words(kbbq_ctx* ctx, int which) {
+    return (ctx && (which == 0 || which == 1) && ctx->filt[which].exists) ? ctx->filt[which].d_words : nullptr;
+}
+void* kbbq_bloom_device_counter(kbbq_ctx* ctx, int which) {
+    return (ctx && (which == 0 || which == 1) && ctx->filt[which].exists) ? ctx->filt[which].d_inserted : nullptr;
+}
+
+int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other, uint64_t first_word, uint64_t n_words) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    if ((first_word & 1) || (n_words & 1) || first_word + n_words > f.geom.table_bits / 64)
+        return fail(KBBQ_EINVAL, "word range must be even-aligned and inside the table");
+    if (n_words == 0) return KBBQ_OK;
+    const unsigned long long n2 = n_words / 2;
+    const int grid = (int)std::min<unsigned long long>((n2 + 255) / 256, (unsigned long long)ctx->sm_count * 8);
+    or_words_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<ulonglong2*>(f.d_words + first_word),
+                                                   reinterpret_cast<const ulonglong2*>((const unsigned long long*)other + first_word), n2);
+    return check_launch(ctx, "or_words_kernel");
+}
+
+// ---- batches -------------------------------------------------------------------------------------------------------
+void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
+    if (!b) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(b->d_bases); cudaFree(b->d_nmask); cudaFree(b->d_qual); cudaFree(b->d_word_off); cudaFree(b->d_len);
+    cudaFree(b->d_rg); cudaFree(b->d_second); cudaFree(b->d_slot_off); cudaFree(b->d_sample_bits);
+    cudaFree(b->d_err_bits); cudaFree(b->d_newqual);
+    delete b;
+}
+
+int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) {
+    if (int rc = use(ctx)) return rc;
+    if (!h || !out) return fail(KBBQ_EINVAL, "null argument");
+    if (h->max_len > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
+    if ((int)h->max_len > ctx->max_cycle) return fail(KBBQ_ERANGE, "read longer than the context's max_cycle");
+    const uint32_t n = h->n_reads;
+    std::vector<unsigned long long> slot_off((size_t)n + 1);
+    unsigned long long slots = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+        slot_off[r] = slots;
+        const uint32_t l = h->len[r];
+        if (l > h->max_len) return fail(KBBQ_ERANGE, "len[r] exceeds max_len");
+        if (h->rg && h->rg[r] >= ctx->n_rg) return fail(KBBQ_ERANGE, "read group id >= n_rg");
+        if ((int)l >= ctx->k) slots += l - ctx->k + 1;
+    }
+    slot_off[n] = slots;
+    kbbq_dbatch* b = new (std::nothrow) kbbq_dbatch();
+    if (!b) return fail(KBBQ_ENOMEM, "out of host memory");
+    b->n_reads = n; b->max_len = h->max_len; b->n_words = h->n_words; b->n_slots = slots; b->k = ctx->k;
+    const size_t nw = std::max<uint64_t>(h->n_words, 1);
+#define UP(dst, src, bytes)                                                                   \
+    do {                                                                                      \
+        cudaError_t e1 = cudaMalloc(&(dst), std::max<size_t>((bytes), 16));                   \
+        if (e1 == cudaSuccess && (src) && (bytes))                                            \
+            e1 = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream); \
+        else if (e1 == cudaSuccess)                                                           \
+            e1 = cudaMemsetAsync((dst), 0, std::max<size_t>((bytes), 16), ctx->stream);       \
+        if (e1 != cudaSuccess) {                                                              \
+            kbbq_batch_free(ctx, b);                                                          \
+            return fail(e1 == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA,           \
+                        std::string("batch upload: ") + cudaGetErrorString(e1));              \
+        }                                                                                     \
+    } while (0)
+    // one padding word after the last read keeps two-word k-mer extraction in bounds
+    UP(b->d_bases, (const void*)nullptr, (nw + 1) * 8);
+    UP(b->d_nmask, (const void*)nullptr, (nw + 1) * 4);
+    if (h->n_words) {
+        CU(cudaMemcpyAsync(b->d_bases, h->bases, h->n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(b->d_nmask, h->nmask, h->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    UP(b->d_qual, h->qual, (size_t)h->n_words * 32);
+    UP(b->d_word_off, h->word_off, ((size_t)n + 1) * 4);
+    UP(b->d_len, h->len, (size_t)n * 4);
+    UP(b->d_rg, h->rg, (size_t)n * 2);
+    UP(b->d_second, h->second, (size_t)n);
+    UP(b->d_slot_off, slot_off.data(), ((size_t)n + 1) * 8);
+#undef UP
+    CU(cudaStreamSynchronize(ctx->stream));  // slot_off is a stack-owned vector
+    *out = b;
+    return KBBQ_OK;
+}
+
+uint64_t kbbq_batch_slots(const kbbq_dbatch* b) { return b ? b->n_slots : 0; }
+void* kbbq_batch_device_newqual(kbbq_dbatch* b) { return b ? b->d_newqual : nullptr; }
+
+// ---- pass 1 --------------------------------------------------------------------------------------------------------
+int kbbq_sampler_seed(kbbq_ctx* ctx, uint32_t seed, double alpha) {
+    if (int rc = use(ctx)) return rc;
+    host::Xoshiro256ss r;
+    r.seed(seed);
+    std::memcpy(ctx->sampler_state0, r.s, 32);
+    ctx->sampler_pos = 0;
+    ctx->alpha = alpha;
+    ctx->sampler_seeded = true;
+    if (!ctx->d_jump) {
+        const host::JumpTables& jt = host::jump_tables();
+        CU(cudaMalloc(&ctx->d_jump, (size_t)26 * 1024 * 8));
+        CU(cudaMemcpyAsync(ctx->d_jump, jt.matrix(10), (size_t)26 * 1024 * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return KBBQ_OK;
+}
+
+int kbbq_sampler_seek(kbbq_ctx* ctx, uint64_t slot_ordinal) {
+    if (!ctx || !ctx->sampler_seeded) return fail(KBBQ_ESTATE, "sampler not seeded");
+    ctx->sampler_pos = slot_ordinal;
+    return KBBQ_OK;
+}
+
+int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
+    if (int rc = use(ctx)) return rc;
+    if (!ctx->sampler_seeded) return fail(KBBQ_ESTATE, "sampler not seeded");
+    if (int rc = filter_ok(ctx, KBBQ_FILTER_SAMPLED)) return rc;
+    kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
+    if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
+    pass_begin(ctx);
+    if (b->n_slots) {
+        const uint64_t chunks = (b->n_slots + 1023) / 1024;
+        if (!b->d_sample_bits) CU(cudaMalloc(&b->d_sample_bits, chunks * 32 * 4));
+        uint64_t st[4];
+        std::memcpy(st, ctx->sampler_state0, 32);
+        host::rng_advance(st, ctx->sampler_pos);
+        rng_sample_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(st[0], st[1], st[2], st[3], ctx->d_jump,
+                                                                                     b->n_slots, ctx->alpha, b->d_sample_bits);
+        if (int rc = check_launch(ctx, "rng_sample_kernel")) return rc;
+        pass1_insert_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+            b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);
+        if (int rc = check_launch(ctx, "pass1_insert_kernel")) return rc;
+    }
+    pass_end(ctx);
+    ctx->sampler_pos += b->n_slots;
+    return KBBQ_OK;
+}
+
+// ---- pass 2 --------------------------------------------------------------------------------------------------------
+int kbbq_set_thresholds(kbbq_ctx* ctx, const int* thresholds) {
+    if (int rc = use(ctx)) return rc;
+    if (!thresholds) return fail(KBBQ_EINVAL, "null thresholds");
+    int tmp[KBBQ_MAX_K + 1] = {0};
+    std::memcpy(tmp, thresholds, sizeof(int) * (ctx->k + 1));
+    CU(cudaMemcpyAsync(ctx->d_thresholds, tmp, sizeof tmp, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_thresholds = true;
+    return KBBQ_OK;
+}
+
+int kbbq_compute_thresholds(kbbq_ctx* ctx, long double alpha, int* thresholds_out) {
+    double fpr = 0;
+    if (int rc = kbbq_bloom_fprate(ctx, KBBQ_FILTER_SAMPLED, &fpr)) return rc;
+    int th[KBBQ_MAX_K + 1] = {0};
+    host::calculate_thresholds(ctx->k, host::calculate_phit(fpr, alpha), th);
+    if (thresholds_out) std::memcpy(thresholds_out, th, sizeof(int) * (ctx->k + 1));
+    return kbbq_set_thresholds(ctx, th);
+}
+
+static int fetch_bits(kbbq_ctx* ctx, kbbq_dbatch* b, uint32_t* host_bits) {
+    if (!host_bits || !b->n_words) return KBBQ_OK;
+    CU(cudaMemcpyAsync(host_bits, b->d_err_bits, b->n_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
+int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bits) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, KBBQ_FILTER_SAMPLED)) return rc;
+    if (int rc = filter_ok(ctx, KBBQ_FILTER_TRUSTED)) return rc;
+    if (!ctx->have_thresholds) return fail(KBBQ_ESTATE, "thresholds not set");
+    kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
+    if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
+    if (err_bits && !b->d_err_bits) {
+        CU(cudaMalloc(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4));
+    }
+    if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+    pass_begin(ctx);
+    if (b->n_reads) {
+        pass2_trusted_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+            b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, ctx->d_thresholds,
+            err_bits ? b->d_err_bits : nullptr);
+        if (int rc = check_launch(ctx, "pass2_trusted_kernel")) return rc;
+    }
+    pass_end(ctx);
+    return fetch_bits(ctx, b, err_bits);
+}
+
+// ---- pass 3 --------------------------------------------------------------------------------------------------------
+int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bits) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, KBBQ_FILTER_TRUSTED)) return rc;
+    kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
+    if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
+    if (err_bits && !b->d_err_bits) CU(cudaMalloc(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4));
+    if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+    pass_begin(ctx);
+    if (b->n_reads) {
+        CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+        pass3_errors_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+            b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->counts(), ctx->k, err_bits ? b->d_err_bits : nullptr, 1,
+            ctx->d_work);
+        if (int rc = check_launch(ctx, "pass3_errors_kernel")) return rc;
+    }
+    pass_end(ctx);
+    return fetch_bits(ctx, b, err_bits);
+}
+
+int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* err_bits) {
+    if (int rc = use(ctx)) return rc;
+    kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
+    if (!b || !err_bits) return fail(KBBQ_EINVAL, "null argument");
+    if (!b->d_err_bits) CU(cudaMalloc(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4));
+    if (b->n_words) CU(cudaMemcpyAsync(b->d_err_bits, err_bits, b->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    pass_begin(ctx);
+    if (b->n_reads) {
+        consume_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), ctx->counts(),
+                                                                                                  b->d_err_bits);
+        if (int rc = check_launch(ctx, "consume_kernel")) return rc;
+    }
+    pass_end(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));  // err_bits is the caller's buffer
+    return KBBQ_OK;
+}
+
+int kbbq_covariates_reset(kbbq_ctx* ctx) {
+    if (int rc = use(ctx)) return rc;
+    CU(cudaMemsetAsync(ctx->d_counts, 0, ctx->n_counts() * 8, ctx->stream));
+    return KBBQ_OK;
+}
+
+int kbbq_covariates_download(kbbq_ctx* ctx, uint64_t* rgc, uint64_t* qc, uint64_t* cyc, uint64_t* dic) {
+    if (int rc = use(ctx)) return rc;
+    const CountView c = ctx->counts();
+    if (rgc) CU(cudaMemcpyAsync(rgc, c.rgc, ctx->n_rgc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (qc) CU(cudaMemcpyAsync(qc, c.qc, ctx->n_qc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cyc) CU(cudaMemcpyAsync(cyc, c.cyc, ctx->n_cyc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dic) CU(cudaMemcpyAsync(dic, c.dic, ctx->n_dic * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
+void* kbbq_covariates_device(kbbq_ctx* ctx, uint64_t* n_words) {
+    if (!ctx) return nullptr;
+    if (n_words) *n_words = ctx->n_counts();
+    return ctx->d_counts;
+}
+
+// ---- model ----------------------------------------------------------------------------------------------------------
+int kbbq_set_model(kbbq_ctx* ctx, const int32_t* meanq, const int32_t* rgdq, const int32_t* qdq, const int32_t* cydq,
+                   const int32_t* didq) {
+    if (int rc = use(ctx)) return rc;
+    if (!meanq || !rgdq || !qdq || !cydq || !didq) return fail(KBBQ_EINVAL, "null model table");
+    const int R = ctx->n_rg, C = ctx->max_cycle;
+    // fold dq_t into the three tables CReadData::recalibrate walks (readutils.cc:579-587)
+    std::vector<int16_t> base((size_t)R * KBBQ_NQ);
+    std::vector<int8_t> cy((size_t)R * KBBQ_NQ * 2 * C), di((size_t)R * KBBQ_NQ * 16);
+    for (int r = 0; r < R; ++r)
+        for (int q = 0; q < KBBQ_NQ; ++q) base[(size_t)r * KBBQ_NQ + q] = (int16_t)(meanq[r] + rgdq[r] + qdq[(size_t)r * KBBQ_NQ + q]);
+    for (size_t i = 0; i < cy.size(); ++i) cy[i] = (int8_t)cydq[i];  // |dq| <= 93
+    for (size_t i = 0; i < di.size(); ++i) di[i] = (int8_t)didq[i];
+    CU(cudaMemcpyAsync(ctx->d_base, base.data(), base.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_cy, cy.data(), cy.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_di, di.data(), di.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_model = true;
+    return KBBQ_OK;
+}
+
+int kbbq_fit_model(kbbq_ctx* ctx, int32_t* meanq, int32_t* rgdq, int32_t* qdq, int32_t* cydq, int32_t* didq) {
+    if (int rc = use(ctx)) return rc;
+    const int R = ctx->n_rg, C = ctx->max_cycle;
+    std::vector<uint64_t> counts(ctx->n_counts());
+    CU(cudaMemcpyAsync(counts.data(), ctx->d_counts, counts.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> m(R, 0), g(R, 0), q((size_t)R * KBBQ_NQ, 0), cy((size_t)R * KBBQ_NQ * 2 * C, 0), di((size_t)R * KBBQ_NQ * 16, 0);
+    const uint64_t* rgc = counts.data();
+    const uint64_t* qc = rgc + ctx->n_rgc;
+    const uint64_t* cyc = qc + ctx->n_qc;
+    const uint64_t* dic = cyc + ctx->n_cyc;
+    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    host::fit_model(R, C, rgc, qc, cyc, dic, m.data(), g.data(), q.data(), cy.data(), di.data(), nt);
+    if (meanq) std::memcpy(meanq, m.data(), m.size() * 4);
+    if (rgdq) std::memcpy(rgdq, g.data(), g.size() * 4);
+    if (qdq) std::memcpy(qdq, q.data(), q.size() * 4);
+    if (cydq) std::memcpy(cydq, cy.data(), cy.size() * 4);
+    if (didq) std::memcpy(didq, di.data(), di.size() * 4);
+    return kbbq_set_model(ctx, m.data(), g.data(), q.data(), cy.data(), di.data());
+}
+
+// ---- pass 4 --------------------------------------------------------------------------------------------------------
+int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_out) {
+    if (int rc = use(ctx)) return rc;
+    if (!ctx->have_model) return fail(KBBQ_ESTATE, "model not set");
+    kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
+    if (!b) return fail(KBBQ_EINVAL, "null batch");
+    if (!b->d_newqual) {
+        CU(cudaMalloc(&b->d_newqual, std::max<size_t>((size_t)b->n_words * 32, 16)));
+        CU(cudaMemsetAsync(b->d_newqual, 0, std::max<size_t>((size_t)b->n_words * 32, 16), ctx->stream));
+    }
+    pass_begin(ctx);
+    if (b->n_reads) {
+        ModelView mv{ctx->d_base, ctx->d_cy, ctx->d_di, ctx->max_cycle};
+        pass4_apply_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), mv, b->d_newqual);
+        if (int rc = check_launch(ctx, "pass4_apply_kernel")) return rc;
+    }
+    pass_end(ctx);
+    if (qual_out && b->n_words) {
+        CU(cudaMemcpyAsync(qual_out, b->d_newqual, (size_t)b->n_words * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return KBBQ_OK;
+}
+
+}  // extern "C"
