@@ -1,0 +1,124 @@
+"""Merging the per-GPU partial results of a sharded run.
+
+One process per GPU; `torch.distributed` is the plumbing.  The path has exactly three exchange steps:
+  after pass 1 and pass 2 -- bitwise OR of the Bloom bit arrays and SUM of the insert counters,
+  after pass 3          -- SUM of the covariate count tables.
+NCCL has no bitwise-OR reduction, so the OR is done by this repo's own kernel (`kbbq_bloom_or_from`,
+or_words_kernel) over the gathered partial arrays; the sums are plain all-reduces on int64 views.
+
+`Comm` only needs a tensor view of the state to merge, so the same code runs over NCCL on device memory (product)
+and over gloo on host memory (the world_size-2 CPU tests, where the oracle port plays the compute engine).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import api
+
+
+class _DevMem:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def device_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
+    return torch.as_tensor(_DevMem(ptr, nbytes), device=f"cuda:{device}")
+
+
+class Comm:
+    def __init__(self, rank: int, world: int):
+        self.rank, self.world = rank, world
+
+    # ---- scalars -------------------------------------------------------------------------------------------------
+    def exclusive_prefix(self, x: int, device=None) -> int:
+        """sum of x over the ranks below this one: the ordinal of this rank's first k-mer slot."""
+        t = torch.tensor([x], dtype=torch.int64, device=device if device is not None else "cpu")
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return int(sum(int(o.item()) for o in out[: self.rank]))
+
+    # ---- generic tensor merges (either backend) ---------------------------------------------------------------------
+    def or_reduce_(self, words: torch.Tensor, or_into=None) -> None:
+        """words |= every other rank's words.  `or_into(dst_tensor, src_tensor)` performs dst |= src."""
+        if self.world == 1:
+            return
+        gathered = torch.empty((self.world,) + tuple(words.shape), dtype=words.dtype, device=words.device)
+        dist.all_gather_into_tensor(gathered, words.contiguous())
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            if or_into is None:
+                words.bitwise_or_(gathered[r])
+            else:
+                or_into(words, gathered[r])
+
+    def sum_reduce_(self, t: torch.Tensor) -> None:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    # ---- the three exchange steps on a GPU context --------------------------------------------------------------------
+    def merge_filter(self, ctx: api.Context, which: int) -> None:
+        if self.world == 1:
+            return
+        g = ctx.bloom_info(which)
+        nbytes = g.table_bits // 8
+        ctx.sync()  # the library works on its own stream
+        words = device_tensor(ctx.bloom_device_words(which), nbytes, ctx.device).view(torch.int64)
+        counter = device_tensor(ctx.bloom_device_counter(which), 8, ctx.device).view(torch.int64)
+
+        def or_kernel(dst, src):
+            torch.cuda.current_stream().synchronize()
+            ctx.bloom_or_from(which, src.data_ptr(), 0, g.table_bits // 64)
+            ctx.sync()
+
+        self.or_reduce_(words, or_kernel)
+        self.sum_reduce_(counter)
+        torch.cuda.current_stream().synchronize()
+
+    def merge_counts(self, ctx: api.Context) -> None:
+        if self.world == 1:
+            return
+        ptr, n = ctx.covariates_device()
+        ctx.sync()
+        t = device_tensor(ptr, n * 8, ctx.device).view(torch.int64)
+        self.sum_reduce_(t)
+        torch.cuda.current_stream().synchronize()
+
+    def exclusive_prefix_gpu(self, x: int, device: int) -> int:
+        return self.exclusive_prefix(x, device=f"cuda:{device}")
+
+
+class GpuComm(Comm):
+    """Comm whose scalar exchanges also go through NCCL (tensors must live on the rank's GPU)."""
+
+    def __init__(self, rank: int, world: int, device: int):
+        super().__init__(rank, world)
+        self.device = device
+
+    def exclusive_prefix(self, x: int, device=None) -> int:
+        return super().exclusive_prefix(x, device=f"cuda:{self.device}")
+
+    def max_float(self, v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{self.device}")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_int(self, v: int) -> int:
+        t = torch.tensor([v], dtype=torch.int64, device=f"cuda:{self.device}")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(device_ids=[self.device])
+
+
+def shard_bounds(n_reads: int, world: int) -> np.ndarray:
+    """contiguous shards of reads; any assignment gives identical results, contiguous keeps file order per rank"""
+    return np.linspace(0, n_reads, world + 1).astype(np.int64)

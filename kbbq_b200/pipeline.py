@@ -72,7 +72,7 @@ class Recalibrator:
         self.ctx.covariates_reset()
 
     # ---- the passes ----------------------------------------------------------------------------------------------
-    def run(self, fetch_quals: bool = False, want_errors: bool = False) -> RunStats:
+    def run(self, fetch_quals: bool = False, want_errors: bool = False, qual_bufs=None) -> RunStats:
         st = RunStats()
         ctx, comm = self.ctx, self.comm
         launches0 = ctx.launches
@@ -117,7 +117,8 @@ class Recalibrator:
         ctx.fit_model_quiet()
         st.host_ms["fit"] = (time.perf_counter() - t0) * 1e3
         # pass 4
-        quals = timed_pass("pass4", lambda b: ctx.pass4(b, fetch=fetch_quals))
+        bufs = iter(qual_bufs) if qual_bufs is not None else None
+        quals = timed_pass("pass4", lambda b: ctx.pass4(b, out=next(bufs) if bufs is not None else None, fetch=fetch_quals))
         ctx.sync()
         st.launches = ctx.launches - launches0
         self.last_errors2, self.last_errors3, self.last_quals = e2, e3, quals
