@@ -167,6 +167,22 @@ KBBQ_HD int next_zero(const uint32_t* m, int n, int from) {
     }
     return n;
 }
+// largest index <= from whose bit is clear, or -1 when there is none (from >= 0)
+KBBQ_HD int prev_zero(const uint32_t* m, int from) {
+    while (from >= 0) {
+        const int o = from & 31;
+        const uint32_t x = ~m[from >> 5] << (31 - o);  // bit `from` moved to the top
+        if (x) {
+#if defined(__CUDA_ARCH__)
+            return from - __clz((int)x);
+#else
+            return from - __builtin_clz(x);
+#endif
+        }
+        from = (from & ~31) - 1;
+    }
+    return -1;
+}
 // number of set bits in [lo, hi)
 KBBQ_HD int count_range(const uint32_t* m, int lo, int hi) {
     int c = 0;

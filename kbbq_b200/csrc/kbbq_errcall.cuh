@@ -2,19 +2,40 @@
 //
 // This is CReadData::get_errors (readutils.cc:238-570) and its helpers (bloom.cc:83-305, readutils.cc:195-235)
 // re-designed for a warp: the read lives in shared memory as 2-bit words, every question the reference asks of the
-// filter one k-mer at a time is asked for up to 32 k-mers at once through `Q::query` (one lane per k-mer, one
-// ballot), and all the bookkeeping (anchors, streaks, windows, error flags) is bit-mask arithmetic that every lane
-// carries out identically, so the control flow is warp-uniform and the only shared-memory writes are idempotent.
+// filter one k-mer at a time is asked for up to 32 k-mers at once (one lane per k-mer, one ballot), and all the
+// bookkeeping (anchors, streaks, windows, error flags) is bit-mask arithmetic that every lane carries out identically,
+// so the control flow is warp-uniform and the only shared-memory writes are idempotent.
 //
-// `Q` supplies   template<class F> uint32_t query(int count, F f)
-// which evaluates f(t, key) -> bool valid for t in [0,count), count <= 32, and returns the mask of t for which the
-// k-mer is valid AND present in the trusted filter (Bloom::query, bloom.hh:398).  On the device that is one lane per
-// t and a __ballot_sync; tests/emu provides a serial stand-in so the logic can be exercised without a GPU.
+// `Q` supplies the two warp-wide primitives:
+//   template<class F> uint32_t query(int count, F f)
+//       evaluates f(t, key) -> bool valid for t in [0,count), count <= 32, and returns the mask of t for which the
+//       k-mer is valid AND present in the trusted filter (Bloom::query, bloom.hh:398);
+//   template<class F> uint32_t map32(F f)
+//       returns the mask of t in [0,32) for which f(t) is true.
+// On the device those are one lane per t and a __ballot_sync; tests/emu provides serial stand-ins so the logic can be
+// exercised without a GPU.
+//
+// Probe economy (none of it changes a result):
+//   * the initial scan's flags are kept (T): a k-mer the running call has not modified is never queried again --
+//     the reference re-queries the whole original read for its "adjust" test (readutils.cc:435-454) and walks the
+//     rest of the read for every candidate base (bloom.cc:147-172);
+//   * candidate bases are pre-tested on their first k-mer in ONE query; only survivors get the other k-mers that
+//     contain the repaired base queried.
+//
+// Code size matters here (the kernel runs from the instruction cache or not at all): the one heavy routine,
+// kmers_mask, is out of line, the two sides of the anchor share one loop, and the three get_errors invocations of a
+// read (whole read, bad prefix, bad suffix) share one call site.
 //
 // Conventions: positions are int; NPOS (-1) stands for std::string::npos where the reference uses it as a flag.
 // Deliberate reproduction of reference behaviour is marked "ref quirk".
 #pragma once
 #include "kbbq_core.cuh"
+
+#if defined(__CUDACC__)
+#define KBBQ_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define KBBQ_HD_NOINLINE __attribute__((noinline))
+#endif
 
 namespace kbbq {
 
@@ -32,6 +53,7 @@ struct ErrScratch {
     uint32_t T_orig[KBBQ_MAXW + 1]; // trusted flag of every k-mer of original_seq (bit j = k-mer starting at j)
     uint32_t T_cur[KBBQ_MAXW + 1];  // same for seq after correct_one, when that ran
     uint32_t E[KBBQ_MAXW + 1];      // this->errors of the top-level read
+    uint32_t QL[KBBQ_MAXW + 1];     // bit i: qual[i] <= 6 (the overcorrection half weight), top-level coordinates
 };
 
 struct ErrResult {
@@ -43,21 +65,27 @@ template <class Q>
 struct ErrCaller {
     Q& q;
     const int k;
-    const uint8_t* qual;  // qualities of the top-level read
+    const uint8_t* qual;  // qualities of the top-level read (only correct_one's tie-break reads them)
     ErrScratch& sc;
+    const uint32_t* T = nullptr;  // cached trusted flags of the running call's sequence (see cached_run)
+    bool T_mirrored = false;
     KBBQ_HD ErrCaller(Q& q_, int k_, const uint8_t* qual_, ErrScratch& sc_) : q(q_), k(k_), qual(qual_), sc(sc_) {}
 
-    // mask of trusted k-mers among those starting at j0 .. j0+count-1 (count <= 32) of s with base p replaced by c
-    KBBQ_HD uint32_t trusted_mask(const SeqRef& s, int j0, int count, int p, int c) {
+    // THE probe routine.  Lane t asks about the k-mer of s starting at j0 + t*stride with base p replaced:
+    //   stride == 1: consecutive k-mers, replacement base c (c < 0: no replacement);
+    //   stride == 0: one k-mer, lane t tries base (cpack >> 2t) & 3  -- the candidate pre-test.
+    KBBQ_HD_NOINLINE uint32_t kmers_mask(const SeqRef& s, int j0, int stride, int count, int p, int c, uint32_t cpack) {
         const int kk = k;
-        return q.query(count, [&](int t, uint64_t& key) { return kmer_key(s, j0 + t, kk, p, c, key); });
+        return q.query(count, [&](int t, uint64_t& key) {
+            return kmer_key(s, j0 + t * stride, kk, p, stride ? c : (int)((cpack >> (2 * t)) & 3u), key);
+        });
     }
     // number of consecutive trusted k-mers starting at j0, looking no further than j1 (exclusive)
     KBBQ_HD int trusted_run(const SeqRef& s, int j0, int j1, int p, int c) {
         int j = j0;
         while (j < j1) {
             const int count = j1 - j < 32 ? j1 - j : 32;
-            const uint32_t m = trusted_mask(s, j, count, p, c);
+            const uint32_t m = kmers_mask(s, j, 1, count, p, c, 0);
             const uint32_t full = count < 32 ? ((1u << count) - 1) : ~0u;
             if (m != full) return j - j0 + ctz32(~m);
             j += count;
@@ -65,28 +93,48 @@ struct ErrCaller {
         return j1 - j0;
     }
     // fill T[0 .. nk) with the trusted flag of every k-mer of s
-    KBBQ_HD void scan(const SeqRef& s, uint32_t* T) {
+    KBBQ_HD void scan(const SeqRef& s, uint32_t* Tout) {
         const int nk = s.len - k + 1;
-        for (int j = 0; j < nk; j += 32) {
-            const int count = nk - j < 32 ? nk - j : 32;
-            T[j >> 5] = trusted_mask(s, j, count, 0, -1);
-        }
+        for (int j = 0; j < nk; j += 32) Tout[j >> 5] = kmers_mask(s, j, 1, nk - j < 32 ? nk - j : 32, 0, -1, 0);
     }
 
     // bloom::find_longest_trusted_seq (bloom.cc:96-128) on the k-mer flags: first longest streak wins
-    KBBQ_HD void longest_trusted(const uint32_t* T, int len, int& a0, int& a1) {
+    KBBQ_HD void longest_trusted(const uint32_t* Tm, int len, int& a0, int& a1) {
         const int nk = len - k + 1;
         int best = 0, bs = 0, be = 0, pos = 0;
         while (true) {
-            const int s = next_one(T, nk, pos);
+            const int s = next_one(Tm, nk, pos);
             if (s >= nk) break;
-            const int e = next_zero(T, nk, s);
+            const int e = next_zero(Tm, nk, s);
             if (e - s > best) { best = e - s; bs = s; be = e; }
             pos = e;
         }
         if (best == 0) { a0 = KBBQ_NPOS; a1 = KBBQ_NPOS; return; }
         a0 = bs;
         a1 = be == nk ? KBBQ_NPOS : be - 1 + k - 1;
+    }
+
+    // Trusted flags of k-mers the running call has NOT modified since its scan, looked up instead of re-queried.
+    // `T` holds one bit per k-mer of the scanned sequence in forward coordinates; when the working sequence is the
+    // reverse complement, k-mer j of it is k-mer nk-1-j of the forward read (canonical k-mers are strand symmetric).
+    // Returns the number of consecutive trusted k-mers of the working sequence starting at index j.
+    KBBQ_HD int cached_run(int j, int len) const {
+        const int nk = len - k + 1;
+        if (j >= nk) return 0;
+        if (!T_mirrored) return next_zero(T, nk, j) - j;
+        const int f = nk - 1 - j;
+        return f - prev_zero(T, f);
+    }
+
+    // bases of "ACGT" (or "TGCA") that differ from s[p], packed 2 bits each in test order
+    KBBQ_HD uint32_t candidates(const SeqRef& s, int p, bool reverse_order, int& ncand) {
+        uint32_t pack = 0;
+        ncand = 0;
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c = reverse_order ? 3 - ci : ci;  // bloom.cc:140-141
+            if (!seq_eq(s, p, c)) pack |= (uint32_t)c << (2 * ncand++);
+        }
+        return pack;
     }
 
     // bloom::find_longest_fix (bloom.cc:130-188) for the substring of s starting at `start`; the base under repair is
@@ -96,14 +144,20 @@ struct ErrCaller {
         const int sublen = s.len - start;
         const int nsub = sublen - k + 1;                          // k-mers of the substring that lie inside the read
         const int i_stop = 2 * k - 1 > sublen ? 2 * k - 1 : sublen;  // bloom.cc:147
-        int nbest = 0, best_i = 0, first_ok = 0;
+        const int nin = nsub < k ? nsub : k;                      // ... of which these contain p
+        int nbest = 0, best_i = 0, first_ok = 0, ncand;
         fix0 = 0;
-        for (int ci = 0; ci < 4; ++ci) {
-            const int c = reverse_order ? 3 - ci : ci;  // ACGT or TGCA (bloom.cc:140-141)
-            if (seq_eq(s, p, c)) continue;
-            int run = trusted_run(s, start, start + nsub, p, c);
+        const uint32_t cpack = candidates(s, p, reverse_order, ncand);
+        const uint32_t m0 = kmers_mask(s, start, 0, ncand, p, 0, cpack);
+        for (int t = 0; t < ncand; ++t) {
+            const int c = (int)((cpack >> (2 * t)) & 3u);
+            int run = 0;
+            if ((m0 >> t) & 1u) {
+                ++first_ok;  // `single`/`multiple` bookkeeping, bloom.cc:163-166
+                run = 1 + trusted_run(s, start + 1, start + nin, p, c);
+                if (run == nin && nsub > nin) run += cached_run(start + nin, s.len);
+            }
             int i = k - 1 + run;
-            if (run >= 1) ++first_ok;  // `single`/`multiple` bookkeeping, bloom.cc:163-166
             if (run == nsub && sublen < i_stop) {
                 // walked off the read end with every k-mer trusted: extend with guessed bases (bloom.cc:83-94,149)
                 uint64_t v = extract_le(s.w, s.len - k, k);
@@ -114,14 +168,14 @@ struct ErrCaller {
                 const int kk = k;
                 for (i = sublen; i < i_stop; ++i) {
                     const uint64_t shifted = v >> 2;
-                    const uint32_t m = q.query(4, [&](int t, uint64_t& key) {
-                        const int cc = reverse_order ? 3 - t : t;
+                    const uint32_t m = q.query(4, [&](int tt, uint64_t& key) {
+                        const int cc = reverse_order ? 3 - tt : tt;
                         key = canonical(shifted | ((uint64_t)cc << (2 * (kk - 1))), kk);
                         return true;
                     });
                     if (m == 0) break;  // no trusted next k-mer
-                    const int t = ctz32(m);
-                    v = shifted | ((uint64_t)(reverse_order ? 3 - t : t) << (2 * (k - 1)));
+                    const int tt = ctz32(m);
+                    v = shifted | ((uint64_t)(reverse_order ? 3 - tt : tt) << (2 * (k - 1)));
                 }
             }
             if (i > best_i) { nbest = 1; fix0 = c; best_i = i; }
@@ -135,35 +189,51 @@ struct ErrCaller {
     // bloom::adjust_right_anchor (bloom.cc:208-277)
     KBBQ_HD int adjust_right_anchor(int anchor, const SeqRef& s, bool& multiple) {
         multiple = false;
-        int m = anchor + 1;
+        const int kk = k;
         {   // does a single substitution at anchor+1 repair everything it touches?  then the anchor stands
+            const int m = anchor + 1;
             int cnt = s.len - m;  // queries possible before the read ends: i = 0 .. min(k, len-1-m)
             if (cnt > k + 1) cnt = k + 1;
-            for (int c = 0; c < 4; ++c) {
-                if (seq_eq(s, m, c)) continue;
-                if (trusted_run(s, m - k + 1, m - k + 1 + cnt, m, c) == cnt) return anchor;
+            const int nin = cnt < k ? cnt : k;  // k-mers that contain m; the (k+1)-th, if any, starts past m
+            int ncand;
+            const uint32_t cpack = candidates(s, m, false, ncand);
+            const uint32_t m0 = kmers_mask(s, m - k + 1, 0, ncand, m, 0, cpack);
+            for (int t = 0; t < ncand; ++t) {
+                if (!((m0 >> t) & 1u)) continue;
+                int run = 1 + trusted_run(s, m - k + 2, m - k + 1 + nin, m, (int)((cpack >> (2 * t)) & 3u));
+                if (run == nin && cnt > nin) run += cached_run(m + 1, s.len) >= 1 ? 1 : 0;
+                if (run == cnt) return anchor;
             }
         }
-        // otherwise try pulling the anchor back by up to k/2
-        for (int i = k / 2 - 1; i >= 0 && anchor > i + k - 1; --i) {
-            m = anchor - i;
-            const int need = k / 2 + 2;  // k-mers ending at m .. m+k/2+1 must all be trusted
-            for (int c = 0; c < 4; ++c) {
-                if (seq_eq(s, m, c)) continue;
-                int j1 = m - k + 1 + need;
-                const int jmax = s.len - k + 1;
-                const bool fits = j1 <= jmax;
-                if (!fits) j1 = jmax;
-                const int run = trusted_run(s, m - k + 1, j1, m, c);
-                if (run >= 1) multiple = true;
-                if (fits && run == need) return m - 1;
+        // otherwise try pulling the anchor back by up to k/2: first k-mers of every (position, base) pair in bulk
+        int ni = 0;  // positions i = k/2-1 .. 0 that satisfy anchor > i+k-1 form a prefix of that descending walk
+        for (int i = k / 2 - 1; i >= 0 && anchor > i + k - 1; --i) ++ni;
+        const int npairs = 4 * ni;
+        const int need = k / 2 + 2;  // k-mers ending at m .. m+k/2+1 must all be trusted
+        const int jmax = s.len - k + 1;
+        for (int c0 = 0; c0 < npairs; c0 += 32) {
+            const int count = npairs - c0 < 32 ? npairs - c0 : 32;
+            uint32_t hits = q.query(count, [&](int t, uint64_t& key) {
+                const int i = kk / 2 - 1 - ((c0 + t) >> 2), c = (c0 + t) & 3;
+                const int m = anchor - i;
+                if (seq_eq(s, m, c)) return false;
+                return kmer_key(s, m - kk + 1, kk, m, c, key);
+            });
+            while (hits) {
+                const int t = ctz32(hits);
+                hits &= hits - 1;
+                const int i = k / 2 - 1 - ((c0 + t) >> 2), c = (c0 + t) & 3;
+                const int m = anchor - i;
+                multiple = true;
+                const int j1 = m - k + 1 + need;
+                if (j1 <= jmax && 1 + trusted_run(s, m - k + 2, j1, m, c) == need) return m - 1;
             }
         }
         return anchor;
     }
 
     // CReadData::correct_one (readutils.cc:195-235) + bloom::biggest_consecutive_trusted_block (bloom.cc:279-305)
-    KBBQ_HD int correct_one(const SeqRef& s, int qbase, int& out_base) {
+    KBBQ_HD_NOINLINE int correct_one(const SeqRef& s, int qbase, int& out_base) {
         const int len = s.len;
         int best_len = 0, best_base = 0, best_pos = KBBQ_NPOS;
         const int ncand = 4 * len;  // candidate id = 4*i + c; identical bases are skipped like `continue`
@@ -185,7 +255,7 @@ struct ErrCaller {
                 const int start = i > k - 1 ? i - k + 1 : 0;
                 int nwin = len - k + 1 - start;  // k-mers of substr(start, 2k-1)
                 if (nwin > k) nwin = k;
-                uint32_t m = trusted_mask(s, start, nwin, i, c);
+                uint32_t m = kmers_mask(s, start, 1, nwin, i, c, 0);
                 // the walk stops once k - (#misses) < best_len (bloom.cc:295): cut the mask at that miss
                 if (best_len >= 1) {
                     const int stop_after = k - best_len + 1;  // this many misses end the walk
@@ -247,6 +317,8 @@ struct ErrCaller {
         for (int w = 0; w <= nw; ++w) sc.O_nm[w] = cur.nm[w];
         bool multiple = false;
         scan(cur, sc.T_orig);
+        T = sc.T_orig;
+        T_mirrored = false;
         int a0, a1;
         longest_trusted(sc.T_orig, len, a0, a1);
         if (a0 == KBBQ_NPOS) {  // no trusted k-mer in the read (readutils.cc:250-262)
@@ -255,6 +327,7 @@ struct ErrCaller {
             const int idx = correct_one(cur, base, fixed_base);
             if (idx == KBBQ_NPOS) return;
             scan(cur, sc.T_cur);
+            T = sc.T_cur;
             longest_trusted(sc.T_cur, len, a0, a1);
             bit_set(sc.E, base + idx);
             if (a0 == 0 && a1 == KBBQ_NPOS) {  // ref quirk: returns with the corrected base still in seq
@@ -266,70 +339,54 @@ struct ErrCaller {
         }
         const int anchor_len = (a1 == KBBQ_NPOS ? len - 1 : a1) + 1 - a0;
         bool corrected = false;
-        // ---- right of the anchor (readutils.cc:271-346)
-        if (a1 != KBBQ_NPOS) {
-            if (anchor_len - k + 1 >= k) {
+        // ---- the two sides of the anchor: right on `cur` (readutils.cc:271-346), then left on its reverse complement
+        //      (348-422).  In the reverse complement's own coordinates the left walk is the same loop: the base under
+        //      repair sits at j, the next one at start + fixlen; only the flag index (len-1-j) is mirrored.
+        SeqRef rc{sc.C_w, sc.C_nm, len};
+        for (int side = 0; side < 2; ++side) {
+            int anchor;
+            if (side == 0) {
+                if (a1 == KBBQ_NPOS) continue;
+                anchor = a1;
+            } else {
+                if (a0 == 0) continue;
+                revcomp(cur, rc);  // of the read WITH its right-side fixes
+                T_mirrored = true;
+                anchor = len - a0 - 1;
+            }
+            const SeqRef& s = side ? rc : cur;
+            if (anchor_len - k + 1 >= k) {  // at least k trusted k-mers: the anchor's tail may be false positives
                 bool cm;
-                a1 = adjust_right_anchor(a1, cur, cm);
+                anchor = adjust_right_anchor(anchor, s, cm);  // ref quirk: ACGT order on both sides (readutils.cc:374)
                 multiple = multiple || cm;
             }
-            for (int i = a1 + 1; i < len;) {
-                const int start = i - k + 1;
-                int fix0, fixlen;
-                bool cm;
-                const int nfix = longest_fix(cur, start, false, fix0, fixlen, cm);
-                multiple = multiple || cm;
-                const int next_untrusted = start + fixlen;
-                if (next_untrusted > i) {
-                    if (nfix > 1) {
-                        multiple = true;
-                        const int largest = i + k - 1 < len - 1 ? i + k - 1 : len - 1;
-                        if (next_untrusted <= largest || largest - i + 1 < k) { bad_suffix = i; break; }
-                    } else {
-                        seq_set(cur, i, fix0);
-                        bit_set(sc.E, base + i);
-                    }
-                    corrected = true;
-                    i += fixlen - k + 1;
-                } else {
-                    bad_suffix = i;
-                    break;
-                }
-            }
-        }
-        // ---- left of the anchor, on the reverse complement (readutils.cc:348-422)
-        if (a0 != 0) {
-            SeqRef rc{sc.C_w, sc.C_nm, len};
-            revcomp(cur, rc);
-            if (anchor_len - k + 1 >= k) {
-                bool cm;
-                const int left_adjust = adjust_right_anchor(len - a0 - 1, rc, cm);  // ref quirk: ACGT order here
-                a0 = len - left_adjust - 1;
-                multiple = multiple || cm;
-            }
-            for (int i = a0 - 1; i >= 0;) {
-                const int j = len - i - 1;
+            int bad = KBBQ_NPOS;
+            for (int j = anchor + 1; j < len;) {
                 const int start = j - k + 1;
                 int fix0, fixlen;
                 bool cm;
-                const int nfix = longest_fix(rc, start, true, fix0, fixlen, cm);
+                const int nfix = longest_fix(s, start, side != 0, fix0, fixlen, cm);
                 multiple = multiple || cm;
                 const int next_untrusted = start + fixlen;
                 if (next_untrusted > j) {
                     if (nfix > 1) {
                         multiple = true;
                         const int largest = j + k - 1 < len - 1 ? j + k - 1 : len - 1;
-                        if (next_untrusted <= largest || largest - j + 1 < k) { bad_prefix = i; break; }
+                        if (next_untrusted <= largest || largest - j + 1 < k) { bad = j; break; }
                     } else {
-                        seq_set(rc, j, fix0);  // ref quirk: left-side fixes never reach this->seq
-                        bit_set(sc.E, base + i);
+                        seq_set(s, j, fix0);  // ref quirk: left-side fixes land in the reverse complement only
+                        bit_set(sc.E, base + (side ? len - 1 - j : j));
                     }
                     corrected = true;
-                    i -= next_untrusted - j;
+                    j = next_untrusted;
                 } else {
-                    bad_prefix = i;
+                    bad = j;
                     break;
                 }
+            }
+            if (bad != KBBQ_NPOS) {
+                if (side == 0) bad_suffix = bad;
+                else bad_prefix = len - 1 - bad;
             }
         }
         // ---- overcorrection check (readutils.cc:429-546)
@@ -349,19 +406,30 @@ struct ErrCaller {
                 }
             }
             adjust = adjust && !multiple;
-            // sliding 20-base window, weight 1 per flagged base, 1/2 when qual <= minqual(6); counted in half units
+            // sliding 20-base window over the flagged bases whose ORIGINAL base was ACGT: weight 1, or 1/2 when
+            // qual <= minqual(6); flagged position i is overcorrected when the window ending at i weighs more than
+            // the threshold (4, or 5 in the interior when `adjust`).  Counted in half units, 32 positions per step.
             const int ocwindow = 20, base_threshold = 4;
-            int occ2 = 0;
-            bool any_oc = false;
             uint32_t* OC = sc.T_cur;  // T_cur is dead from here on: reuse it for the overcorrected-index list
-            for (int w = 0; w <= nw; ++w) OC[w] = 0;
-            for (int i = 0; i < len; ++i) {
-                if (bit_get(sc.E, base + i) && !bit_get(sc.O_nm, i)) occ2 += qual[base + i] <= 6 ? 1 : 2;
-                if (i >= ocwindow && bit_get(sc.E, base + i - ocwindow) && !bit_get(sc.O_nm, i - ocwindow))
-                    occ2 -= qual[base + i - ocwindow] <= 6 ? 1 : 2;
-                const int threshold = adjust && i >= ocwindow && i + ocwindow - 1 < len ? base_threshold + 1 : base_threshold;
-                if (occ2 > 2 * threshold && bit_get(sc.E, base + i)) { bit_set(OC, i); any_oc = true; }
+            bool any_oc = false;
+            const uint32_t* E = sc.E;
+            const uint32_t* QL = sc.QL;
+            const uint32_t* ON = sc.O_nm;
+            for (int w = 0; w < nw; ++w) {
+                const uint32_t m = q.map32([&](int t) {
+                    const int i = 32 * w + t;
+                    if (i >= len || !bit_get(E, base + i)) return false;
+                    const int lo = i - ocwindow + 1 > 0 ? i - ocwindow + 1 : 0;
+                    int occ2 = 0;
+                    for (int x = lo; x <= i; ++x)
+                        if (bit_get(E, base + x) && !bit_get(ON, x)) occ2 += bit_get(QL, base + x) ? 1 : 2;
+                    const int threshold = adjust && i >= ocwindow && i + ocwindow - 1 < len ? base_threshold + 1 : base_threshold;
+                    return occ2 > 2 * threshold;
+                });
+                OC[w] = m;
+                any_oc = any_oc || m != 0;
             }
+            OC[nw] = 0;
             if (any_oc) {  // un-flag everything within k of an overcorrected base, transitively (521-545)
                 for (int oc = next_one(OC, len, 0); oc < len; oc = next_one(OC, len, oc + 1)) {
                     if (!bit_get(sc.E, base + oc)) continue;
@@ -385,45 +453,40 @@ struct ErrCaller {
     }
 
     // Top level: get_errors(first_call=true) including the one-level recursion on a long bad prefix / suffix
-    // (readutils.cc:547-563).  `P` must hold the read; sc.E must be zero.  On return sc.E holds read.errors.
+    // (readutils.cc:547-563).  sc.P_* must hold the read, sc.QL its low-quality flags, sc.E must be zero.
+    // On return sc.E holds read.errors.
     KBBQ_HD ErrResult run(int len) {
         ErrResult res;
         res.mod_idx = -1;
         res.mod_base = -1;
-        SeqRef P{sc.P_w, sc.P_nm, len};
-        int bad_prefix, bad_suffix;
-        call(P, 0, true, bad_prefix, bad_suffix, res);
         if (len < k) return res;
-        if (bad_prefix > 0 && (bad_prefix >= len / 2 || bad_prefix >= 2 * k)) {
-            const int sl = bad_prefix + 1;  // substr(0, bad_prefix+1) of the partly corrected read
-            SeqRef A{sc.A_w, sc.A_nm, sl};
-            const int nw = (sl + 31) >> 5;
-            for (int w = 0; w < nw; ++w) { A.w[w] = P.w[w]; A.nm[w] = P.nm[w]; }
-            if (sl & 31) {
-                A.w[nw - 1] &= kmask(sl & 31);
-                A.nm[nw - 1] &= (1u << (sl & 31)) - 1;
+        SeqRef P{sc.P_w, sc.P_nm, len};
+        SeqRef A{sc.A_w, sc.A_nm, 0};
+        int top_prefix = 0, top_suffix = KBBQ_NPOS;
+        for (int job = 0; job < 3; ++job) {  // 0: the read; 1: substr(0, bad_prefix+1); 2: substr(bad_suffix)
+            int from = 0;
+            if (job == 1) {
+                if (!(top_prefix > 0 && (top_prefix >= len / 2 || top_prefix >= 2 * k))) continue;
+                A.len = top_prefix + 1;
+            } else if (job == 2) {
+                if (!(top_suffix != KBBQ_NPOS && top_suffix < len && (len - top_suffix > len / 2 || len - top_suffix > 2 * k))) continue;
+                from = top_suffix;
+                A.len = len - top_suffix;
             }
-            A.w[nw] = 0;
-            A.nm[nw] = 0;
-            int bp, bs;
-            ErrResult dummy;
-            call(A, 0, false, bp, bs, dummy);
-        }
-        if (bad_suffix != KBBQ_NPOS && bad_suffix < len && (len - bad_suffix > len / 2 || len - bad_suffix > 2 * k)) {
-            const int sl = len - bad_suffix;  // substr(bad_suffix)
-            SeqRef A{sc.A_w, sc.A_nm, sl};
-            const int nw = (sl + 31) >> 5;
-            for (int w = 0; w < nw; ++w) {
-                const int s0 = bad_suffix + 32 * w;
-                const int cnt = sl - 32 * w < 32 ? sl - 32 * w : 32;
-                A.w[w] = extract_le(P.w, s0, cnt);
-                A.nm[w] = extract_n(P.nm, s0, cnt);
+            if (job) {  // the sub-read is cut from the partly corrected read and inherits its flags (readutils.cc:597-608)
+                const int nw = (A.len + 31) >> 5;
+                for (int w = 0; w < nw; ++w) {
+                    const int cnt = A.len - 32 * w < 32 ? A.len - 32 * w : 32;
+                    A.w[w] = extract_le(P.w, from + 32 * w, cnt);
+                    A.nm[w] = extract_n(P.nm, from + 32 * w, cnt);
+                }
+                A.w[nw] = 0;
+                A.nm[nw] = 0;
             }
-            A.w[nw] = 0;
-            A.nm[nw] = 0;
             int bp, bs;
-            ErrResult dummy;
-            call(A, bad_suffix, false, bp, bs, dummy);
+            ErrResult sub;
+            call(job ? A : P, from, job == 0, bp, bs, job ? sub : res);
+            if (job == 0) { top_prefix = bp; top_suffix = bs; }
         }
         return res;
     }

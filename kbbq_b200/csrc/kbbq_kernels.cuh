@@ -81,6 +81,103 @@ __device__ __forceinline__ void bloom_insert_dev(const BloomView& f, uint64_t ke
     }
 }
 
+// ---- warp-cooperative probes ---------------------------------------------------------------------------------------
+// A probe touches one 64-byte block at a random address plus one 64-byte pattern.  With one lane per probe a warp
+// load instruction hits 32 different cache lines and uses 16 of each line's 128 bytes: 4x the L1/L2 wavefronts the
+// data needs.  Here FOUR lanes share a probe, each moving one 16-byte quarter, so a warp instruction covers 8 probes
+// as 8 fully used 64-byte segments; a 32-probe query is 4 rounds, all of whose loads are issued before any is used.
+
+// eight flags spaced 4 bits apart (bits 0,4,..,28) -> bits 0..7
+__device__ __forceinline__ uint32_t gather_nibble_flags(uint32_t t) {
+    t = (t | (t >> 3)) & 0x03030303u;
+    t = (t | (t >> 6)) & 0x000F000Fu;
+    return (t | (t >> 12)) & 0xFFu;
+}
+
+// The probe proper: every lane brings the (block, pattern) of its own key; returns the mask of lanes that hit.
+template <int ROUNDS_AT_ONCE>
+__device__ __forceinline__ uint32_t coop_probe_impl(const unsigned long long* __restrict__ words,
+                                                    const unsigned long long* __restrict__ patterns, uint64_t blk,
+                                                    uint32_t pat, uint32_t vmask) {
+    const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
+    uint32_t result = 0;
+#pragma unroll
+    for (int r0 = 0; r0 < 4; r0 += ROUNDS_AT_ONCE) {
+        if (!((vmask >> (8 * r0)) & (ROUNDS_AT_ONCE == 4 ? 0xFFFFFFFFu : ((1u << (8 * ROUNDS_AT_ONCE)) - 1)))) continue;
+        uint4 x[ROUNDS_AT_ONCE], y[ROUNDS_AT_ONCE];
+        bool v[ROUNDS_AT_ONCE];
+#pragma unroll
+        for (int i = 0; i < ROUNDS_AT_ONCE; ++i) {  // issue every load of the group before using any
+            const int src = 8 * (r0 + i) + grp;
+            const uint64_t b = __shfl_sync(KBBQ_FULL, blk, src);
+            const uint32_t p = __shfl_sync(KBBQ_FULL, pat, src);
+            v[i] = (vmask >> src) & 1u;
+            x[i] = make_uint4(0, 0, 0, 0);
+            y[i] = make_uint4(0, 0, 0, 0);
+            if (v[i]) {
+                x[i] = __ldg(reinterpret_cast<const uint4*>(words + b * 8) + sub);
+                y[i] = __ldg(reinterpret_cast<const uint4*>(patterns + (uint64_t)p * 8) + sub);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ROUNDS_AT_ONCE; ++i) {
+            const bool ok = v[i] && ((~x[i].x & y[i].x) | (~x[i].y & y[i].y) | (~x[i].z & y[i].z) | (~x[i].w & y[i].w)) == 0;
+            uint32_t m = __ballot_sync(KBBQ_FULL, ok);
+            m &= (m >> 1) & (m >> 2) & (m >> 3) & 0x11111111u;  // all four quarters of a probe agree
+            result |= gather_nibble_flags(m) << (8 * (r0 + i));
+        }
+    }
+    return result;
+}
+// out-of-line copy for the error-calling kernel, which asks from a dozen places
+__device__ __noinline__ uint32_t coop_probe_call(const unsigned long long* words, const unsigned long long* patterns,
+                                                 uint64_t blk, uint32_t pat, uint32_t vmask) {
+    return coop_probe_impl<2>(words, patterns, blk, pat, vmask);
+}
+
+// mask of lanes whose key is valid and contained in f (pattern_blocked_bf::contains, bloom.hh:276-292).
+// All 32 lanes must call.
+template <bool INLINE>
+__device__ __forceinline__ uint32_t warp_bloom_query(const BloomView& f, bool valid, uint64_t key) {
+    const uint32_t vmask = __ballot_sync(KBBQ_FULL, valid);
+    if (vmask == 0) return 0;
+    const uint64_t blk = valid ? bloom_block(f, key) : 0;
+    const uint32_t pat = valid ? bloom_pattern(f, key) : 0;
+    if (INLINE) return coop_probe_impl<4>(f.words, f.patterns, blk, pat, vmask);
+    return coop_probe_call(f.words, f.patterns, blk, pat, vmask);
+}
+
+// pattern_blocked_bf::insert (bloom.hh:255-267) for the lanes with `ins` set; returns how many were inserted.
+// The (block, pattern) pairs are first compacted through `stage` (32 x 12 bytes of per-warp shared memory) so that
+// sparse inserts (pass 1 samples ~14-35 % of the k-mers) still fill every round.  All 32 lanes must call.
+struct InsertStage {
+    unsigned long long blk[32];
+    uint32_t pat[32];
+};
+__device__ __forceinline__ int warp_bloom_insert(const BloomView& f, bool ins, uint64_t key, InsertStage& stage) {
+    const uint32_t imask = __ballot_sync(KBBQ_FULL, ins);
+    if (imask == 0) return 0;
+    const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
+    const int n = __popc(imask);
+    if (ins) {
+        const int rank = __popc(imask & ((1u << lane) - 1));
+        stage.blk[rank] = bloom_block(f, key);
+        stage.pat[rank] = bloom_pattern(f, key);
+    }
+    __syncwarp();
+    for (int base = 0; base < n; base += 8) {
+        const int idx = base + grp;
+        if (idx < n) {
+            const ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(f.patterns + (uint64_t)stage.pat[idx] * 8) + sub);
+            unsigned long long* B = f.words + stage.blk[idx] * 8 + 2 * sub;
+            if (p.x) atomicOr(B, p.x);
+            if (p.y) atomicOr(B + 1, p.y);
+        }
+    }
+    __syncwarp();
+    return n;
+}
+
 // ---- pass 1a: the sampling stream ---------------------------------------------------------------------------------
 // One serial xoshiro256** stream decides every k-mer slot of the file (htsiter.cc:113-129).  The generator is linear
 // over GF(2): thread t jumps straight to draw 1024*t with precomputed 256x256 bit matrices of 2^e steps
@@ -134,6 +231,8 @@ __global__ void __launch_bounds__(128) rng_sample_kernel(uint64_t s0, uint64_t s
 // ---- pass 1b: insert the sampled k-mers (recalibrateutils.cc:7-13) ---------------------------------------------------
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel(BatchView b, BloomView f, int k,
                                                                                   const uint32_t* __restrict__ sample_bits) {
+    __shared__ InsertStage stage_all[KBBQ_WARPS_PER_BLOCK];
+    InsertStage& stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
@@ -147,17 +246,13 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
             bool ins = false;
+            uint64_t key = 0;
             if (j < nk) {
                 const unsigned long long slot = so + (unsigned)j;
-                if ((__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u) {
-                    uint64_t key;
-                    if (kmer_key(s, j, k, 0, -1, key)) {  // an invalid k-mer still consumed its draw
-                        bloom_insert_dev(f, key);
-                        ins = true;
-                    }
-                }
+                if ((__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u)
+                    ins = kmer_key(s, j, k, 0, -1, key);  // an invalid k-mer still consumed its draw
             }
-            inserted += __popc(__ballot_sync(KBBQ_FULL, ins));
+            inserted += warp_bloom_insert(f, ins, key, stage);
         }
     }
     if (lane == 0 && inserted) atomicAdd(f.inserted, inserted);
@@ -170,6 +265,8 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
     __shared__ int thr[KBBQ_MAX_K + 1];
     __shared__ uint32_t Pm_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
     __shared__ uint32_t Em_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
+    __shared__ InsertStage stage_all[KBBQ_WARPS_PER_BLOCK];
+    InsertStage& stage = stage_all[threadIdx.x >> 5];
     if (threadIdx.x <= k) thr[threadIdx.x] = thresholds[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -187,12 +284,9 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         // kmer_present (bloom.cc:35-47)
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
-            bool hit = false;
-            if (j < nk) {
-                uint64_t key;
-                if (kmer_key(s, j, k, 0, -1, key)) hit = bloom_contains_dev(sampled, key);
-            }
-            const uint32_t m = __ballot_sync(KBBQ_FULL, hit);
+            uint64_t key = 0;
+            const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+            const uint32_t m = warp_bloom_query<true>(sampled, valid, key);
             if (lane == 0) Pm[j0 >> 5] = m;
         }
         __syncwarp();
@@ -216,15 +310,9 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         // a k-mer is trusted when it is valid and none of its k bases is flagged (recalibrateutils.cc:26-36)
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
-            bool ins = false;
-            if (j < nk && count_range(Em, j, j + k) == 0) {
-                uint64_t key;
-                if (kmer_key(s, j, k, 0, -1, key)) {
-                    bloom_insert_dev(trusted, key);
-                    ins = true;
-                }
-            }
-            inserted += __popc(__ballot_sync(KBBQ_FULL, ins));
+            uint64_t key = 0;
+            const bool ins = j < nk && count_range(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key);
+            inserted += warp_bloom_insert(trusted, ins, key, stage);
         }
         __syncwarp();
     }
@@ -289,14 +377,20 @@ struct DevQuery {
     KBBQ_HD uint32_t query(int count, F fn) {
 #if defined(__CUDA_ARCH__)
         const int lane = threadIdx.x & 31;
-        bool hit = false;
-        if (lane < count) {
-            uint64_t key;
-            if (fn(lane, key)) hit = bloom_contains_dev(f, key);
-        }
-        return __ballot_sync(KBBQ_FULL, hit);
+        uint64_t key = 0;
+        const bool valid = lane < count && fn(lane, key);
+        return warp_bloom_query<false>(f, valid, key);
 #else
         (void)count; (void)fn;
+        return 0;
+#endif
+    }
+    template <class F>
+    KBBQ_HD uint32_t map32(F fn) {
+#if defined(__CUDA_ARCH__)
+        return __ballot_sync(KBBQ_FULL, fn((int)(threadIdx.x & 31)));
+#else
+        (void)fn;
         return 0;
 #endif
     }
@@ -323,6 +417,11 @@ pass3_errors_kernel(BatchView b, BloomView trusted, CountView cv, int k, uint32_
             sc.P_w[lane] = lane < nw ? b.bases[wo + lane] : 0ull;
             sc.P_nm[lane] = lane < nw ? b.nmask[wo + lane] : 0u;
             sc.E[lane] = 0;
+        }
+        for (int i0 = 0; i0 <= len; i0 += 32) {  // low-quality flags for the overcorrection half weight
+            const int i = i0 + lane;
+            const uint32_t m = __ballot_sync(KBBQ_FULL, i < len && qual[i] <= 6);
+            if (lane == 0) sc.QL[i0 >> 5] = m;
         }
         __syncwarp();
         ErrCaller<DevQuery> ec(q, k, qual, sc);

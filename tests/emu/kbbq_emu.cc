@@ -43,6 +43,13 @@ struct HostQuery {
         }
         return m;
     }
+    template <class F>
+    uint32_t map32(F fn) {
+        uint32_t m = 0;
+        for (int t = 0; t < 32; ++t)
+            if (fn(t)) m |= 1u << t;
+        return m;
+    }
 };
 BloomView make_view(uint64_t* words, const uint64_t* patterns, uint64_t* inserted, uint64_t n_blocks, uint32_t s0, uint32_t s1) {
     BloomView v;
@@ -120,6 +127,8 @@ uint64_t emu_get_errors(uint32_t n, const uint64_t* bases, const uint32_t* nmask
         ErrScratch sc;
         std::memset(&sc, 0, sizeof sc);
         for (int w = 0; w < nw; ++w) { sc.P_w[w] = bases[wo + w]; sc.P_nm[w] = nmask[wo + w]; }
+        for (int i = 0; i < L; ++i)
+            if (qual[(size_t)wo * 32 + i] <= 6) bit_set(sc.QL, i);
         ErrCaller<HostQuery> ec(q, k, qual + (size_t)wo * 32, sc);
         const ErrResult res = ec.run(L);
         for (int w = 0; w < nw; ++w) err_bits[wo + w] = sc.E[w];
