@@ -137,29 +137,70 @@ struct ErrCaller {
         return pack;
     }
 
+    // What the pre-test and the walks over the k-mers containing position p found, remembered between
+    // adjust_right_anchor's first phase and the find_longest_fix that immediately follows it at the same position on
+    // the same, still unmodified, sequence (they ask the filter exactly the same questions).
+    struct Memo {
+        int p;            // position, -1 = empty
+        bool mirrored;    // which working sequence
+        uint32_t first;   // bit c: first k-mer with base c trusted
+        int run_in[4];    // per base: trusted streak over the k-mers containing p (>= 1), or -1 when not walked yet
+    };
+    Memo memo;
+
+    KBBQ_HD void memo_reset() { memo.p = -1; }
+    // first-k-mer flags of all candidate bases at p (bit c of the result), through the memo
+    KBBQ_HD uint32_t first_flags(const SeqRef& s, int p, uint32_t cpack, int ncand) {
+        if (memo.p == p && memo.mirrored == T_mirrored) return memo.first;
+        const uint32_t m0 = kmers_mask(s, p - k + 1, 0, ncand, p, 0, cpack);
+        memo.p = p;
+        memo.mirrored = T_mirrored;
+        memo.first = 0;
+        for (int t = 0; t < ncand; ++t) {
+            const int c = (int)((cpack >> (2 * t)) & 3u);
+            if ((m0 >> t) & 1u) memo.first |= 1u << c;
+            memo.run_in[c] = -1;
+        }
+        return memo.first;
+    }
+    // trusted streak over the k-mers that contain p (there are nin of them) with base c at p, first one known trusted
+    KBBQ_HD int run_containing(const SeqRef& s, int p, int nin, int c) {
+        if (memo.run_in[c] < 0) memo.run_in[c] = 1 + trusted_run(s, p - k + 2, p - k + 1 + nin, p, c);
+        return memo.run_in[c];
+    }
+
     // bloom::find_longest_fix (bloom.cc:130-188) for the substring of s starting at `start`; the base under repair is
     // p = start + k - 1.  Returns the number of best candidates; fix0 = the first of them, fixlen = best_i.
+    // The walk past the read end with guessed bases (bloom.cc:83-94,149) only ever matters as a tie-break between
+    // candidates that BOTH keep every in-read k-mer trusted: a lone such candidate is the unique best whatever its
+    // extension, and the caller only uses its fixlen as "reaches the read end".  It is skipped in that case.
     KBBQ_HD int longest_fix(const SeqRef& s, int start, bool reverse_order, int& fix0, int& fixlen, bool& multiple) {
         const int p = start + k - 1;
         const int sublen = s.len - start;
         const int nsub = sublen - k + 1;                          // k-mers of the substring that lie inside the read
         const int i_stop = 2 * k - 1 > sublen ? 2 * k - 1 : sublen;  // bloom.cc:147
         const int nin = nsub < k ? nsub : k;                      // ... of which these contain p
-        int nbest = 0, best_i = 0, first_ok = 0, ncand;
+        int nbest = 0, best_i = 0, first_ok = 0, ncand, nreach = 0;
+        int runs[4];
         fix0 = 0;
         const uint32_t cpack = candidates(s, p, reverse_order, ncand);
-        const uint32_t m0 = kmers_mask(s, start, 0, ncand, p, 0, cpack);
+        const uint32_t first = first_flags(s, p, cpack, ncand);
         for (int t = 0; t < ncand; ++t) {
             const int c = (int)((cpack >> (2 * t)) & 3u);
             int run = 0;
-            if ((m0 >> t) & 1u) {
+            if ((first >> c) & 1u) {
                 ++first_ok;  // `single`/`multiple` bookkeeping, bloom.cc:163-166
-                run = 1 + trusted_run(s, start + 1, start + nin, p, c);
+                run = run_containing(s, p, nin, c);
                 if (run == nin && nsub > nin) run += cached_run(start + nin, s.len);
             }
-            int i = k - 1 + run;
-            if (run == nsub && sublen < i_stop) {
-                // walked off the read end with every k-mer trusted: extend with guessed bases (bloom.cc:83-94,149)
+            runs[t] = run;
+            nreach += run == nsub;
+        }
+        const bool extend = sublen < i_stop && nreach >= 2;
+        for (int t = 0; t < ncand; ++t) {
+            const int c = (int)((cpack >> (2 * t)) & 3u);
+            int i = k - 1 + runs[t];
+            if (extend && runs[t] == nsub) {
                 uint64_t v = extract_le(s.w, s.len - k, k);
                 if (p >= s.len - k) {
                     const int o = p - (s.len - k);
@@ -197,10 +238,11 @@ struct ErrCaller {
             const int nin = cnt < k ? cnt : k;  // k-mers that contain m; the (k+1)-th, if any, starts past m
             int ncand;
             const uint32_t cpack = candidates(s, m, false, ncand);
-            const uint32_t m0 = kmers_mask(s, m - k + 1, 0, ncand, m, 0, cpack);
+            const uint32_t first = first_flags(s, m, cpack, ncand);
             for (int t = 0; t < ncand; ++t) {
-                if (!((m0 >> t) & 1u)) continue;
-                int run = 1 + trusted_run(s, m - k + 2, m - k + 1 + nin, m, (int)((cpack >> (2 * t)) & 3u));
+                const int c = (int)((cpack >> (2 * t)) & 3u);
+                if (!((first >> c) & 1u)) continue;
+                int run = run_containing(s, m, nin, c);
                 if (run == nin && cnt > nin) run += cached_run(m + 1, s.len) >= 1 ? 1 : 0;
                 if (run == cnt) return anchor;
             }
@@ -316,6 +358,7 @@ struct ErrCaller {
         const int nw = (len + 31) >> 5;
         for (int w = 0; w <= nw; ++w) sc.O_nm[w] = cur.nm[w];
         bool multiple = false;
+        memo_reset();
         scan(cur, sc.T_orig);
         T = sc.T_orig;
         T_mirrored = false;
@@ -375,6 +418,7 @@ struct ErrCaller {
                         if (next_untrusted <= largest || largest - j + 1 < k) { bad = j; break; }
                     } else {
                         seq_set(s, j, fix0);  // ref quirk: left-side fixes land in the reverse complement only
+                        memo_reset();
                         bit_set(sc.E, base + (side ? len - 1 - j : j));
                     }
                     corrected = true;

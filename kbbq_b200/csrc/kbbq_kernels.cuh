@@ -51,18 +51,23 @@ struct CSeqRef {
 #define KBBQ_FULL 0xffffffffu
 
 // ---- filter probes ------------------------------------------------------------------------------------------------
-// pattern_blocked_bf::contains (bloom.hh:276-292): (block & pattern) == pattern over 512 bits
+// 32 bytes in one LDG.E.256 (sm_100): a 64-byte block or pattern is two instructions
+__device__ __forceinline__ void ldg256(const unsigned long long* p, unsigned long long& a, unsigned long long& b,
+                                       unsigned long long& c, unsigned long long& d) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+// pattern_blocked_bf::contains (bloom.hh:276-292): (block & pattern) == pattern over 512 bits, one lane per key
 __device__ __forceinline__ bool bloom_contains_dev(const BloomView& f, uint64_t key) {
     const uint64_t blk = bloom_block(f, key);
     const uint32_t pat = bloom_pattern(f, key);
-    const uint4* B = reinterpret_cast<const uint4*>(f.words + blk * 8);
-    const uint4* P = reinterpret_cast<const uint4*>(f.patterns + (uint64_t)pat * 8);
-    uint4 b0 = __ldg(B), b1 = __ldg(B + 1), b2 = __ldg(B + 2), b3 = __ldg(B + 3);
-    uint4 p0 = __ldg(P), p1 = __ldg(P + 1), p2 = __ldg(P + 2), p3 = __ldg(P + 3);
-    uint32_t miss = (~b0.x & p0.x) | (~b0.y & p0.y) | (~b0.z & p0.z) | (~b0.w & p0.w);
-    miss |= (~b1.x & p1.x) | (~b1.y & p1.y) | (~b1.z & p1.z) | (~b1.w & p1.w);
-    miss |= (~b2.x & p2.x) | (~b2.y & p2.y) | (~b2.z & p2.z) | (~b2.w & p2.w);
-    miss |= (~b3.x & p3.x) | (~b3.y & p3.y) | (~b3.z & p3.z) | (~b3.w & p3.w);
+    const unsigned long long* B = f.words + blk * 8;
+    const unsigned long long* P = f.patterns + (uint64_t)pat * 8;
+    unsigned long long b0, b1, b2, b3, b4, b5, b6, b7, p0, p1, p2, p3, p4, p5, p6, p7;
+    ldg256(B, b0, b1, b2, b3);
+    ldg256(B + 4, b4, b5, b6, b7);
+    ldg256(P, p0, p1, p2, p3);
+    ldg256(P + 4, p4, p5, p6, p7);
+    const unsigned long long miss = (~b0 & p0) | (~b1 & p1) | (~b2 & p2) | (~b3 & p3) | (~b4 & p4) | (~b5 & p5) | (~b6 & p6) | (~b7 & p7);
     return miss == 0;
 }
 
@@ -379,7 +384,7 @@ struct DevQuery {
         const int lane = threadIdx.x & 31;
         uint64_t key = 0;
         const bool valid = lane < count && fn(lane, key);
-        return warp_bloom_query<false>(f, valid, key);
+        return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(f, key));
 #else
         (void)count; (void)fn;
         return 0;
