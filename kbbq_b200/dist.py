@@ -46,8 +46,10 @@ class Comm:
         """words |= every other rank's words.  `or_into(dst_tensor, src_tensor)` performs dst |= src."""
         if self.world == 1:
             return
-        gathered = torch.empty((self.world,) + tuple(words.shape), dtype=words.dtype, device=words.device)
-        dist.all_gather_into_tensor(gathered, words.contiguous())
+        flat = words.contiguous().view(-1)
+        gathered = torch.empty(self.world * flat.numel(), dtype=words.dtype, device=words.device)
+        dist.all_gather_into_tensor(gathered, flat)
+        gathered = gathered.view(self.world, flat.numel())
         for r in range(self.world):
             if r == self.rank:
                 continue

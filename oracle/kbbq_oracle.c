@@ -325,8 +325,15 @@ void ko_thresholds_from_filter(const ko_bloom *sampled, long double alpha_num, l
 /* ---- a5/a6: KmerSubsampler::next + subsample_kmers (htsiter.cc:89-129; recalibrateutils.cc:7-13) ---- */
 uint64_t ko_subsample(uint64_t n, const char *seq, const uint64_t *off, int k, double alpha, uint32_t seed,
                       ko_bloom *sampled) {
+    return ko_subsample_skip(n, seq, off, k, alpha, seed, 0, sampled);
+}
+
+/* the same over a shard of the input whose first k-mer slot has ordinal `skip` in the file-wide stream */
+uint64_t ko_subsample_skip(uint64_t n, const char *seq, const uint64_t *off, int k, double alpha, uint32_t seed,
+                           uint64_t skip, ko_bloom *sampled) {
     uint64_t st[4], slots = 0;
     ko_rng_seed(seed, st);
+    for (uint64_t i = 0; i < skip; ++i) ko_rng_next(st);
     kmer_t km;
     kmer_init(&km, k);
     for (uint64_t r = 0; r < n; ++r) {

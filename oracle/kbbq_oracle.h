@@ -65,6 +65,8 @@ void ko_thresholds_from_filter(const ko_bloom *sampled, long double alpha_num, l
 /* passes */
 uint64_t ko_subsample(uint64_t n, const char *seq, const uint64_t *off, int k, double alpha, uint32_t seed,
                       ko_bloom *sampled);
+uint64_t ko_subsample_skip(uint64_t n, const char *seq, const uint64_t *off, int k, double alpha, uint32_t seed,
+                           uint64_t skip, ko_bloom *sampled);
 void ko_infer_errors(uint64_t n, const char *seq, const uint64_t *off, const uint8_t *qual, int k,
                      const ko_bloom *sampled, const int *thresholds, uint8_t *errors);
 void ko_find_trusted(uint64_t n, const char *seq, const uint64_t *off, const uint8_t *qual, int k,

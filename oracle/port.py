@@ -61,6 +61,8 @@ def lib():
         L.ko_thresholds_from_filter.argtypes = [BP, C.c_longdouble, C.c_longdouble, C.c_int, _i32p]
         L.ko_subsample.restype = C.c_uint64
         L.ko_subsample.argtypes = [C.c_uint64, _u8p, _u64p, C.c_int, C.c_double, C.c_uint32, BP]
+        L.ko_subsample_skip.restype = C.c_uint64
+        L.ko_subsample_skip.argtypes = [C.c_uint64, _u8p, _u64p, C.c_int, C.c_double, C.c_uint32, C.c_uint64, BP]
         L.ko_infer_errors.argtypes = [C.c_uint64, _u8p, _u64p, _u8p, C.c_int, BP, _i32p, _u8p]
         L.ko_find_trusted.argtypes = [C.c_uint64, _u8p, _u64p, _u8p, C.c_int, BP, _i32p, BP]
         L.ko_get_errors.argtypes = [C.c_uint64, _u8p, _u64p, _u8p, C.c_int, BP, _u8p, C.c_void_p]
@@ -126,8 +128,8 @@ class PortPipeline:
         self.k = k
         self.L = lib()
 
-    def subsample(self, sampled: PortBloom, alpha: float, seed: int) -> int:
-        return int(self.L.ko_subsample(self.rs.n, self.rs.seq, self.rs.off, self.k, alpha, seed, sampled.p))
+    def subsample(self, sampled: PortBloom, alpha: float, seed: int, skip: int = 0) -> int:
+        return int(self.L.ko_subsample_skip(self.rs.n, self.rs.seq, self.rs.off, self.k, alpha, seed, skip, sampled.p))
 
     def thresholds(self, sampled: PortBloom, alpha_num: float, alpha_den: float) -> np.ndarray:
         out = np.zeros(self.k + 1, dtype=np.int32)
