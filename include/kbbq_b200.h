@@ -84,6 +84,11 @@ double kbbq_effective_fpp(uint64_t table_bits, uint64_t inserted, uint32_t n_sal
 /* bloom::calculate_phit (bloom.cc:190-195) chained into covariateutils::calculate_thresholds (covariateutils.hh:71-85),
  * exactly as kbbq.cc:304-313; thresholds[k+1] */
 int kbbq_thresholds_from_fpr(double fpr, long double alpha, int k, int* thresholds);
+/* the two halves of the above on their own: bloom::calculate_phit and covariateutils::calculate_thresholds */
+int kbbq_phit(double fpr, long double alpha, long double* p);
+int kbbq_thresholds_from_p(int k, long double p, int* thresholds);
+/* minion::create_seed_seq().GenerateOne() (minion.hpp:337-408, kbbq.cc:268-270) for a given time() and getpid() */
+uint32_t kbbq_default_seed(uint64_t time_now, uint32_t pid);
 /* minion::Random::Seed(uint32) state (minion.hpp:355-375) advanced by `skip` draws */
 int kbbq_rng_state(uint32_t seed, uint64_t skip, uint64_t state[4]);
 /* CCovariateData::get_dqs (covariateutils.cc:204-230) on dense tables */

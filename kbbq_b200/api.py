@@ -62,6 +62,10 @@ def lib():
         L.kbbq_effective_fpp.argtypes = [u64, u64, u32]
         L.kbbq_thresholds_from_fpr.argtypes = [dbl, C.c_longdouble, i32, vp]
         L.kbbq_rng_state.argtypes = [u32, u64, vp]
+        L.kbbq_phit.argtypes = [dbl, C.c_longdouble, C.POINTER(C.c_longdouble)]
+        L.kbbq_thresholds_from_p.argtypes = [i32, C.c_longdouble, vp]
+        L.kbbq_default_seed.restype = u32
+        L.kbbq_default_seed.argtypes = [u64, u32]
         L.kbbq_fit_model_host.argtypes = [i32, i32] + [vp] * 9
         L.kbbq_pack_size.argtypes = [u64, vp, C.POINTER(u64), C.POINTER(u32)]
         L.kbbq_pack_reads.argtypes = [u64] + [vp] * 8 + [i32]

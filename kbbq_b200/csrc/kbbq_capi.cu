@@ -217,6 +217,20 @@ int kbbq_thresholds_from_fpr(double fpr, long double alpha, int k, int* threshol
     return KBBQ_OK;
 }
 
+int kbbq_phit(double fpr, long double alpha, long double* p) {
+    if (!p) return fail(KBBQ_EINVAL, "null output");
+    *p = host::calculate_phit(fpr, alpha);
+    return KBBQ_OK;
+}
+
+int kbbq_thresholds_from_p(int k, long double p, int* thresholds) {
+    if (!thresholds || k < 1 || k > KBBQ_MAX_K) return fail(KBBQ_EINVAL, "k must be in 1..32");
+    host::calculate_thresholds(k, p, thresholds);
+    return KBBQ_OK;
+}
+
+uint32_t kbbq_default_seed(uint64_t time_now, uint32_t pid) { return host::default_seed(time_now, pid); }
+
 int kbbq_rng_state(uint32_t seed, uint64_t skip, uint64_t state[4]) {
     host::Xoshiro256ss r;
     r.seed(seed);

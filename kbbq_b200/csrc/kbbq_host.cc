@@ -71,6 +71,17 @@ void Xoshiro256ss::seed(uint32_t seed) {
     for (int i = 0; i < 256; ++i) next();
 }
 
+uint32_t default_seed(uint64_t time_now, uint32_t pid) {
+    // create_seed_seq: {time lo, time hi, pid, 0xC8F978DB, 0x0B32F62E} (the __cpluscplus typo in minion.hpp:385 disables
+    // the chrono / random_device branch); GenerateOne hashes the single word 0xFD57D105 with it
+    const uint32_t seq[5] = {(uint32_t)time_now, (uint32_t)(time_now >> 32), pid, 0xC8F978DBu, 0x0B32F62Eu};
+    uint64_t st = 0xFD57D105u;
+    uint64_t sum = splitmix64(st);
+    for (uint32_t u : seq) sum += splitmix64(st) * u;
+    sum += splitmix64(st);
+    return (uint32_t)(sum >> 32);
+}
+
 static void matvec(const uint64_t* cols, const uint64_t in[4], uint64_t out[4]) {
     uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (int w = 0; w < 4; ++w) {

@@ -45,6 +45,8 @@ struct Xoshiro256ss {
     uint64_t next();
     void seed(uint32_t seed);  // Random::Seed(uint32_t)
 };
+// minion::create_seed_seq().GenerateOne(): time, pid and two fixed words hashed by SeedSeq32 (minion.hpp:337-408)
+uint32_t default_seed(uint64_t time_now, uint32_t pid);
 // The state transition is linear over GF(2).  jump_pow2[e] is the matrix of 2^e steps, stored as 256 columns of
 // 4 words (column c = image of state bit c).  Built once per process.
 struct JumpTables {

@@ -1,0 +1,170 @@
+// kbbq_cli.cc -- the kbbq command line over the B200 hot path.
+//
+// Same options, same order of operations and the same stderr lines as the reference's main()
+// (src/kbbq/kbbq.cc:81-459); the pass calls are the reference's own four, now backed by kernels.  Added: --seed,
+// because the reference seeds from time()+getpid() (kbbq.cc:268-270) and cannot be reproduced otherwise.
+// Differences a user can see: the input is read once instead of five times; FASTQ (plain/gzip) only -- BAM/CRAM
+// need htslib, which this image does not have.
+#include <getopt.h>
+#include <unistd.h>
+
+#include <ctime>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+
+#include "kbbq_host_api.hh"
+
+namespace recalibrateutils {
+covariateutils::CCovariateData download_covariates(kbbq::Session& ses, int R, int C);
+}
+
+static std::ostream& put_now(std::ostream& os) {
+    std::time_t t = std::time(nullptr);
+    std::tm tm = *std::localtime(&t);
+    return os << std::put_time(&tm, "[%F %T %Z]");
+}
+
+static struct option long_options[] = {
+    {"ksize", required_argument, 0, 'k'},   {"use-oq", no_argument, 0, 'u'},        {"set-oq", no_argument, 0, 's'},
+    {"genomelen", required_argument, 0, 'g'}, {"coverage", required_argument, 0, 'c'}, {"fixed", required_argument, 0, 'f'},
+    {"alpha", required_argument, 0, 'a'},   {"threads", required_argument, 0, 't'}, {"seed", required_argument, 0, 'S'},
+    {0, 0, 0, 0}};
+
+int main(int argc, char* argv[]) {
+    int k = 32;
+    long double alpha = 0;
+    uint64_t genomelen = 0;
+    unsigned int coverage = 0;
+    uint32_t seed = 0;
+    int nthreads = 0;
+    std::string fixedinput = "";
+    int opt = 0, opt_idx = 0;
+    while ((opt = getopt_long(argc, argv, "k:usg:c:f:a:t:S:", long_options, &opt_idx)) != -1) {
+        switch (opt) {
+        case 'k':
+            k = std::stoi(std::string(optarg));
+            if (k <= 0 || k > KBBQ_MAX_KMER) {
+                std::cerr << put_now << "  Error: k must be <= " << KBBQ_MAX_KMER << " and > 0." << std::endl;
+                return 1;  // the reference prints and carries on into undefined behaviour
+            }
+            break;
+        case 'u': case 's':
+            std::cerr << put_now << " Warning: --use-oq/--set-oq only apply to BAM input." << std::endl;
+            break;
+        case 'g': genomelen = std::stoull(std::string(optarg)); break;
+        case 'c': coverage = std::stoul(std::string(optarg)); break;
+        case 'f': fixedinput = std::string(optarg); break;
+        case 'a': alpha = std::stold(std::string(optarg)); break;
+        case 't':
+            nthreads = std::stoi(std::string(optarg));
+            if (nthreads < 0) std::cerr << put_now << " Error: threads must be >= 0." << std::endl;
+            break;
+        case 'S': seed = (uint32_t)std::stoul(std::string(optarg)); break;
+        case '?':
+        default:
+            std::cerr << put_now << "  Unknown argument " << (char)opt << std::endl;
+            return 1;
+        }
+    }
+    std::string filename("-");
+    if (optind < argc) {
+        filename = std::string(argv[optind]);
+        while (++optind < argc) std::cerr << put_now << " Warning: Extra argument " << argv[optind] << " ignored." << std::endl;
+    }
+    long double sampler_desiredfpr = 0.01;    // Lighter uses .01
+    long double trusted_desiredfpr = 0.0005;  // and .0005
+
+    try {
+        // the one parse of the input (the reference re-opens the file for every pass, kbbq.cc:232,258,336,365,456)
+        std::unique_ptr<htsiter::FastqFile> file(new htsiter::FastqFile(filename, nthreads));
+        const kbbq::ReadStore& store = file->store();
+        if (store.n() == 0) {
+            std::cerr << put_now << " Error: total sequence length in file " << filename << " is 0. Check that the file isn't empty." << std::endl;
+            return 1;
+        }
+        const int n_rg = (int)std::max<size_t>(1, readutils::CReadData::rg_to_int.size());
+        kbbq::Session session(k, n_rg, (int)std::max<uint32_t>(1, store.max_len));
+        covariateutils::CCovariateData data;
+
+        if (fixedinput == "") {
+            if (genomelen == 0) {
+                std::cerr << put_now << " Error: --genomelen must be specified if input is not a bam." << std::endl;
+                return 1;
+            }
+            if (alpha == 0) {
+                std::cerr << put_now << " Estimating alpha." << std::endl;
+                if (coverage == 0) {
+                    std::cerr << put_now << " Estimating coverage." << std::endl;
+                    uint64_t seqlen = store.off.back();  // sum of sequence lengths (kbbq.cc:234-236)
+                    std::cerr << put_now << " Total Sequence length: " << seqlen << std::endl;
+                    std::cerr << put_now << " Genome length: " << genomelen << std::endl;
+                    coverage = seqlen / genomelen;
+                    std::cerr << put_now << " Estimated coverage: " << coverage << std::endl;
+                    if (coverage == 0) {
+                        std::cerr << put_now << " Error: estimated coverage is 0." << std::endl;
+                        return 1;
+                    }
+                }
+                alpha = 7.0l / (long double)coverage;
+            }
+            if (coverage == 0) coverage = 7.0l / alpha;
+            std::cerr << put_now << " Sampling kmers at rate " << alpha << std::endl;
+            unsigned long long int approx_kmers = genomelen * coverage * alpha;
+            bloom::Bloom subsampled(approx_kmers, sampler_desiredfpr);
+            bloom::Bloom trusted(approx_kmers, trusted_desiredfpr);
+            if (seed == 0) seed = kbbq_default_seed((uint64_t)time(nullptr), (uint32_t)getpid());
+            std::cerr << put_now << " Seed: " << seed << std::endl;
+
+            htsiter::KmerSubsampler subsampler(file.get(), k, alpha, seed);
+            recalibrateutils::subsample_kmers(subsampler, subsampled);
+            std::cerr << put_now << " Sampled " << subsampled.inserted_elements() << " valid kmers." << std::endl;
+
+            long double fpr = subsampled.fprate();
+            std::cerr << put_now << " Approximate false positive rate: " << fpr << std::endl;
+            if (fpr > .15) {
+                std::cerr << put_now << " Error: false positive rate is too high. Increase genomelen parameter and try again." << std::endl;
+                return 1;
+            }
+            long double p = bloom::calculate_phit(subsampled, alpha);
+            std::vector<int> thresholds = covariateutils::calculate_thresholds(k, p);
+
+            std::cerr << put_now << " Finding trusted kmers" << std::endl;
+            recalibrateutils::find_trusted_kmers(file.get(), trusted, subsampled, thresholds, k);
+            std::cerr << put_now << " Finding errors" << std::endl;
+            data = recalibrateutils::get_covariatedata(file.get(), trusted, k);
+        } else {
+            // --fixed: a base is an error when it differs from the same base of the pre-corrected file (kbbq.cc:367-378)
+            std::cerr << put_now << " Using fixed file to find errors." << std::endl;
+            auto saved_int = readutils::CReadData::rg_to_int;
+            auto saved_pu = readutils::CReadData::rg_to_pu;
+            std::unique_ptr<htsiter::FastqFile> fixedfile(new htsiter::FastqFile(fixedinput, nthreads));
+            readutils::CReadData::rg_to_int = saved_int;
+            readutils::CReadData::rg_to_pu = saved_pu;
+            const kbbq::ReadStore& fx = fixedfile->store();
+            session.ensure_resident(store);
+            for (size_t b = 0; b < session.batches().size(); ++b) {
+                std::vector<uint32_t> bits(std::max<uint64_t>(session.n_words(b), 1), 0);
+                const size_t first = session.batch_ranges()[b].first;
+                for (size_t i = first; i < session.batch_ranges()[b].second && i < fx.n(); ++i) {
+                    const size_t L = store.off[i + 1] - store.off[i];
+                    const uint32_t wo = session.word_off(b)[i - first];
+                    for (size_t j = 0; j < L; ++j)
+                        if (store.seq[store.off[i] + j] != fx.seq[fx.off[i] + j]) bits[wo + (j >> 5)] |= 1u << (j & 31);
+                }
+                if (kbbq_consume_errors(session.ctx(), session.batches()[b], bits.data()) != KBBQ_OK) kbbq::throw_last(-3);
+            }
+            data = recalibrateutils::download_covariates(session, n_rg, (int)std::max<uint32_t>(1, store.max_len));
+        }
+
+        std::cerr << put_now << " Training model" << std::endl;
+        covariateutils::dq_t dqs = data.get_dqs();
+        std::cerr << put_now << " Recalibrating file" << std::endl;
+        recalibrateutils::recalibrate_and_write(file.get(), dqs, "-");
+    } catch (const std::exception& e) {
+        std::cerr << put_now << " Error: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

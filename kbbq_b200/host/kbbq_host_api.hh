@@ -1,0 +1,220 @@
+// kbbq_host_api.hh -- C++ host mirror of the reference's library surface for the hot path, over the C ABI.
+//
+// Same namespaces, names, argument meaning and error behaviour as the reference's headers
+// (include/kbbq/{bloom,htsiter,readutils,covariateutils,recalibrateutils}.hh), so that the reference's main()
+// (src/kbbq/kbbq.cc:229-457) -- reproduced in kbbq_cli.cc -- reads the same.  What differs is where work happens:
+// the input is parsed ONCE into packed batches that stay resident in HBM (the reference re-opens and re-parses the
+// file for each of its five passes), and the four pass drivers launch the sm_100a kernels through
+// include/kbbq_b200.h instead of looping over records.  There is no CPU fallback: without a GPU the Session
+// constructor throws.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kbbq_b200.h"
+
+#define KBBQ_MAX_KMER 32
+#define KBBQ_MAXQ 93
+#define INFER_ERROR_BAD_QUAL 2
+
+namespace kbbq {
+
+// Everything parsed from the input, kept for all passes: the reference's per-record kseq_t / CReadData, columnar.
+struct ReadStore {
+    std::string path;
+    std::vector<char> names, comments, seq;  // concatenated, no terminators
+    std::vector<uint8_t> qual;               // phred
+    std::vector<uint64_t> name_off, comment_off, off;  // n+1 each
+    std::vector<uint16_t> rg;
+    std::vector<uint8_t> second;
+    size_t n() const { return off.empty() ? 0 : off.size() - 1; }
+    uint32_t max_len = 0;
+};
+
+// One GPU context plus the resident batches of one input.
+class Session {
+public:
+    Session(int k, int n_rg, int max_cycle, int device = 0);
+    ~Session();
+    Session(const Session&) = delete;
+    kbbq_ctx* ctx() const { return ctx_; }
+    int k() const { return k_; }
+    // pack + upload the store once; later calls are no-ops
+    void ensure_resident(const ReadStore& rs);
+    const std::vector<kbbq_dbatch*>& batches() const { return batches_; }
+    const std::vector<std::pair<size_t, size_t>>& batch_ranges() const { return ranges_; }
+    const std::vector<uint32_t>& word_off(size_t b) const { return word_off_[b]; }
+    uint64_t n_words(size_t b) const { return n_words_[b]; }
+    static Session& current();           // the session the mirror classes use
+    static void set_current(Session* s);
+    int next_filter_slot() { return next_slot_++; }
+
+private:
+    kbbq_ctx* ctx_ = nullptr;
+    int k_;
+    const ReadStore* resident_ = nullptr;
+    std::vector<kbbq_dbatch*> batches_;
+    std::vector<std::pair<size_t, size_t>> ranges_;
+    std::vector<std::vector<uint32_t>> word_off_;
+    std::vector<uint64_t> n_words_;
+    int next_slot_ = 0;
+};
+
+[[noreturn]] void throw_last(int rc);  // maps KBBQ_E* to the reference's exception types
+
+}  // namespace kbbq
+
+namespace bloom {
+
+// bloom::Kmer (bloom.hh:339-379): kept for API compatibility; the kernels never roll a k-mer
+class Kmer {
+    size_t s;
+    int k;
+    uint64_t x[2], mask, shift;
+
+public:
+    explicit Kmer(int k_) : s(0), k(k_), mask(k_ < 32 ? (1ULL << k_ * 2) - 1 : ~0ULL), shift((k_ - 1) * 2) { x[0] = x[1] = 0; }
+    size_t push_back(char ch);
+    uint64_t get() const { return x[0] < x[1] ? x[0] : x[1]; }
+    void reset() { s = 0; x[0] = x[1] = 0; }
+    size_t size() const { return s; }
+    bool valid() const { return s >= (size_t)k; }
+    int ksize() const { return k; }
+    explicit operator bool() const { return valid(); }
+};
+
+// bloom::Bloom (bloom.hh:385-402) living in HBM
+class Bloom {
+public:
+    Bloom(unsigned long long projected_element_count, double fpr, unsigned long long seed = KBBQ_DEFAULT_BLOOM_SEED);
+    Bloom(Bloom&&) noexcept = default;
+    kbbq_bloom_geom params;  // geometry the reference keeps in params / bloom
+    void insert(const Kmer& kmer);
+    bool query(const Kmer& kmer) const;
+    double fprate() const;
+    unsigned long long inserted_elements() const;
+    int slot() const { return slot_; }
+
+private:
+    int slot_;
+};
+
+long double calculate_phit(const Bloom& bf, long double alpha);  // bloom.cc:190-195
+
+}  // namespace bloom
+
+namespace covariateutils {
+
+typedef std::vector<int> meanq_t;
+typedef std::vector<int> rgdq_t;
+typedef std::vector<std::vector<int>> qscoredq_t;
+typedef std::vector<std::vector<std::array<std::vector<int>, 2>>> cycledq_t;
+typedef std::vector<std::vector<std::vector<int>>> dinucdq_t;
+struct dq_t {  // covariateutils.hh:27-34
+    meanq_t meanq;
+    rgdq_t rgdq;
+    qscoredq_t qscoredq;
+    cycledq_t cycledq;
+    dinucdq_t dinucdq;
+};
+typedef std::array<unsigned long long, 2> covariate_t;
+typedef std::vector<covariate_t> CCovariate;
+
+// covariateutils.hh:157-172; the tables are filled by the pass-3 kernel and downloaded
+class CCovariateData {
+public:
+    std::vector<covariate_t> rgcov;                                      // [rg]
+    std::vector<CCovariate> qcov;                                        // [rg][q]
+    std::vector<std::vector<std::array<CCovariate, 2>>> cycov;           // [rg][q][second][cycle]
+    std::vector<std::vector<CCovariate>> dicov;                          // [rg][q][dinuc]
+    dq_t get_dqs();  // covariateutils.cc:204-230, host long double
+    // dense images (layout of include/kbbq_b200.h), kept so get_dqs feeds the fit without re-densifying
+    int n_rg = 0, max_cycle = 0;
+    std::vector<uint64_t> d_rgc, d_qc, d_cyc, d_dic;
+};
+
+std::vector<int> calculate_thresholds(unsigned long long k, long double p, long double quartile = .995l);  // covariateutils.hh:71-85
+
+}  // namespace covariateutils
+
+namespace readutils {
+// the slice of CReadData (readutils.hh:44-74) that callers of the pass drivers look at
+class CReadData {
+public:
+    static std::unordered_map<std::string, std::string> rg_to_pu;
+    static std::unordered_map<std::string, int> rg_to_int;
+    std::string seq, name, rg;
+    std::vector<uint8_t> qual;
+    std::vector<bool> skips, errors;
+    bool second = false;
+    int get_rg_int() const { return rg_to_int[rg]; }
+};
+}  // namespace readutils
+
+namespace htsiter {
+
+// htsiter::HTSFile (htsiter.hh:40-49)
+class HTSFile {
+public:
+    virtual ~HTSFile() {}
+    virtual int next() = 0;
+    virtual std::string next_str() = 0;
+    virtual readutils::CReadData get() = 0;
+    virtual void recalibrate(const std::vector<uint8_t>& qual) = 0;
+    virtual int open_out(std::string filename) = 0;
+    virtual int write() = 0;
+    virtual const kbbq::ReadStore& store() const = 0;  // mirror-only: the parsed input behind the iterator
+};
+
+// htsiter::FastqFile (htsiter.hh:101-126): FASTQ, plain or gzip
+class FastqFile : public HTSFile {
+public:
+    explicit FastqFile(std::string filename, int nthreads = 0);
+    ~FastqFile() override;
+    int next() override;
+    std::string next_str() override;
+    readutils::CReadData get() override;
+    void recalibrate(const std::vector<uint8_t>& qual) override;
+    int open_out(std::string filename) override;
+    int write() override;
+    const kbbq::ReadStore& store() const override { return *store_; }
+    // mirror-only: write every record with new qualities (layout of kbbq_batch.qual per batch), in input order
+    int write_all(const kbbq::Session& s, const std::vector<std::vector<uint8_t>>& newq);
+
+private:
+    std::shared_ptr<kbbq::ReadStore> store_;
+    size_t cur_ = 0;  // index of the NEXT record
+    std::vector<uint8_t> cur_qual_;
+    void* out_ = nullptr;  // FILE*: gzip members are written raw
+    std::string pending_;  // records waiting to become the next gzip member
+    int nthreads_;
+    int flush_pending();
+};
+
+// htsiter::KmerSubsampler (htsiter.hh:128-156): carries file, k, alpha, seed to subsample_kmers
+class KmerSubsampler {
+public:
+    HTSFile* file;
+    int k;
+    double alpha;
+    uint64_t seed;
+    size_t total_kmers = 0;
+    bool not_eof = true;
+    KmerSubsampler(HTSFile* file_, int k_, double alpha_, uint64_t seed_);
+};
+
+}  // namespace htsiter
+
+namespace recalibrateutils {
+// recalibrateutils.hh:29-44
+void subsample_kmers(htsiter::KmerSubsampler& s, bloom::Bloom& sampled);
+void find_trusted_kmers(htsiter::HTSFile* file, bloom::Bloom& trusted, const bloom::Bloom& sampled, std::vector<int> thresholds, int k);
+covariateutils::CCovariateData get_covariatedata(htsiter::HTSFile* file, const bloom::Bloom& trusted, int k);
+void recalibrate_and_write(htsiter::HTSFile* in, const covariateutils::dq_t& dqs, std::string outfn);
+inline long double q_to_p(int q);
+}  // namespace recalibrateutils

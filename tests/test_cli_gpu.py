@@ -1,0 +1,70 @@
+"""End to end through the C++ host mirror and the kbbq CLI (kbbq_b200/host): the recalibrated FASTQ must be byte for
+byte the reference CLI's (oracle/_ref/kbbq_ref run with its seed pinned; outputs committed under tests/golden/)."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "kbbq_b200", "host", "kbbq")
+GOLD = os.path.join(ROOT, "tests", "golden")
+pytestmark = pytest.mark.gpu
+
+
+def _gunzip_to(src, dst):
+    with gzip.open(src) as f, open(dst, "wb") as o:
+        o.write(f.read())
+
+
+def _run(args, tmp_path):
+    out = tmp_path / "out.gz"
+    with open(out, "wb") as fo:
+        r = subprocess.run([CLI] + args, stdout=fo, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    return gzip.open(out).read(), r.stderr.decode()
+
+
+def test_cli_matches_reference_cli(tmp_path):
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-C", os.path.dirname(CLI)])
+    fq = str(tmp_path / "in.fq")
+    _gunzip_to(os.path.join(GOLD, "cli_in.fq.gz"), fq)
+    got, log = _run(["--seed", "2854027472", "-k", "31", "-g", "4000", "-c", "25", fq], tmp_path)
+    want = gzip.open(os.path.join(GOLD, "cli_out.fq.gz")).read()
+    assert "Seed: 2854027472" in log and "Sampled 20870 valid kmers." in log
+    assert got == want
+    # gzip input gives the same answer (the reference reads FASTQ through BGZF either way)
+    got2, _ = _run(["--seed", "2854027472", "-k", "31", "-g", "4000", "-c", "25", os.path.join(GOLD, "cli_in.fq.gz")], tmp_path)
+    assert got2 == want
+    # coverage estimated by the extra pass (kbbq.cc:229-250): 666*150/4000 = 24 != 25, so the output differs from -c 25
+    got3, log3 = _run(["--seed", "2854027472", "-k", "31", "-g", "4000", fq], tmp_path)
+    assert "Estimated coverage: 24" in log3
+
+
+def test_cli_fixed_mode_matches_reference_cli(tmp_path):
+    fq, fx = str(tmp_path / "in.fq"), str(tmp_path / "fixed.fq")
+    _gunzip_to(os.path.join(GOLD, "cli_in.fq.gz"), fq)
+    _gunzip_to(os.path.join(GOLD, "cli_fixed.fq.gz"), fx)
+    got, _ = _run(["-k", "31", "-f", fx, fq], tmp_path)
+    assert got == gzip.open(os.path.join(GOLD, "cli_fixed_out.fq.gz")).read()
+
+
+def test_cli_against_live_reference_cli(tmp_path):
+    """Where the prebuilt reference CLI travelled with the repo: a fresh, larger input through both binaries."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/kbbq_ref not present")
+    import sys
+    sys.path.insert(0, ROOT)
+    from kbbq_b200 import synth
+
+    rs = synth.make_reads(100000, 20, 100, seed=77, n_rg=3, n_frac=0.001)
+    fq = str(tmp_path / "big.fq")
+    synth.to_fastq(rs, fq)
+    args = ["-k", "32", "-g", "100000", "-c", "20", fq]
+    with open(tmp_path / "ref.gz", "wb") as fo:
+        r = subprocess.run([ref] + args, stdout=fo, stderr=subprocess.PIPE)
+    assert r.returncode == 0
+    got, _ = _run(["--seed", "2854027472"] + args, tmp_path)
+    assert got == gzip.open(tmp_path / "ref.gz").read()
