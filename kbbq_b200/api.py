@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkbbq_b200.so")
+LIB_PATH = os.environ.get("KBBQ_B200_LIB", os.path.join(_HERE, "libkbbq_b200.so"))  # override: kernel experiments
 
 FILTER_SAMPLED = 0
 FILTER_TRUSTED = 1

@@ -334,6 +334,14 @@ int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) 
     c->max_cycle = max_cycle;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // batch buffers come from the stream-ordered pool and stay cached in it: cudaMalloc/cudaFree of hundreds of MB
+        // per batch cost up to a second each on this driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     c->n_rgc = (size_t)n_rg * 2;
@@ -530,13 +538,12 @@ int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other, uint64_t fir
 // ---- batches -------------------------------------------------------------------------------------------------------
 void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (!b) return;
-    if (ctx) {
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-    }
-    cudaFree(b->d_bases); cudaFree(b->d_nmask); cudaFree(b->d_qual); cudaFree(b->d_word_off); cudaFree(b->d_len);
-    cudaFree(b->d_rg); cudaFree(b->d_second); cudaFree(b->d_slot_off); cudaFree(b->d_sample_bits);
-    cudaFree(b->d_err_bits); cudaFree(b->d_newqual);
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx ? ctx->stream : nullptr;
+    void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
+                    b->d_sample_bits, b->d_err_bits, b->d_newqual};
+    for (void* p : ptrs)
+        if (p) cudaFreeAsync(p, st);
     delete b;
 }
 
@@ -562,7 +569,7 @@ int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) {
     const size_t nw = std::max<uint64_t>(h->n_words, 1);
 #define UP(dst, src, bytes)                                                                   \
     do {                                                                                      \
-        cudaError_t e1 = cudaMalloc(&(dst), std::max<size_t>((bytes), 16));                   \
+        cudaError_t e1 = cudaMallocAsync(&(dst), std::max<size_t>((bytes), 16), ctx->stream); \
         if (e1 == cudaSuccess && (src) && (bytes))                                            \
             e1 = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream); \
         else if (e1 == cudaSuccess)                                                           \
@@ -628,7 +635,7 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
     pass_begin(ctx);
     if (b->n_slots) {
         const uint64_t chunks = (b->n_slots + 1023) / 1024;
-        if (!b->d_sample_bits) CU(cudaMalloc(&b->d_sample_bits, chunks * 32 * 4));
+        if (!b->d_sample_bits) CU(cudaMallocAsync(&b->d_sample_bits, chunks * 32 * 4, ctx->stream));
         uint64_t st[4];
         std::memcpy(st, ctx->sampler_state0, 32);
         host::rng_advance(st, ctx->sampler_pos);
@@ -680,7 +687,7 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
     kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
     if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
     if (err_bits && !b->d_err_bits) {
-        CU(cudaMalloc(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4));
+        CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     }
     if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     pass_begin(ctx);
@@ -700,7 +707,7 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
     if (int rc = filter_ok(ctx, KBBQ_FILTER_TRUSTED)) return rc;
     kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
     if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
-    if (err_bits && !b->d_err_bits) CU(cudaMalloc(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4));
+    if (err_bits && !b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     pass_begin(ctx);
     if (b->n_reads) {
@@ -718,7 +725,7 @@ int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* er
     if (int rc = use(ctx)) return rc;
     kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
     if (!b || !err_bits) return fail(KBBQ_EINVAL, "null argument");
-    if (!b->d_err_bits) CU(cudaMalloc(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4));
+    if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     if (b->n_words) CU(cudaMemcpyAsync(b->d_err_bits, err_bits, b->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     pass_begin(ctx);
     if (b->n_reads) {
@@ -803,7 +810,7 @@ int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_o
     kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
     if (!b) return fail(KBBQ_EINVAL, "null batch");
     if (!b->d_newqual) {
-        CU(cudaMalloc(&b->d_newqual, std::max<size_t>((size_t)b->n_words * 32, 16)));
+        CU(cudaMallocAsync(&b->d_newqual, std::max<size_t>((size_t)b->n_words * 32, 16), ctx->stream));
         CU(cudaMemsetAsync(b->d_newqual, 0, std::max<size_t>((size_t)b->n_words * 32, 16), ctx->stream));
     }
     pass_begin(ctx);

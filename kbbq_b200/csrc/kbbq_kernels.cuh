@@ -401,7 +401,11 @@ struct DevQuery {
     }
 };
 
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32)
+// 4 blocks/SM = 64 registers, 32 warps/SM: measured 21.2 ms vs 23.0 (unbounded, 80 regs) and 23.8 (5 blocks, spills)
+#ifndef KBBQ_P3_MIN_BLOCKS
+#define KBBQ_P3_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
 pass3_errors_kernel(BatchView b, BloomView trusted, CountView cv, int k, uint32_t* __restrict__ err_out, int do_consume,
                     unsigned int* __restrict__ work_counter) {
     __shared__ ErrScratch scratch[KBBQ_WARPS_PER_BLOCK];
