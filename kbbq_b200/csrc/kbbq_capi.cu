@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -71,6 +72,8 @@ struct kbbq_ctx {
     uint64_t sampler_state0[4] = {0, 0, 0, 0};  // state right after Seed()
     uint64_t sampler_pos = 0;
     double alpha = 0;
+    unsigned long long sample_threshold = 0;  // draw x is sampled iff take_all or x < threshold (see kbbq_sampler_seed)
+    int sample_all = 0;
     unsigned long long* d_jump = nullptr;  // 26 matrices: 2^(10+b) steps
     // thresholds
     bool have_thresholds = false;
@@ -611,6 +614,26 @@ int kbbq_sampler_seed(kbbq_ctx* ctx, uint32_t seed, double alpha) {
     ctx->sampler_pos = 0;
     ctx->alpha = alpha;
     ctx->sampler_seeded = true;
+    {   // libstdc++'s bernoulli_distribution(p)(urng) on a 64-bit URBG: double(x) / 2^64, clamped below 1, < p.
+        // The predicate is monotone in x: find the smallest x for which it is false.
+        auto sampled = [alpha](unsigned long long x) {
+            double r = (double)x / 18446744073709551616.0;
+            if (r >= 1.0) r = std::nextafter(1.0, 0.0);
+            return r < alpha;
+        };
+        if (sampled(~0ull)) {
+            ctx->sample_all = 1;
+            ctx->sample_threshold = ~0ull;
+        } else {
+            unsigned long long lo = 0, hi = ~0ull;  // sampled(hi) is false; find the first false
+            while (lo < hi) {
+                const unsigned long long mid = lo + (hi - lo) / 2;
+                if (sampled(mid)) lo = mid + 1; else hi = mid;
+            }
+            ctx->sample_all = 0;
+            ctx->sample_threshold = lo;
+        }
+    }
     if (!ctx->d_jump) {
         const host::JumpTables& jt = host::jump_tables();
         CU(cudaMalloc(&ctx->d_jump, (size_t)26 * 1024 * 8));
@@ -640,7 +663,7 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
         std::memcpy(st, ctx->sampler_state0, 32);
         host::rng_advance(st, ctx->sampler_pos);
         rng_sample_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(st[0], st[1], st[2], st[3], ctx->d_jump,
-                                                                                     b->n_slots, ctx->alpha, b->d_sample_bits);
+                                                                                     b->n_slots, ctx->sample_threshold, ctx->sample_all, b->d_sample_bits);
         if (int rc = check_launch(ctx, "rng_sample_kernel")) return rc;
         pass1_insert_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
             b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);

@@ -191,8 +191,8 @@ __device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) 
 
 __global__ void __launch_bounds__(128) rng_sample_kernel(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3,
                                                          const unsigned long long* __restrict__ jump,
-                                                         unsigned long long n_slots, double p,
-                                                         uint32_t* __restrict__ bits) {
+                                                         unsigned long long n_slots, unsigned long long threshold,
+                                                         int take_all, uint32_t* __restrict__ bits) {
     const unsigned long long chunk = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long first = chunk * 1024ull;
     if (first >= n_slots) return;
@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(128) rng_sample_kernel(uint64_t s0, uint64_t s
             s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
             s[2] ^= t;
             s[3] = rotl64(s[3], 45);
-            // std::bernoulli_distribution: generate_canonical<double,53> = double(x)/2^64 (clamped below 1) < p
-            double r = __ull2double_rn(x) * 0x1p-64;  // exact scaling
-            if (r >= 1.0) r = 0x1.fffffffffffffp-1;  // nextafter(1, 0)
-            if (r < p && first + (unsigned)(w * 32 + i) < n_slots) word |= 1u << i;
+            // std::bernoulli_distribution: generate_canonical<double,53> = double(x)/2^64 (clamped below 1) < p.
+            // u64 -> double rounding is monotone, so the test is "x below a threshold" that the host found with the
+            // very same double arithmetic (kbbq_sampler_seed): one integer compare instead of an I2F + DMUL + DSETP.
+            if ((take_all || x < threshold) && first + (unsigned)(w * 32 + i) < n_slots) word |= 1u << i;
         }
         bits[chunk * 32 + w] = word;
     }

@@ -42,21 +42,31 @@ class Comm:
         return int(sum(int(o.item()) for o in out[: self.rank]))
 
     # ---- generic tensor merges (either backend) ---------------------------------------------------------------------
+    # elements per all-gather slice: bounds the staging buffer to world x 256 MiB whatever the filter size
+    # (the human-scale filters are 26 and 43 GB)
+    SLICE_ELEMS = 32 << 20
+
     def or_reduce_(self, words: torch.Tensor, or_into=None) -> None:
-        """words |= every other rank's words.  `or_into(dst_tensor, src_tensor)` performs dst |= src."""
+        """words |= every other rank's words, slice by slice.
+        `or_into(first_elem, n_elems, src_tensor)` performs words[first:first+n] |= src (this repo's kernel on GPUs)."""
         if self.world == 1:
             return
-        flat = words.contiguous().view(-1)
-        gathered = torch.empty(self.world * flat.numel(), dtype=words.dtype, device=words.device)
-        dist.all_gather_into_tensor(gathered, flat)
-        gathered = gathered.view(self.world, flat.numel())
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            if or_into is None:
-                words.bitwise_or_(gathered[r])
-            else:
-                or_into(words, gathered[r])
+        flat = words.view(-1)
+        n = flat.numel()
+        step = min(n, self.SLICE_ELEMS)
+        gathered = torch.empty(self.world * step, dtype=words.dtype, device=words.device)
+        for lo in range(0, n, step):
+            m = min(step, n - lo)
+            g = gathered[: self.world * m]
+            dist.all_gather_into_tensor(g, flat[lo : lo + m])
+            g = g.view(self.world, m)
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                if or_into is None:
+                    flat[lo : lo + m].bitwise_or_(g[r])
+                else:
+                    or_into(lo, m, g[r])
 
     def sum_reduce_(self, t: torch.Tensor) -> None:
         if self.world > 1:
@@ -72,9 +82,10 @@ class Comm:
         words = device_tensor(ctx.bloom_device_words(which), nbytes, ctx.device).view(torch.int64)
         counter = device_tensor(ctx.bloom_device_counter(which), 8, ctx.device).view(torch.int64)
 
-        def or_kernel(dst, src):
+        def or_kernel(first, n, src):
+            # src holds words [first, first+n) of a peer; kbbq_bloom_or_from indexes both sides by absolute word
             torch.cuda.current_stream().synchronize()
-            ctx.bloom_or_from(which, src.data_ptr(), 0, g.table_bits // 64)
+            ctx.bloom_or_from(which, src.data_ptr() - 8 * first, first, n)
             ctx.sync()
 
         self.or_reduce_(words, or_kernel)
