@@ -3,8 +3,8 @@
 // Same options, same order of operations and the same stderr lines as the reference's main()
 // (src/kbbq/kbbq.cc:81-459); the pass calls are the reference's own four, now backed by kernels.  Added: --seed,
 // because the reference seeds from time()+getpid() (kbbq.cc:268-270) and cannot be reproduced otherwise.
-// Differences a user can see: the input is read once instead of five times; FASTQ (plain/gzip) only -- BAM/CRAM
-// need htslib, which this image does not have.
+// Differences a user can see: the input is read once instead of five times; FASTQ (plain/gzip) and BAM are read by
+// this repo's own BGZF/BAM code (htslib is not in this image); CRAM is not supported.
 #include <getopt.h>
 #include <unistd.h>
 
@@ -40,6 +40,7 @@ int main(int argc, char* argv[]) {
     uint32_t seed = 0;
     int nthreads = 0;
     std::string fixedinput = "";
+    bool use_oq = false, set_oq = false;
     int opt = 0, opt_idx = 0;
     while ((opt = getopt_long(argc, argv, "k:usg:c:f:a:t:S:", long_options, &opt_idx)) != -1) {
         switch (opt) {
@@ -50,9 +51,8 @@ int main(int argc, char* argv[]) {
                 return 1;  // the reference prints and carries on into undefined behaviour
             }
             break;
-        case 'u': case 's':
-            std::cerr << put_now << " Warning: --use-oq/--set-oq only apply to BAM input." << std::endl;
-            break;
+        case 'u': use_oq = true; break;
+        case 's': set_oq = true; break;
         case 'g': genomelen = std::stoull(std::string(optarg)); break;
         case 'c': coverage = std::stoul(std::string(optarg)); break;
         case 'f': fixedinput = std::string(optarg); break;
@@ -78,7 +78,18 @@ int main(int argc, char* argv[]) {
 
     try {
         // the one parse of the input (the reference re-opens the file for every pass, kbbq.cc:232,258,336,365,456)
-        std::unique_ptr<htsiter::FastqFile> file(new htsiter::FastqFile(filename, nthreads));
+        bool is_bam = false;
+        try {
+            is_bam = htsiter::is_bam_file(filename);  // hts_detect_format (kbbq.cc:172-190)
+        } catch (const std::exception& e) {
+            std::cerr << put_now << " " << e.what() << std::endl;
+            return 1;
+        }
+        auto open_file = [&](const std::string& fn) -> std::unique_ptr<htsiter::StoreFile> {  // kbbq.cc:22-32
+            if (is_bam) return std::unique_ptr<htsiter::StoreFile>(new htsiter::BamFile(fn, nthreads, use_oq, set_oq));
+            return std::unique_ptr<htsiter::StoreFile>(new htsiter::FastqFile(fn, nthreads));
+        };
+        std::unique_ptr<htsiter::StoreFile> file = open_file(filename);
         const kbbq::ReadStore& store = file->store();
         if (store.n() == 0) {
             std::cerr << put_now << " Error: total sequence length in file " << filename << " is 0. Check that the file isn't empty." << std::endl;
@@ -90,8 +101,20 @@ int main(int argc, char* argv[]) {
 
         if (fixedinput == "") {
             if (genomelen == 0) {
-                std::cerr << put_now << " Error: --genomelen must be specified if input is not a bam." << std::endl;
-                return 1;
+                if (is_bam) {  // sum of the header's reference lengths (kbbq.cc:196-216)
+                    std::cerr << put_now << " Estimating genome length" << std::endl;
+                    for (uint64_t l : store.ref_len) genomelen += l;
+                    if (genomelen == 0) {
+                        std::cerr << put_now << " Header does not contain genome information."
+                                  << " Unable to estimate genome length; please provide it on the command line"
+                                  << " using the --genomelen option." << std::endl;
+                        return 1;
+                    }
+                    std::cerr << put_now << " Genome length is " << genomelen << " bp." << std::endl;
+                } else {
+                    std::cerr << put_now << " Error: --genomelen must be specified if input is not a bam." << std::endl;
+                    return 1;  // the reference carries on into a division by zero
+                }
             }
             if (alpha == 0) {
                 std::cerr << put_now << " Estimating alpha." << std::endl;
@@ -139,7 +162,7 @@ int main(int argc, char* argv[]) {
             std::cerr << put_now << " Using fixed file to find errors." << std::endl;
             auto saved_int = readutils::CReadData::rg_to_int;
             auto saved_pu = readutils::CReadData::rg_to_pu;
-            std::unique_ptr<htsiter::FastqFile> fixedfile(new htsiter::FastqFile(fixedinput, nthreads));
+            std::unique_ptr<htsiter::StoreFile> fixedfile = open_file(fixedinput);
             readutils::CReadData::rg_to_int = saved_int;
             readutils::CReadData::rg_to_pu = saved_pu;
             const kbbq::ReadStore& fx = fixedfile->store();

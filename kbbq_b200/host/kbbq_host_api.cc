@@ -285,93 +285,106 @@ static std::shared_ptr<kbbq::ReadStore> load_fastq(const std::string& filename) 
     return rs;
 }
 
-FastqFile::FastqFile(std::string filename, int nthreads) : store_(load_fastq(filename)), nthreads_(nthreads) {}
-FastqFile::~FastqFile() {
+FastqFile::FastqFile(std::string filename, int nthreads) : StoreFile(load_fastq(filename), nthreads) {}
+
+StoreFile::~StoreFile() {
     if (out_) {
-        flush_pending();
+        flush_pending(true);
         FILE* f = (FILE*)out_;
         if (f == stdout) fflush(f); else fclose(f);
     }
 }
-int FastqFile::next() {
+int StoreFile::next() {
     if (cur_ >= store_->n()) return -1;
     ++cur_;
     return (int)(store_->off[cur_] - store_->off[cur_ - 1]);
 }
-std::string FastqFile::next_str() {
+std::string StoreFile::next_str() {
     if (next() < 0) return "";
     return std::string(store_->seq.data() + store_->off[cur_ - 1], store_->seq.data() + store_->off[cur_]);
 }
-readutils::CReadData FastqFile::get() {
+readutils::CReadData StoreFile::get() {
     const size_t i = cur_ - 1;
     readutils::CReadData r;
     r.seq.assign(store_->seq.data() + store_->off[i], store_->seq.data() + store_->off[i + 1]);
     r.qual.assign(store_->qual.data() + store_->off[i], store_->qual.data() + store_->off[i + 1]);
     r.skips.assign(r.seq.size(), false);
     r.errors.assign(r.seq.size(), false);
-    std::string full(store_->names.data() + store_->name_off[i], store_->names.data() + store_->name_off[i + 1]);
-    r.name = full.substr(0, full.find('_'));
-    if (r.name.size() >= 2 && (r.name.substr(r.name.size() - 2) == "/1" || r.name.substr(r.name.size() - 2) == "/2"))
-        r.name = r.name.substr(0, r.name.size() - 2);
+    r.name.assign(store_->names.data() + store_->name_off[i], store_->names.data() + store_->name_off[i + 1]);
+    if (store_->bam_off.empty()) {  // FASTQ: first '_' field without its /1 or /2 (readutils.cc:74-97); BAM: the qname
+        r.name = r.name.substr(0, r.name.find('_'));
+        if (r.name.size() >= 2 && (r.name.substr(r.name.size() - 2) == "/1" || r.name.substr(r.name.size() - 2) == "/2"))
+            r.name = r.name.substr(0, r.name.size() - 2);
+    }
     for (auto& kv : readutils::CReadData::rg_to_int)
         if (kv.second == store_->rg[i]) r.rg = kv.first;
     r.second = store_->second[i];
     return r;
 }
-void FastqFile::recalibrate(const std::vector<uint8_t>& qual) { cur_qual_ = qual; }
-int FastqFile::open_out(std::string filename) {
+int StoreFile::open_out(std::string filename) {
     out_ = filename == "-" ? (void*)stdout : (void*)fopen(filename.c_str(), "wb");
-    return out_ == nullptr ? -1 : 0;
-}
-static void format_record(const kbbq::ReadStore& rs, size_t i, const uint8_t* q, std::string& s) {
-    // "@" + name + "\n" + seq + "\n+" + comment + "\n" + qual + "\n": the comment moves to the '+' line (htsiter.cc:84)
-    s.push_back('@');
-    s.append(rs.names.data() + rs.name_off[i], rs.names.data() + rs.name_off[i + 1]);
-    s.push_back('\n');
-    s.append(rs.seq.data() + rs.off[i], rs.seq.data() + rs.off[i + 1]);
-    s.append("\n+");
-    s.append(rs.comments.data() + rs.comment_off[i], rs.comments.data() + rs.comment_off[i + 1]);
-    s.push_back('\n');
-    const size_t L = rs.off[i + 1] - rs.off[i];
-    for (size_t j = 0; j < L; ++j) s.push_back((char)(q[j] + 33));
-    s.push_back('\n');
-}
-// The output is a sequence of gzip members (what BGZF is, minus the block index): members can be compressed by
-// independent threads and concatenated in input order; zlib/gzip/htslib read the result as one stream.
-static bool deflate_member(const std::string& in, std::string& out) {
-    z_stream zs;
-    std::memset(&zs, 0, sizeof zs);
-    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
-    out.resize(deflateBound(&zs, in.size()) + 64);
-    zs.next_in = (Bytef*)in.data();
-    zs.avail_in = (uInt)in.size();
-    zs.next_out = (Bytef*)out.data();
-    zs.avail_out = (uInt)out.size();
-    const int rc = deflate(&zs, Z_FINISH);
-    out.resize(zs.total_out);
-    deflateEnd(&zs);
-    return rc == Z_STREAM_END;
+    if (!out_) return -1;
+    format_header(pending_);
+    return 0;
 }
 
-int FastqFile::flush_pending() {
-    if (!out_ || pending_.empty()) return 0;
+// ---- BGZF: gzip members of <= 64 KiB with the "BC" extra field, closed by the empty EOF block --------------------
+static const size_t kBgzfInput = 0xff00;
+static bool bgzf_block(const char* in, size_t n, std::string& out) {
+    z_stream zs;
+    std::memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    const size_t start = out.size();
+    out.resize(start + 18 + deflateBound(&zs, n) + 8);
+    unsigned char* o = (unsigned char*)&out[start];
+    static const unsigned char head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    std::memcpy(o, head, 16);
+    zs.next_in = (Bytef*)in;
+    zs.avail_in = (uInt)n;
+    zs.next_out = o + 18;
+    zs.avail_out = (uInt)(out.size() - start - 18 - 8);
+    const int rc = deflate(&zs, Z_FINISH);
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    if (rc != Z_STREAM_END) return false;
+    const size_t bsize = 18 + clen + 8;
+    o[16] = (unsigned char)((bsize - 1) & 0xff);
+    o[17] = (unsigned char)((bsize - 1) >> 8);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)in, (uInt)n), isize = (uint32_t)n;
+    std::memcpy(o + 18 + clen, &crc, 4);
+    std::memcpy(o + 18 + clen + 4, &isize, 4);
+    out.resize(start + bsize);
+    return true;
+}
+static bool bgzf_compress(const std::string& in, std::string& out) {
+    for (size_t p = 0; p < in.size(); p += kBgzfInput)
+        if (!bgzf_block(in.data() + p, std::min(kBgzfInput, in.size() - p), out)) return false;
+    return true;
+}
+
+int StoreFile::flush_pending(bool final) {
+    if (!out_) return 0;
     std::string z;
-    if (!deflate_member(pending_, z)) return -1;
+    if (!pending_.empty() && !bgzf_compress(pending_, z)) return -1;
     pending_.clear();
+    if (final) {
+        static const unsigned char eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        z.append((const char*)eof, 28);
+    }
     return fwrite(z.data(), 1, z.size(), (FILE*)out_) == z.size() ? 0 : -1;
 }
 
-int FastqFile::write() {
+int StoreFile::write() {
     if (!out_) return -1;
     const size_t before = pending_.size();
-    format_record(*store_, cur_ - 1, cur_qual_.data(), pending_);
+    format_record(cur_ - 1, cur_qual_.data(), pending_);
     const int n = (int)(pending_.size() - before);
-    if (pending_.size() > (8u << 20) && flush_pending() < 0) return -1;
+    if (pending_.size() > (8u << 20) && flush_pending(false) < 0) return -1;
     return n;
 }
 
-int FastqFile::write_all(const kbbq::Session& ses, const std::vector<std::vector<uint8_t>>& newq) {
-    if (!out_ || flush_pending() < 0) return -1;
+int StoreFile::write_all(const kbbq::Session& ses, const std::vector<std::vector<uint8_t>>& newq) {
+    if (!out_ || flush_pending(false) < 0) return -1;
     const kbbq::ReadStore& rs = *store_;
     const size_t chunk = 1u << 15;
     const int nt = (int)std::max(1u, nthreads_ > 0 ? (unsigned)nthreads_ : std::min(16u, std::thread::hardware_concurrency()));
@@ -392,10 +405,11 @@ int FastqFile::write_all(const kbbq::Session& ses, const std::vector<std::vector
                 for (size_t j = j0 + t; j < j1; j += nt) {
                     const Job& jb = jobs[j];
                     text.clear();
+                    outs[j - j0].clear();
                     const size_t first = ses.batch_ranges()[jb.b].first;
                     for (size_t i = jb.lo; i < jb.hi; ++i)
-                        format_record(rs, i, newq[jb.b].data() + (size_t)ses.word_off(jb.b)[i - first] * 32, text);
-                    if (!deflate_member(text, outs[j - j0])) ok[t] = 0;
+                        format_record(i, newq[jb.b].data() + (size_t)ses.word_off(jb.b)[i - first] * 32, text);
+                    if (!bgzf_compress(text, outs[j - j0])) ok[t] = 0;
                 }
             });
         for (auto& t : th) t.join();
@@ -406,6 +420,203 @@ int FastqFile::write_all(const kbbq::Session& ses, const std::vector<std::vector
     }
     cur_ = rs.n();
     return 0;
+}
+
+void FastqFile::format_record(size_t i, const uint8_t* q, std::string& s) const {
+    // "@" + name + "\n" + seq + "\n+" + comment + "\n" + qual + "\n": the comment moves to the '+' line (htsiter.cc:84)
+    const kbbq::ReadStore& rs = *store_;
+    s.push_back('@');
+    s.append(rs.names.data() + rs.name_off[i], rs.names.data() + rs.name_off[i + 1]);
+    s.push_back('\n');
+    s.append(rs.seq.data() + rs.off[i], rs.seq.data() + rs.off[i + 1]);
+    s.append("\n+");
+    s.append(rs.comments.data() + rs.comment_off[i], rs.comments.data() + rs.comment_off[i + 1]);
+    s.push_back('\n');
+    const size_t L = rs.off[i + 1] - rs.off[i];
+    for (size_t j = 0; j < L; ++j) s.push_back((char)(q[j] + 33));
+    s.push_back('\n');
+}
+
+// ---- BAM ---------------------------------------------------------------------------------------------------------------
+static std::vector<uint8_t> gunzip_all(const std::string& filename) {
+    gzFile gz = filename == "-" ? gzdopen(0, "rb") : gzopen(filename.c_str(), "rb");
+    if (!gz) throw std::runtime_error("Error opening file " + filename);
+    gzbuffer(gz, 1 << 22);
+    std::vector<uint8_t> data;
+    std::vector<uint8_t> buf(1 << 24);
+    int got;
+    while ((got = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.insert(data.end(), buf.begin(), buf.begin() + got);
+    gzclose(gz);
+    return data;
+}
+
+bool is_bam_file(const std::string& filename) {
+    gzFile gz = gzopen(filename.c_str(), "rb");
+    if (!gz) throw std::runtime_error("Error opening file " + filename);
+    unsigned char head[4] = {0, 0, 0, 0};
+    const int n = gzread(gz, head, 4);
+    gzclose(gz);
+    if (n >= 4 && std::memcmp(head, "BAM\1", 4) == 0) return true;
+    if (n >= 1 && head[0] == '@') return false;
+    throw std::runtime_error("Error: File format must be bam, cram, or fastq.");
+}
+
+// tag value of a Z-typed aux field, or nullptr; `*pos` (optional) receives the offset of the tag's first byte
+static const uint8_t* aux_find(const uint8_t* aux, const uint8_t* end, const char tag[2], const uint8_t** field_begin, const uint8_t** field_end) {
+    const uint8_t* s = aux;
+    while (end - s >= 3) {
+        const uint8_t* f = s;
+        const uint8_t type = s[2];
+        const uint8_t* v = s + 3;
+        size_t sz = 0;
+        switch (type) {
+        case 'A': case 'c': case 'C': sz = 1; break;
+        case 's': case 'S': sz = 2; break;
+        case 'i': case 'I': case 'f': sz = 4; break;
+        case 'd': sz = 8; break;
+        case 'Z': case 'H': { const uint8_t* z = v; while (z < end && *z) ++z; sz = (size_t)(z - v) + 1; break; }
+        case 'B': {
+            if (end - v < 5) return nullptr;
+            uint32_t cnt; std::memcpy(&cnt, v + 1, 4);
+            const size_t es = (v[0] == 'c' || v[0] == 'C') ? 1 : (v[0] == 's' || v[0] == 'S') ? 2 : 4;
+            sz = 5 + es * cnt;
+            break;
+        }
+        default: return nullptr;
+        }
+        if ((size_t)(end - v) < sz) return nullptr;
+        if (f[0] == (uint8_t)tag[0] && f[1] == (uint8_t)tag[1]) {
+            if (field_begin) *field_begin = f;
+            if (field_end) *field_end = v + sz;
+            return type == 'Z' ? v : nullptr;
+        }
+        s = v + sz;
+    }
+    return nullptr;
+}
+
+struct BamRec {
+    uint8_t l_read_name; uint16_t n_cigar, flag; int32_t l_seq;
+    const uint8_t *name, *seq, *qual, *aux, *end;
+};
+static BamRec bam_parse(const uint8_t* rec, size_t len) {
+    BamRec r;
+    r.l_read_name = rec[8];
+    std::memcpy(&r.n_cigar, rec + 12, 2);
+    std::memcpy(&r.flag, rec + 14, 2);
+    std::memcpy(&r.l_seq, rec + 16, 4);
+    r.name = rec + 32;
+    r.seq = r.name + r.l_read_name + 4 * (size_t)r.n_cigar;
+    r.qual = r.seq + (r.l_seq + 1) / 2;
+    r.aux = r.qual + r.l_seq;
+    r.end = rec + len;
+    return r;
+}
+
+static std::shared_ptr<kbbq::ReadStore> load_bam(const std::string& filename, bool use_oq) {
+    std::vector<uint8_t> d = gunzip_all(filename);
+    auto rs = std::make_shared<kbbq::ReadStore>();
+    rs->path = filename;
+    if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) throw std::runtime_error("Error opening file " + filename);
+    size_t p = 4;
+    int32_t l_text, n_ref;
+    std::memcpy(&l_text, &d[p], 4); p += 4 + (size_t)l_text;
+    std::memcpy(&n_ref, &d[p], 4); p += 4;
+    for (int i = 0; i < n_ref; ++i) {
+        int32_t l_name; uint32_t l_ref;
+        std::memcpy(&l_name, &d[p], 4); p += 4 + (size_t)l_name;
+        std::memcpy(&l_ref, &d[p], 4); p += 4;
+        rs->ref_len.push_back(l_ref);
+    }
+    rs->bam_header.assign(d.begin(), d.begin() + p);
+    rs->name_off.push_back(0); rs->comment_off.push_back(0); rs->off.push_back(0); rs->bam_off.push_back(0);
+    readutils::CReadData::rg_to_int.clear();
+    readutils::CReadData::rg_to_pu.clear();
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";
+    static const int nt16_int[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
+    while (p + 4 <= d.size()) {
+        int32_t block_size;
+        std::memcpy(&block_size, &d[p], 4);
+        p += 4;
+        if (block_size < 32 || p + (size_t)block_size > d.size()) throw std::runtime_error("truncated BAM record in " + filename);
+        const uint8_t* rec = &d[p];
+        const BamRec r = bam_parse(rec, (size_t)block_size);
+        const bool rev = r.flag & 16;
+        const std::string name((const char*)r.name);
+        // bam_seq_str (readutils.hh:30-42): forward orientation; a reverse-strand record is complemented, then reversed
+        const size_t L = (size_t)r.l_seq, s0 = rs->seq.size();
+        rs->seq.resize(s0 + L);
+        for (size_t i = 0; i < L; ++i) {
+            const int nib = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xf;
+            char c = nt16[nib];
+            if (rev) c = nt16_int[nib] < 4 ? "ACGT"[3 - nt16_int[nib]] : 'N';
+            rs->seq[s0 + (rev ? L - 1 - i : i)] = c;
+        }
+        rs->qual.resize(s0 + L);
+        if (use_oq) {
+            const uint8_t* oq = aux_find(r.aux, r.end, "OQ", nullptr, nullptr);
+            if (!oq) {
+                std::cerr << "Error: --use-oq was specified but unable to read OQ tag on read " << name << std::endl;
+                throw std::invalid_argument("Unable to read OQ tag.");
+            }
+            for (size_t i = 0; i < L; ++i) rs->qual[s0 + (rev ? L - 1 - i : i)] = (uint8_t)(oq[i] - 33);
+        } else {
+            for (size_t i = 0; i < L; ++i) rs->qual[s0 + (rev ? L - 1 - i : i)] = r.qual[i];
+        }
+        const uint8_t* rgz = aux_find(r.aux, r.end, "RG", nullptr, nullptr);
+        if (!rgz) {
+            std::cerr << "Error: Unable to read RG tag on read " << name << std::endl;
+            throw std::invalid_argument("Unable to read RG tag.");
+        }
+        const std::string rg((const char*)rgz);
+        auto& r2i = readutils::CReadData::rg_to_int;
+        if (readutils::CReadData::rg_to_pu.count(rg) == 0) {
+            const int id = (int)r2i.size();
+            r2i[rg] = id;
+            readutils::CReadData::rg_to_pu[rg] = rg;
+        }
+        rs->rg.push_back((uint16_t)r2i[rg]);
+        rs->second.push_back((r.flag & 0x80) ? 1 : 0);
+        rs->names.insert(rs->names.end(), name.begin(), name.end());
+        rs->name_off.push_back(rs->names.size());
+        rs->comment_off.push_back(0);
+        rs->off.push_back(rs->seq.size());
+        rs->max_len = std::max<uint32_t>(rs->max_len, (uint32_t)L);
+        rs->bam_blob.insert(rs->bam_blob.end(), rec, rec + block_size);
+        rs->bam_off.push_back(rs->bam_blob.size());
+        p += (size_t)block_size;
+    }
+    return rs;
+}
+
+BamFile::BamFile(std::string filename, int nthreads, bool use_oq, bool set_oq)
+    : StoreFile(load_bam(filename, use_oq), nthreads), use_oq_(use_oq), set_oq_(set_oq) {}
+
+void BamFile::format_header(std::string& out) const { out.append((const char*)store_->bam_header.data(), store_->bam_header.size()); }
+
+void BamFile::format_record(size_t i, const uint8_t* newq, std::string& out) const {
+    // BamFile::recalibrate + write (htsiter.cc:11-35,45): optional OQ tag from the record's current qualities, then the
+    // new qualities, reversed back for a reverse-strand record
+    const kbbq::ReadStore& rs = *store_;
+    const uint8_t* rec = rs.bam_blob.data() + rs.bam_off[i];
+    const size_t len = rs.bam_off[i + 1] - rs.bam_off[i];
+    const BamRec r = bam_parse(rec, len);
+    const size_t L = (size_t)r.l_seq;
+    std::string body((const char*)rec, len);
+    if (set_oq_) {
+        std::string oq(L, '!');
+        for (size_t j = 0; j < L; ++j) oq[j] = (char)(r.qual[j] + 33);
+        const uint8_t *fb = nullptr, *fe = nullptr;
+        std::string field = std::string("OQZ") + oq + '\0';
+        if (aux_find(r.aux, r.end, "OQ", &fb, &fe) || fb) body.replace((size_t)(fb - rec), (size_t)(fe - fb), field);  // bam_aux_update_str: in place
+        else body.append(field);
+    }
+    uint8_t* q = (uint8_t*)&body[(size_t)(r.qual - rec)];
+    const bool rev = r.flag & 16;
+    for (size_t j = 0; j < L; ++j) q[j] = newq[rev ? L - 1 - j : j];
+    const int32_t block_size = (int32_t)body.size();
+    out.append((const char*)&block_size, 4);
+    out.append(body);
 }
 
 KmerSubsampler::KmerSubsampler(HTSFile* file_, int k_, double alpha_, uint64_t seed_) : file(file_), k(k_), alpha(alpha_), seed(seed_) {
@@ -525,8 +736,8 @@ void recalibrate_and_write(htsiter::HTSFile* in, const covariateutils::dq_t& dqs
         newq[b].resize(std::max<uint64_t>(ses.n_words(b), 1) * 32);
         CK(kbbq_pass4_recalibrate(ses.ctx(), ses.batches()[b], newq[b].data()));
     }
-    // FASTQ fast path: format + compress in parallel, members written in input order
-    if (auto* fq = dynamic_cast<htsiter::FastqFile*>(in)) {
+    // fast path: format + compress in parallel, BGZF blocks written in input order
+    if (auto* fq = dynamic_cast<htsiter::StoreFile*>(in)) {
         fq->write_all(ses, newq);
         return;
     }

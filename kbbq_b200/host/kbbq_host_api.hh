@@ -34,6 +34,10 @@ struct ReadStore {
     std::vector<uint8_t> second;
     size_t n() const { return off.empty() ? 0 : off.size() - 1; }
     uint32_t max_len = 0;
+    // BAM input only: the header as it was read, every record's bytes (core + data, without block_size), strand flags
+    std::vector<uint8_t> bam_header, bam_blob;
+    std::vector<uint64_t> bam_off;
+    std::vector<uint64_t> ref_len;
 };
 
 // One GPU context plus the resident batches of one input.
@@ -171,30 +175,57 @@ public:
     virtual const kbbq::ReadStore& store() const = 0;  // mirror-only: the parsed input behind the iterator
 };
 
-// htsiter::FastqFile (htsiter.hh:101-126): FASTQ, plain or gzip
-class FastqFile : public HTSFile {
+// What FastqFile and BamFile share in this mirror: the input parsed once into a ReadStore, a cursor for the
+// reference's next()/get()/write() protocol, and a BGZF writer (blocks compressed by independent threads).
+class StoreFile : public HTSFile {
 public:
-    explicit FastqFile(std::string filename, int nthreads = 0);
-    ~FastqFile() override;
+    ~StoreFile() override;
     int next() override;
     std::string next_str() override;
     readutils::CReadData get() override;
-    void recalibrate(const std::vector<uint8_t>& qual) override;
+    void recalibrate(const std::vector<uint8_t>& qual) override { cur_qual_ = qual; }
     int open_out(std::string filename) override;
     int write() override;
     const kbbq::ReadStore& store() const override { return *store_; }
     // mirror-only: write every record with new qualities (layout of kbbq_batch.qual per batch), in input order
     int write_all(const kbbq::Session& s, const std::vector<std::vector<uint8_t>>& newq);
 
-private:
+protected:
+    StoreFile(std::shared_ptr<kbbq::ReadStore> st, int nthreads) : store_(std::move(st)), nthreads_(nthreads) {}
+    virtual void format_record(size_t i, const uint8_t* newq, std::string& out) const = 0;
+    virtual void format_header(std::string&) const {}
     std::shared_ptr<kbbq::ReadStore> store_;
     size_t cur_ = 0;  // index of the NEXT record
     std::vector<uint8_t> cur_qual_;
-    void* out_ = nullptr;  // FILE*: gzip members are written raw
-    std::string pending_;  // records waiting to become the next gzip member
+    void* out_ = nullptr;  // FILE*: BGZF blocks are written raw
+    std::string pending_;  // bytes waiting to be compressed
     int nthreads_;
-    int flush_pending();
+    int flush_pending(bool final);
 };
+
+// htsiter::FastqFile (htsiter.hh:101-126): FASTQ, plain or gzip
+class FastqFile : public StoreFile {
+public:
+    explicit FastqFile(std::string filename, int nthreads = 0);
+
+protected:
+    void format_record(size_t i, const uint8_t* newq, std::string& out) const override;
+};
+
+// htsiter::BamFile (htsiter.hh:51-99): unaligned or aligned BAM; --use-oq reads qualities from the OQ tag,
+// --set-oq stores the input qualities in it (htsiter.cc:11-35)
+class BamFile : public StoreFile {
+public:
+    BamFile(std::string filename, int nthreads = 0, bool use_oq = false, bool set_oq = false);
+
+protected:
+    void format_record(size_t i, const uint8_t* newq, std::string& out) const override;
+    void format_header(std::string& out) const override;
+    bool use_oq_, set_oq_;
+};
+
+// hts_detect_format as far as main() needs it (kbbq.cc:172-190): true for BAM, false for FASTQ, throws otherwise
+bool is_bam_file(const std::string& filename);
 
 // htsiter::KmerSubsampler (htsiter.hh:128-156): carries file, k, alpha, seed to subsample_kmers
 class KmerSubsampler {

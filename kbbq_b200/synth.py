@@ -130,3 +130,68 @@ def to_fastq(rs: ReadSet, path: str) -> None:
             if rs.n_rg > 1:
                 name += b"_RG:Z:rg%d" % int(rs.rg[i])
             fh.write(name + b"\n" + rs.seq[b0:b1].tobytes() + b"\n+\n" + (rs.qual[b0:b1] + 33).tobytes() + b"\n")
+
+
+_NT16 = np.full(256, 15, dtype=np.uint8)
+for _c, _v in zip(b"=ACMGRSVTWYHKDBN", range(16)):
+    _NT16[_c] = _v
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMP[_a] = _b
+
+
+def to_bam(rs: ReadSet, path: str, *, genome_len: int = 0, rev_every: int = 0, with_oq: bool = False,
+           seq_source: np.ndarray | None = None, block: int = 0xFF00) -> None:
+    """Write the read set as an unaligned BAM (BGZF blocks + EOF block): `RG:Z:rg<id>` on every record, flags
+    0x1|0x40 / 0x1|0x80 by `second`, header `@SQ LN:` = genome_len (kbbq.cc:196-216 sums them).
+
+    Every `rev_every`-th record is stored as a reverse-strand record (flag 0x10): its bases are written reverse
+    complemented and its qualities reversed, so that what the reference reads back in forward orientation
+    (readutils.hh:30-42, readutils.cc:36-39) is the read set's own read.  `with_oq` adds an `OQ:Z:` tag holding
+    qual+1 (capped at 93) so --use-oq visibly differs from the QUAL field.
+    """
+    import struct
+    import zlib
+
+    seq = rs.seq if seq_source is None else seq_source
+    text = b"@HD\tVN:1.6\tSO:unsorted\n"
+    if genome_len:
+        text += b"@SQ\tSN:chrSynth\tLN:%d\n" % genome_len
+    for g in range(rs.n_rg):
+        text += b"@RG\tID:rg%d\tPU:rg%d\n" % (g, g)
+    raw = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text)
+    if genome_len:
+        raw += struct.pack("<i", 1) + struct.pack("<i", 9) + b"chrSynth\0" + struct.pack("<i", genome_len)
+    else:
+        raw += struct.pack("<i", 0)
+    for i in range(rs.n):
+        b0, b1 = int(rs.off[i]), int(rs.off[i + 1])
+        L = b1 - b0
+        s = seq[b0:b1]
+        q = rs.qual[b0:b1]
+        flag = 0x1 | 0x4 | (0x80 if rs.second[i] else 0x40)
+        if rev_every and i % rev_every == rev_every - 1:
+            flag |= 0x10
+            s = _COMP[s[::-1]]
+            q = q[::-1]
+        nib = _NT16[s]
+        if L & 1:
+            nib = np.concatenate([nib, np.zeros(1, np.uint8)])
+        packed = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8).tobytes()
+        name = b"r%d\0" % i
+        aux = b""
+        if with_oq:
+            aux += b"OQZ" + (np.minimum(q.astype(np.int32) + 1, 93).astype(np.uint8) + 33).tobytes() + b"\0"
+        aux += b"RGZrg%d\0" % int(rs.rg[i])
+        core = struct.pack("<iiBBHHHiiii", -1, -1, len(name), 0, 4680, 0, flag, L, -1, -1, 0)
+        body = core + name + packed + q.tobytes() + aux
+        raw += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as fh:
+        for p in range(0, len(raw), block):
+            chunk = bytes(raw[p : p + block])
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            bsize = 18 + len(comp) + 8
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize - 1) + comp
+                     + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))

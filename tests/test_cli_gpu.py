@@ -68,3 +68,62 @@ def test_cli_against_live_reference_cli(tmp_path):
     assert r.returncode == 0
     got, _ = _run(["--seed", "2854027472"] + args, tmp_path)
     assert got == gzip.open(tmp_path / "ref.gz").read()
+
+
+def _bam_records(data):
+    """Split an uncompressed BAM stream into (header bytes, [record bytes])."""
+    import struct
+    assert data[:4] == b"BAM\1"
+    p = 4
+    (l_text,) = struct.unpack_from("<i", data, p); p += 4 + l_text
+    (n_ref,) = struct.unpack_from("<i", data, p); p += 4
+    for _ in range(n_ref):
+        (l_name,) = struct.unpack_from("<i", data, p); p += 4 + l_name + 4
+    head, recs = data[:p], []
+    while p < len(data):
+        (bs,) = struct.unpack_from("<i", data, p)
+        recs.append(data[p + 4:p + 4 + bs])
+        p += 4 + bs
+    return head, recs
+
+
+@pytest.mark.parametrize("inp,args,gold", [
+    ("cli_in.bam", ["-k", "31", "-c", "25", "--set-oq"], "cli_bam_out.bam.gz"),           # genome length from the header
+    ("cli_in.bam", ["-k", "31", "-c", "25", "-g", "4000", "--use-oq"], "cli_bam_useoq_out.bam.gz"),
+    ("cli_in_nooq.bam", ["-k", "31", "-c", "25", "--set-oq"], "cli_bam_nooq_out.bam.gz"),  # OQ tag appended
+])
+def test_cli_bam_matches_reference_cli(tmp_path, inp, args, gold):
+    """BASELINE.json configs[1]'s input format: BAM with read groups, reverse-strand records and --set-oq / --use-oq
+    (htsiter.cc:11-35, readutils.cc:13-61); the uncompressed output stream must be the reference CLI's byte for byte."""
+    got, log = _run(["--seed", "2854027472"] + args + [os.path.join(GOLD, inp)], tmp_path)
+    want = gzip.open(os.path.join(GOLD, gold)).read()
+    if got != want:  # say where
+        gh, gr = _bam_records(got)
+        wh, wr = _bam_records(want)
+        assert gh == wh, "BAM header differs"
+        assert len(gr) == len(wr)
+        bad = [i for i, (a, b) in enumerate(zip(gr, wr)) if a != b]
+        assert not bad, "first differing record %d of %d" % (bad[0], len(bad))
+    assert got == want
+    if "-g" not in args:
+        assert "Genome length is 4000 bp." in log
+
+
+def test_cli_bam_against_live_reference_cli(tmp_path):
+    ref = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/kbbq_ref not present")
+    import sys
+    sys.path.insert(0, ROOT)
+    from kbbq_b200 import synth
+
+    rs = synth.make_reads(100000, 20, 100, seed=78, n_rg=3, n_frac=0.001)
+    bam = str(tmp_path / "big.bam")
+    synth.to_bam(rs, bam, genome_len=100000, rev_every=5, with_oq=True)
+    for extra in (["--set-oq"], ["--use-oq", "--set-oq"]):
+        args = ["-k", "32", "-c", "20"] + extra + [bam]
+        with open(tmp_path / "ref.gz", "wb") as fo:
+            r = subprocess.run([ref] + args, stdout=fo, stderr=subprocess.PIPE)
+        assert r.returncode == 0
+        got, _ = _run(["--seed", "2854027472"] + args, tmp_path)
+        assert got == gzip.open(tmp_path / "ref.gz").read()
