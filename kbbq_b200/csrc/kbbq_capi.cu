@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -736,7 +737,12 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
     if (b->n_reads) {
         CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
         pass3_errors_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->counts(), ctx->k, err_bits ? b->d_err_bits : nullptr, 1,
+            b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->counts(), ctx->k, err_bits ? b->d_err_bits : nullptr,
+#if defined(KBBQ_P3_EXPERIMENT)
+            getenv("KBBQ_P3_MODE") ? atoi(getenv("KBBQ_P3_MODE")) : 1,
+#else
+            1,
+#endif
             ctx->d_work);
         if (int rc = check_launch(ctx, "pass3_errors_kernel")) return rc;
     }

@@ -18,6 +18,14 @@
 #define KBBQ_HD inline
 #endif
 
+// Loops in the per-read logic are scalar bookkeeping executed once per read by a whole warp: unrolling them buys
+// nothing and multiplies the code size of a kernel that lives or dies by the instruction cache.
+#if defined(__CUDACC__) && !defined(KBBQ_ALLOW_UNROLL)
+#define KBBQ_NOUNROLL _Pragma("unroll 1")
+#else
+#define KBBQ_NOUNROLL
+#endif
+
 #define KBBQ_MAX_K 32          // KBBQ_MAX_KMER, bloom.hh:15
 #define KBBQ_MAXQ 93           // KBBQ_MAXQ, covariateutils.hh:3
 #define KBBQ_NQ 94
@@ -152,6 +160,7 @@ KBBQ_HD void bit_set(uint32_t* m, int i) { m[i >> 5] |= 1u << (i & 31); }
 KBBQ_HD void bit_clr(uint32_t* m, int i) { m[i >> 5] &= ~(1u << (i & 31)); }
 // smallest index >= from whose bit is set (clear), or n when there is none
 KBBQ_HD int next_one(const uint32_t* m, int n, int from) {
+    KBBQ_NOUNROLL
     while (from < n) {
         const uint32_t x = m[from >> 5] >> (from & 31);
         if (x) { const int r = from + ctz32(x); return r < n ? r : n; }
@@ -160,6 +169,7 @@ KBBQ_HD int next_one(const uint32_t* m, int n, int from) {
     return n;
 }
 KBBQ_HD int next_zero(const uint32_t* m, int n, int from) {
+    KBBQ_NOUNROLL
     while (from < n) {
         const uint32_t x = ~m[from >> 5] >> (from & 31);
         if (x) { const int r = from + ctz32(x); return r < n ? r : n; }
@@ -169,6 +179,7 @@ KBBQ_HD int next_zero(const uint32_t* m, int n, int from) {
 }
 // largest index <= from whose bit is clear, or -1 when there is none (from >= 0)
 KBBQ_HD int prev_zero(const uint32_t* m, int from) {
+    KBBQ_NOUNROLL
     while (from >= 0) {
         const int o = from & 31;
         const uint32_t x = ~m[from >> 5] << (31 - o);  // bit `from` moved to the top
@@ -186,6 +197,7 @@ KBBQ_HD int prev_zero(const uint32_t* m, int from) {
 // number of set bits in [lo, hi)
 KBBQ_HD int count_range(const uint32_t* m, int lo, int hi) {
     int c = 0;
+    KBBQ_NOUNROLL
     while (lo < hi) {
         const int o = lo & 31;
         int take = 32 - o;

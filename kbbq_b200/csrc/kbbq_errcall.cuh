@@ -54,6 +54,8 @@ struct ErrScratch {
     uint32_t T_cur[KBBQ_MAXW + 1];  // same for seq after correct_one, when that ran
     uint32_t E[KBBQ_MAXW + 1];      // this->errors of the top-level read
     uint32_t QL[KBBQ_MAXW + 1];     // bit i: qual[i] <= 6 (the overcorrection half weight), top-level coordinates
+    uint32_t F[KBBQ_MAXW + 1];      // overcorrection check: flagged bases whose original base was ACGT ...
+    uint32_t FQ[KBBQ_MAXW + 1];     // ... and those of them with qual <= 6
 };
 
 struct ErrResult {
@@ -63,26 +65,33 @@ struct ErrResult {
 
 template <class Q>
 struct ErrCaller {
-    Q& q;
+    Q q;  // held by value: on the device it is one pointer, and nothing here may force the caller's state into memory
     const int k;
     const uint8_t* qual;  // qualities of the top-level read (only correct_one's tie-break reads them)
     ErrScratch& sc;
     const uint32_t* T = nullptr;  // cached trusted flags of the running call's sequence (see cached_run)
     bool T_mirrored = false;
-    KBBQ_HD ErrCaller(Q& q_, int k_, const uint8_t* qual_, ErrScratch& sc_) : q(q_), k(k_), qual(qual_), sc(sc_) {}
+    KBBQ_HD ErrCaller(Q q_, int k_, const uint8_t* qual_, ErrScratch& sc_) : q(q_), k(k_), qual(qual_), sc(sc_) {}
 
     // THE probe routine.  Lane t asks about the k-mer of s starting at j0 + t*stride with base p replaced:
     //   stride == 1: consecutive k-mers, replacement base c (c < 0: no replacement);
     //   stride == 0: one k-mer, lane t tries base (cpack >> 2t) & 3  -- the candidate pre-test.
-    KBBQ_HD_NOINLINE uint32_t kmers_mask(const SeqRef& s, int j0, int stride, int count, int p, int c, uint32_t cpack) {
-        const int kk = k;
+    // Out of line, and static with scalar arguments only: a noinline MEMBER would pin `*this` (memo, anchors, flags) in
+    // local memory for the whole call tree.
+    static KBBQ_HD_NOINLINE uint32_t kmers_mask_s(Q q, unsigned long long* w, uint32_t* nm, int kk, int j0, int stride,
+                                                  int count, int p, int c, uint32_t cpack) {
+        const SeqRef s{w, nm, 0};
         return q.query(count, [&](int t, uint64_t& key) {
             return kmer_key(s, j0 + t * stride, kk, p, stride ? c : (int)((cpack >> (2 * t)) & 3u), key);
         });
     }
+    KBBQ_HD uint32_t kmers_mask(const SeqRef& s, int j0, int stride, int count, int p, int c, uint32_t cpack) {
+        return kmers_mask_s(q, s.w, s.nm, k, j0, stride, count, p, c, cpack);
+    }
     // number of consecutive trusted k-mers starting at j0, looking no further than j1 (exclusive)
     KBBQ_HD int trusted_run(const SeqRef& s, int j0, int j1, int p, int c) {
         int j = j0;
+        KBBQ_NOUNROLL
         while (j < j1) {
             const int count = j1 - j < 32 ? j1 - j : 32;
             const uint32_t m = kmers_mask(s, j, 1, count, p, c, 0);
@@ -95,6 +104,7 @@ struct ErrCaller {
     // fill T[0 .. nk) with the trusted flag of every k-mer of s
     KBBQ_HD void scan(const SeqRef& s, uint32_t* Tout) {
         const int nk = s.len - k + 1;
+        KBBQ_NOUNROLL
         for (int j = 0; j < nk; j += 32) Tout[j >> 5] = kmers_mask(s, j, 1, nk - j < 32 ? nk - j : 32, 0, -1, 0);
     }
 
@@ -102,6 +112,7 @@ struct ErrCaller {
     KBBQ_HD void longest_trusted(const uint32_t* Tm, int len, int& a0, int& a1) {
         const int nk = len - k + 1;
         int best = 0, bs = 0, be = 0, pos = 0;
+        KBBQ_NOUNROLL
         while (true) {
             const int s = next_one(Tm, nk, pos);
             if (s >= nk) break;
@@ -130,6 +141,7 @@ struct ErrCaller {
     KBBQ_HD uint32_t candidates(const SeqRef& s, int p, bool reverse_order, int& ncand) {
         uint32_t pack = 0;
         ncand = 0;
+        KBBQ_NOUNROLL
         for (int ci = 0; ci < 4; ++ci) {
             const int c = reverse_order ? 3 - ci : ci;  // bloom.cc:140-141
             if (!seq_eq(s, p, c)) pack |= (uint32_t)c << (2 * ncand++);
@@ -144,8 +156,11 @@ struct ErrCaller {
         int p;            // position, -1 = empty
         bool mirrored;    // which working sequence
         uint32_t first;   // bit c: first k-mer with base c trusted
-        int run_in[4];    // per base: trusted streak over the k-mers containing p (>= 1), or -1 when not walked yet
+        uint64_t run_in;  // per base c, 16 bits at 16c: trusted streak over the k-mers containing p (>= 1), 0 = not walked yet
     };
+    // four small counters in one register (indexed arrays would live in local memory once loops are not unrolled)
+    static KBBQ_HD int get16(uint64_t v, int i) { return (int)((v >> (16 * i)) & 0xFFFFu); }
+    static KBBQ_HD uint64_t set16(uint64_t v, int i, int x) { return (v & ~(0xFFFFull << (16 * i))) | ((uint64_t)(unsigned)x << (16 * i)); }
     Memo memo;
 
     KBBQ_HD void memo_reset() { memo.p = -1; }
@@ -156,17 +171,22 @@ struct ErrCaller {
         memo.p = p;
         memo.mirrored = T_mirrored;
         memo.first = 0;
+        memo.run_in = 0;
+        KBBQ_NOUNROLL
         for (int t = 0; t < ncand; ++t) {
             const int c = (int)((cpack >> (2 * t)) & 3u);
             if ((m0 >> t) & 1u) memo.first |= 1u << c;
-            memo.run_in[c] = -1;
         }
         return memo.first;
     }
     // trusted streak over the k-mers that contain p (there are nin of them) with base c at p, first one known trusted
     KBBQ_HD int run_containing(const SeqRef& s, int p, int nin, int c) {
-        if (memo.run_in[c] < 0) memo.run_in[c] = 1 + trusted_run(s, p - k + 2, p - k + 1 + nin, p, c);
-        return memo.run_in[c];
+        int r = get16(memo.run_in, c);
+        if (r == 0) {
+            r = 1 + trusted_run(s, p - k + 2, p - k + 1 + nin, p, c);
+            memo.run_in = set16(memo.run_in, c, r);
+        }
+        return r;
     }
 
     // bloom::find_longest_fix (bloom.cc:130-188) for the substring of s starting at `start`; the base under repair is
@@ -181,10 +201,11 @@ struct ErrCaller {
         const int i_stop = 2 * k - 1 > sublen ? 2 * k - 1 : sublen;  // bloom.cc:147
         const int nin = nsub < k ? nsub : k;                      // ... of which these contain p
         int nbest = 0, best_i = 0, first_ok = 0, ncand, nreach = 0;
-        int runs[4];
+        uint64_t runs = 0;  // per candidate t, 16 bits at 16t
         fix0 = 0;
         const uint32_t cpack = candidates(s, p, reverse_order, ncand);
         const uint32_t first = first_flags(s, p, cpack, ncand);
+        KBBQ_NOUNROLL
         for (int t = 0; t < ncand; ++t) {
             const int c = (int)((cpack >> (2 * t)) & 3u);
             int run = 0;
@@ -193,20 +214,23 @@ struct ErrCaller {
                 run = run_containing(s, p, nin, c);
                 if (run == nin && nsub > nin) run += cached_run(start + nin, s.len);
             }
-            runs[t] = run;
+            runs = set16(runs, t, run);
             nreach += run == nsub;
         }
         const bool extend = sublen < i_stop && nreach >= 2;
+        KBBQ_NOUNROLL
         for (int t = 0; t < ncand; ++t) {
             const int c = (int)((cpack >> (2 * t)) & 3u);
-            int i = k - 1 + runs[t];
-            if (extend && runs[t] == nsub) {
+            const int run = get16(runs, t);
+            int i = k - 1 + run;
+            if (extend && run == nsub) {
                 uint64_t v = extract_le(s.w, s.len - k, k);
                 if (p >= s.len - k) {
                     const int o = p - (s.len - k);
                     v = (v & ~(3ull << (2 * o))) | ((uint64_t)c << (2 * o));
                 }
                 const int kk = k;
+                KBBQ_NOUNROLL
                 for (i = sublen; i < i_stop; ++i) {
                     const uint64_t shifted = v >> 2;
                     const uint32_t m = q.query(4, [&](int tt, uint64_t& key) {
@@ -239,6 +263,7 @@ struct ErrCaller {
             int ncand;
             const uint32_t cpack = candidates(s, m, false, ncand);
             const uint32_t first = first_flags(s, m, cpack, ncand);
+            KBBQ_NOUNROLL
             for (int t = 0; t < ncand; ++t) {
                 const int c = (int)((cpack >> (2 * t)) & 3u);
                 if (!((first >> c) & 1u)) continue;
@@ -249,10 +274,12 @@ struct ErrCaller {
         }
         // otherwise try pulling the anchor back by up to k/2: first k-mers of every (position, base) pair in bulk
         int ni = 0;  // positions i = k/2-1 .. 0 that satisfy anchor > i+k-1 form a prefix of that descending walk
+        KBBQ_NOUNROLL
         for (int i = k / 2 - 1; i >= 0 && anchor > i + k - 1; --i) ++ni;
         const int npairs = 4 * ni;
         const int need = k / 2 + 2;  // k-mers ending at m .. m+k/2+1 must all be trusted
         const int jmax = s.len - k + 1;
+        KBBQ_NOUNROLL
         for (int c0 = 0; c0 < npairs; c0 += 32) {
             const int count = npairs - c0 < 32 ? npairs - c0 : 32;
             uint32_t hits = q.query(count, [&](int t, uint64_t& key) {
@@ -261,6 +288,7 @@ struct ErrCaller {
                 if (seq_eq(s, m, c)) return false;
                 return kmer_key(s, m - kk + 1, kk, m, c, key);
             });
+            KBBQ_NOUNROLL
             while (hits) {
                 const int t = ctz32(hits);
                 hits &= hits - 1;
@@ -275,11 +303,13 @@ struct ErrCaller {
     }
 
     // CReadData::correct_one (readutils.cc:195-235) + bloom::biggest_consecutive_trusted_block (bloom.cc:279-305)
-    KBBQ_HD_NOINLINE int correct_one(const SeqRef& s, int qbase, int& out_base) {
-        const int len = s.len;
+    // Static for the same reason as kmers_mask_s; returns 4*position + base, or KBBQ_NPOS.
+    static KBBQ_HD_NOINLINE int correct_one_s(Q q, unsigned long long* w, uint32_t* nm, int len, int k, const uint8_t* qual) {
+        const SeqRef s{w, nm, len};
         int best_len = 0, best_base = 0, best_pos = KBBQ_NPOS;
         const int ncand = 4 * len;  // candidate id = 4*i + c; identical bases are skipped like `continue`
         const int kk = k;
+        KBBQ_NOUNROLL
         for (int c0 = 0; c0 < ncand; c0 += 32) {
             const int count = ncand - c0 < 32 ? ncand - c0 : 32;
             // the "magic k-mer" pre-test (readutils.cc:207-213) for 32 (position, base) candidates at once
@@ -290,6 +320,7 @@ struct ErrCaller {
                 if (i > kk / 2 - 1) { ms = i - kk / 2 + 1; if (ms > len - kk) ms = len - kk; }
                 return kmer_key(s, ms, kk, i, c, key);
             });
+            KBBQ_NOUNROLL
             while (hits) {
                 const int t = ctz32(hits);
                 hits &= hits - 1;
@@ -297,12 +328,13 @@ struct ErrCaller {
                 const int start = i > k - 1 ? i - k + 1 : 0;
                 int nwin = len - k + 1 - start;  // k-mers of substr(start, 2k-1)
                 if (nwin > k) nwin = k;
-                uint32_t m = kmers_mask(s, start, 1, nwin, i, c, 0);
+                uint32_t m = kmers_mask_s(q, w, nm, k, start, 1, nwin, i, c, 0);
                 // the walk stops once k - (#misses) < best_len (bloom.cc:295): cut the mask at that miss
                 if (best_len >= 1) {
                     const int stop_after = k - best_len + 1;  // this many misses end the walk
                     uint32_t z = ~m & (nwin < 32 ? ((1u << nwin) - 1) : ~0u);
                     int seen = 0;
+                    KBBQ_NOUNROLL
                     while (z) {
                         const int b = ctz32(z);
                         z &= z - 1;
@@ -310,23 +342,29 @@ struct ErrCaller {
                     }
                 }
                 int n_in = 0;
+                KBBQ_NOUNROLL
                 while (m) {  // longest streak of ones
                     m &= m << 1;
                     ++n_in;
                 }
                 if (n_in > best_len) { best_base = c; best_pos = i; best_len = n_in; }
-                else if (n_in == best_len && qual[qbase + i] < qual[qbase + best_pos]) { best_base = c; best_pos = i; }
+                else if (n_in == best_len && qual[i] < qual[best_pos]) { best_base = c; best_pos = i; }
             }
         }
-        out_base = best_base;
         if (best_len > 0) seq_set(s, best_pos, best_base);
-        return best_pos;
+        return best_pos == KBBQ_NPOS ? KBBQ_NPOS : 4 * best_pos + best_base;
+    }
+    KBBQ_HD int correct_one(const SeqRef& s, int qbase, int& out_base) {
+        const int r = correct_one_s(q, s.w, s.nm, s.len, k, qual + qbase);
+        out_base = r & 3;
+        return r == KBBQ_NPOS ? KBBQ_NPOS : r >> 2;
     }
 
     // reverse complement of src into dst (readutils.cc:351-353): N stays N
     KBBQ_HD void revcomp(const SeqRef& src, const SeqRef& dst) {
         const int len = src.len;
         const int nw = (len + 31) >> 5;
+        KBBQ_NOUNROLL
         for (int wd = 0; wd < nw; ++wd) {
             // dst bases [32wd, 32wd+32) = complement of src bases len-1-32wd down to len-32-32wd
             const int hi = len - 1 - 32 * wd;
@@ -339,6 +377,7 @@ struct ErrCaller {
 #if defined(__CUDA_ARCH__)
             nr = __brev(n) >> (32 - cnt);
 #else
+            KBBQ_NOUNROLL
             for (int b = 0; b < cnt; ++b) nr |= ((n >> b) & 1u) << (cnt - 1 - b);
 #endif
             dst.w[wd] = ~v & kmask(cnt);
@@ -356,6 +395,7 @@ struct ErrCaller {
         bad_suffix = KBBQ_NPOS;
         if (len < k) return;  // the reference is undefined here (bloom.cc:30 / readutils.cc:207 underflow)
         const int nw = (len + 31) >> 5;
+        KBBQ_NOUNROLL
         for (int w = 0; w <= nw; ++w) sc.O_nm[w] = cur.nm[w];
         bool multiple = false;
         memo_reset();
@@ -386,6 +426,7 @@ struct ErrCaller {
         //      (348-422).  In the reverse complement's own coordinates the left walk is the same loop: the base under
         //      repair sits at j, the next one at start + fixlen; only the flag index (len-1-j) is mirrored.
         SeqRef rc{sc.C_w, sc.C_nm, len};
+        KBBQ_NOUNROLL
         for (int side = 0; side < 2; ++side) {
             int anchor;
             if (side == 0) {
@@ -404,6 +445,7 @@ struct ErrCaller {
                 multiple = multiple || cm;
             }
             int bad = KBBQ_NPOS;
+            KBBQ_NOUNROLL
             for (int j = anchor + 1; j < len;) {
                 const int start = j - k + 1;
                 int fix0, fixlen;
@@ -440,6 +482,7 @@ struct ErrCaller {
                 // ref quirk: the streak that runs to the end of the read is never examined (455-465)
                 const int nk = len - k + 1;
                 int pos = 0;
+                KBBQ_NOUNROLL
                 while (adjust) {
                     const int s = next_one(sc.T_orig, nk, pos);
                     if (s >= nk) break;
@@ -456,31 +499,45 @@ struct ErrCaller {
             const int ocwindow = 20, base_threshold = 4;
             uint32_t* OC = sc.T_cur;  // T_cur is dead from here on: reuse it for the overcorrected-index list
             bool any_oc = false;
-            const uint32_t* E = sc.E;
-            const uint32_t* QL = sc.QL;
-            const uint32_t* ON = sc.O_nm;
+            // F = flagged bases that count (original base ACGT), FQ = those of them with the half weight, both in the
+            // call's own coordinates: a window's weight is two popcounts instead of a 20-step loop per base
+            uint32_t* F = sc.F;
+            uint32_t* FQ = sc.FQ;
+            KBBQ_NOUNROLL
             for (int w = 0; w < nw; ++w) {
-                const uint32_t m = q.map32([&](int t) {
-                    const int i = 32 * w + t;
-                    if (i >= len || !bit_get(E, base + i)) return false;
-                    const int lo = i - ocwindow + 1 > 0 ? i - ocwindow + 1 : 0;
-                    int occ2 = 0;
-                    for (int x = lo; x <= i; ++x)
-                        if (bit_get(E, base + x) && !bit_get(ON, x)) occ2 += bit_get(QL, base + x) ? 1 : 2;
-                    const int threshold = adjust && i >= ocwindow && i + ocwindow - 1 < len ? base_threshold + 1 : base_threshold;
-                    return occ2 > 2 * threshold;
-                });
+                const int cnt = len - 32 * w < 32 ? len - 32 * w : 32;
+                const uint32_t e = extract_n(sc.E, base + 32 * w, cnt) & ~sc.O_nm[w];
+                F[w] = e;
+                FQ[w] = e & extract_n(sc.QL, base + 32 * w, cnt);
+            }
+            F[nw] = 0;
+            FQ[nw] = 0;
+            KBBQ_NOUNROLL
+            for (int w = 0; w < nw; ++w) {
+                uint32_t m = 0;
+                if (extract_n(sc.E, base + 32 * w, len - 32 * w < 32 ? len - 32 * w : 32)) {  // only flagged bases can be overcorrected
+                    m = q.map32([&](int t) {
+                        const int i = 32 * w + t;
+                        if (i >= len || !bit_get(sc.E, base + i)) return false;
+                        const int lo = i - ocwindow + 1 > 0 ? i - ocwindow + 1 : 0;
+                        const int occ2 = 2 * count_range(F, lo, i + 1) - count_range(FQ, lo, i + 1);
+                        const int threshold = adjust && i >= ocwindow && i + ocwindow - 1 < len ? base_threshold + 1 : base_threshold;
+                        return occ2 > 2 * threshold;
+                    });
+                }
                 OC[w] = m;
                 any_oc = any_oc || m != 0;
             }
             OC[nw] = 0;
             if (any_oc) {  // un-flag everything within k of an overcorrected base, transitively (521-545)
+                KBBQ_NOUNROLL
                 for (int oc = next_one(OC, len, 0); oc < len; oc = next_one(OC, len, oc + 1)) {
                     if (!bit_get(sc.E, base + oc)) continue;
                     int start = oc - k + 1;
                     start = start >= 0 ? start : 0;
                     int end = oc + k;
                     end = end < len ? end : len;
+                    KBBQ_NOUNROLL
                     for (int i = start; i < end; ++i) {
                         if (bit_get(sc.E, base + i)) {
                             bit_clr(sc.E, base + i);
@@ -507,6 +564,7 @@ struct ErrCaller {
         SeqRef P{sc.P_w, sc.P_nm, len};
         SeqRef A{sc.A_w, sc.A_nm, 0};
         int top_prefix = 0, top_suffix = KBBQ_NPOS;
+        KBBQ_NOUNROLL
         for (int job = 0; job < 3; ++job) {  // 0: the read; 1: substr(0, bad_prefix+1); 2: substr(bad_suffix)
             int from = 0;
             if (job == 1) {
@@ -519,6 +577,7 @@ struct ErrCaller {
             }
             if (job) {  // the sub-read is cut from the partly corrected read and inherits its flags (readutils.cc:597-608)
                 const int nw = (A.len + 31) >> 5;
+                KBBQ_NOUNROLL
                 for (int w = 0; w < nw; ++w) {
                     const int cnt = A.len - 32 * w < 32 ? A.len - 32 * w : 32;
                     A.w[w] = extract_le(P.w, from + 32 * w, cnt);

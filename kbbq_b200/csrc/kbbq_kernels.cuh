@@ -376,15 +376,23 @@ __device__ __forceinline__ void consume_read_warp(const CountView& cv, const uns
 }
 
 // ---- pass 3: get_errors + consume_read (recalibrateutils.cc:42-89) ------------------------------------------------
+// one copy of hash + 4 loads + compare for every question the error caller asks (it asks from five places)
+__device__ __noinline__ uint32_t probe_ballot(const BloomView* f, bool valid, uint64_t key) {
+    return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(*f, key));
+}
 struct DevQuery {
-    BloomView f;
+    const BloomView* f;  // in shared memory: a kernel parameter has no address an out-of-line function could take
     template <class F>
     KBBQ_HD uint32_t query(int count, F fn) {
 #if defined(__CUDA_ARCH__)
         const int lane = threadIdx.x & 31;
         uint64_t key = 0;
         const bool valid = lane < count && fn(lane, key);
-        return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(f, key));
+#if defined(KBBQ_P3_PROBE_INLINE)
+        return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(*f, key));
+#else
+        return probe_ballot(f, valid, key);
+#endif
 #else
         (void)count; (void)fn;
         return 0;
@@ -409,9 +417,12 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
 pass3_errors_kernel(BatchView b, BloomView trusted, CountView cv, int k, uint32_t* __restrict__ err_out, int do_consume,
                     unsigned int* __restrict__ work_counter) {
     __shared__ ErrScratch scratch[KBBQ_WARPS_PER_BLOCK];
+    __shared__ BloomView filter;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     ErrScratch& sc = scratch[wib];
-    DevQuery q{trusted};
+    if (threadIdx.x == 0) filter = trusted;
+    __syncthreads();
+    DevQuery q{&filter};
     for (;;) {
         // reads differ a lot in cost (most need only the mandatory scan, a few need ~1000 probes): pull, don't stride
         uint32_t r = 0;
@@ -434,10 +445,17 @@ pass3_errors_kernel(BatchView b, BloomView trusted, CountView cv, int k, uint32_
         }
         __syncwarp();
         ErrCaller<DevQuery> ec(q, k, qual, sc);
+#if defined(KBBQ_P3_EXPERIMENT)
+        ErrResult res;
+        res.mod_idx = -1; res.mod_base = -1;
+        if (do_consume & 2) { if (len >= k) { SeqRef P{sc.P_w, sc.P_nm, len}; ec.scan(P, sc.T_orig); } }
+        else res = ec.run(len);
+#else
         const ErrResult res = ec.run(len);
+#endif
         __syncwarp();
         if (err_out && lane < nw) err_out[wo + lane] = sc.E[lane];
-        if (do_consume) {
+        if (do_consume & 1) {
             // consume_read sees the original bases (readutils.cc:568) except for the early-return quirk
             if (lane < nw) {
                 sc.A_w[lane] = b.bases[wo + lane];

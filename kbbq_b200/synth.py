@@ -141,14 +141,16 @@ for _a, _b in zip(b"ACGT", b"TGCA"):
 
 
 def to_bam(rs: ReadSet, path: str, *, genome_len: int = 0, rev_every: int = 0, with_oq: bool = False,
-           seq_source: np.ndarray | None = None, block: int = 0xFF00) -> None:
+           seq_source: np.ndarray | None = None, block: int = 0xFF00, first_name: bytes | None = None) -> None:
     """Write the read set as an unaligned BAM (BGZF blocks + EOF block): `RG:Z:rg<id>` on every record, flags
     0x1|0x40 / 0x1|0x80 by `second`, header `@SQ LN:` = genome_len (kbbq.cc:196-216 sums them).
 
     Every `rev_every`-th record is stored as a reverse-strand record (flag 0x10): its bases are written reverse
     complemented and its qualities reversed, so that what the reference reads back in forward orientation
     (readutils.hh:30-42, readutils.cc:36-39) is the read set's own read.  `with_oq` adds an `OQ:Z:` tag holding
-    qual+1 (capped at 93) so --use-oq visibly differs from the QUAL field.
+    qual+1 (capped at 93) so --use-oq visibly differs from the QUAL field.  `first_name` names record 0 (a long
+    name makes the reader's record buffer big enough that appending an OQ tag later never reallocates it: the
+    reference keeps a pointer into that buffer across bam_aux_update_str, htsiter.cc:12-29).
     """
     import struct
     import zlib
@@ -178,7 +180,7 @@ def to_bam(rs: ReadSet, path: str, *, genome_len: int = 0, rev_every: int = 0, w
         if L & 1:
             nib = np.concatenate([nib, np.zeros(1, np.uint8)])
         packed = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8).tobytes()
-        name = b"r%d\0" % i
+        name = (first_name if (i == 0 and first_name) else b"r%d" % i) + b"\0"
         aux = b""
         if with_oq:
             aux += b"OQZ" + (np.minimum(q.astype(np.int32) + 1, 93).astype(np.uint8) + 33).tobytes() + b"\0"

@@ -162,6 +162,16 @@ char *bam_aux2Z(const uint8_t *s) {
     return NULL;
 }
 
+/* htslib's kroundup32: capacity of bam1_t::data grows to the next power of two */
+static uint32_t shim_roundup32(uint32_t x) {
+    --x; x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16;
+    return ++x;
+}
+
+/* Like htslib (sam.c bam_aux_update_str): the tag is rewritten IN PLACE -- the data buffer is only reallocated when
+ * its capacity (m_data, a power of two kept across records) is too small.  This matters for parity: the reference's
+ * BamFile::recalibrate (htsiter.cc:11-35) takes bam_get_qual() BEFORE calling this function and writes the new
+ * qualities through that pointer afterwards, which is only valid while the buffer does not move. */
 int bam_aux_update_str(bam1_t *b, const char tag[2], int len, const char *data) {
     /* len includes the terminating NUL when data is NUL-terminated (htslib contract) */
     size_t dlen = (len > 0 && data[len - 1] == 0) ? (size_t)len - 1 : (len < 0 ? strlen(data) : (size_t)len);
@@ -179,19 +189,20 @@ int bam_aux_update_str(bam1_t *b, const char tag[2], int len, const char *data) 
     }
     size_t tail = (size_t)b->l_data - tail_off;
     size_t newlen = head + 3 + dlen + 1 + tail;
-    uint8_t *nd = (uint8_t *)malloc(newlen ? newlen : 1);
-    if (!nd) { errno = ENOMEM; return -1; }
-    memcpy(nd, b->data, head);
-    nd[head] = (uint8_t)tag[0];
-    nd[head + 1] = (uint8_t)tag[1];
-    nd[head + 2] = 'Z';
-    memcpy(nd + head + 3, data, dlen);
-    nd[head + 3 + dlen] = 0;
-    memcpy(nd + head + 3 + dlen + 1, b->data + tail_off, tail);
-    free(b->data);
-    b->data = nd;
+    if (newlen > b->m_data) {
+        uint32_t cap = shim_roundup32((uint32_t)newlen);
+        uint8_t *nd = (uint8_t *)realloc(b->data, cap);
+        if (!nd) { errno = ENOMEM; return -1; }
+        b->data = nd;
+        b->m_data = cap;
+    }
+    memmove(b->data + head + 3 + dlen + 1, b->data + tail_off, tail);
+    b->data[head] = (uint8_t)tag[0];
+    b->data[head + 1] = (uint8_t)tag[1];
+    b->data[head + 2] = 'Z';
+    memcpy(b->data + head + 3, data, dlen);
+    b->data[head + 3 + dlen] = 0;
     b->l_data = (int)newlen;
-    b->m_data = (uint32_t)newlen;
     return 0;
 }
 
@@ -298,9 +309,10 @@ int sam_read1(samFile *fp, sam_hdr_t *h, bam1_t *b) {
     b->core.bin = bin; b->core.n_cigar = n_cigar; b->core.flag = flag; b->core.l_qseq = l_seq;
     b->core.mtid = next_refID; b->core.mpos = next_pos; b->core.isize = tlen; b->core.l_extranul = 0;
     int l_data = block_size - 32;
-    if ((uint32_t)l_data > b->m_data) {
-        b->data = (uint8_t *)realloc(b->data, (size_t)l_data);
-        b->m_data = (uint32_t)l_data;
+    if ((uint32_t)l_data > b->m_data) { /* htslib: realloc_bam_data rounds the capacity up to a power of two */
+        uint32_t cap = shim_roundup32((uint32_t)l_data);
+        b->data = (uint8_t *)realloc(b->data, (size_t)cap);
+        b->m_data = cap;
     }
     b->l_data = l_data;
     if (l_data && rd(fp->gz, b->data, (size_t)l_data)) return -2;

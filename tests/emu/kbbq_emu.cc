@@ -51,6 +51,14 @@ struct HostQuery {
         return m;
     }
 };
+// ErrCaller holds its query object by value (on the device it is a single pointer): hand it a reference wrapper
+struct HostQueryRef {
+    HostQuery* h;
+    template <class F>
+    uint32_t query(int count, F fn) { return h->query(count, fn); }
+    template <class F>
+    uint32_t map32(F fn) { return h->map32(fn); }
+};
 BloomView make_view(uint64_t* words, const uint64_t* patterns, uint64_t* inserted, uint64_t n_blocks, uint32_t s0, uint32_t s1) {
     BloomView v;
     v.words = (unsigned long long*)words;
@@ -129,7 +137,7 @@ uint64_t emu_get_errors(uint32_t n, const uint64_t* bases, const uint32_t* nmask
         for (int w = 0; w < nw; ++w) { sc.P_w[w] = bases[wo + w]; sc.P_nm[w] = nmask[wo + w]; }
         for (int i = 0; i < L; ++i)
             if (qual[(size_t)wo * 32 + i] <= 6) bit_set(sc.QL, i);
-        ErrCaller<HostQuery> ec(q, k, qual + (size_t)wo * 32, sc);
+        ErrCaller<HostQueryRef> ec(HostQueryRef{&q}, k, qual + (size_t)wo * 32, sc);
         const ErrResult res = ec.run(L);
         for (int w = 0; w < nw; ++w) err_bits[wo + w] = sc.E[w];
         mod_idx[r] = res.mod_idx;

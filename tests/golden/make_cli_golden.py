@@ -47,9 +47,11 @@ def main():
     synth.to_bam(rs, bam, genome_len=4000, rev_every=3, with_oq=True)
     ref(["-k", "31", "-c", "25", "--set-oq", bam], os.path.join(HERE, "cli_bam_out.bam.gz"))
     ref(["-k", "31", "-c", "25", "-g", "4000", "--use-oq", bam], os.path.join(HERE, "cli_bam_useoq_out.bam.gz"))
-    # a BAM without OQ tags: --set-oq appends the tag (bam_aux_update_str, htsiter.cc:13-26)
+    # a BAM without OQ tags: --set-oq appends the tag (bam_aux_update_str, htsiter.cc:13-26).  The reference fetches
+    # bam_get_qual() before that call and writes through it afterwards, so its output is only defined while htslib does
+    # not have to reallocate the record: record 0's long name sizes the (reused) buffer for all later appends.
     bam2 = os.path.join(HERE, "cli_in_nooq.bam")
-    synth.to_bam(rs, bam2, genome_len=4000, rev_every=4, with_oq=False)
+    synth.to_bam(rs, bam2, genome_len=4000, rev_every=4, with_oq=False, first_name=b"r0_" + b"x" * 40)
     ref(["-k", "31", "-c", "25", "--set-oq", bam2], os.path.join(HERE, "cli_bam_nooq_out.bam.gz"))
 
 

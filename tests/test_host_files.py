@@ -1,0 +1,94 @@
+"""CPU-side checks of the host mirror's file layer (kbbq_b200/host: FastqFile, BamFile, the BGZF writer) through
+tests/hosttool -- no GPU: records are read into the ReadStore, and rewritten with the qualities the reference CLI
+produced (taken from the golden outputs); the result must be the golden stream byte for byte."""
+import gzip
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from kbbq_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOOL = os.path.join(ROOT, "tests", "hosttool", "hosttool")
+
+
+@pytest.fixture(scope="module")
+def tool():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "kbbq_b200", "host"), "hosttool"])
+    return TOOL
+
+
+def _records(data):
+    p = 4
+    (lt,) = struct.unpack_from("<i", data, p); p += 4 + lt
+    (nr,) = struct.unpack_from("<i", data, p); p += 4
+    for _ in range(nr):
+        (ln,) = struct.unpack_from("<i", data, p); p += 4 + ln + 4
+    head, out = data[:p], []
+    while p < len(data):
+        (bs,) = struct.unpack_from("<i", data, p)
+        out.append(data[p + 4:p + 4 + bs])
+        p += 4 + bs
+    return head, out
+
+
+def _read_orientation_quals(rec):
+    lname = rec[8]
+    ncig, flag, lseq = struct.unpack_from("<HHi", rec, 12)
+    qoff = 32 + lname + 4 * ncig + (lseq + 1) // 2
+    q = rec[qoff:qoff + lseq]
+    return bytes(c + 33 for c in (q[::-1] if flag & 16 else q))
+
+
+def test_bam_reader_returns_the_read_set(tool):
+    """cli_in.bam was written from this read set with every 3rd record reverse strand (tests/golden/make_cli_golden.py):
+    what BamFile hands out (readutils.hh:30-42, readutils.cc:13-61) must be the read set itself."""
+    rs = synth.make_reads(4000, 25, 150, seed=11, n_rg=2, n_frac=0.002)
+    out = subprocess.run([tool, "dump", os.path.join(GOLD, "cli_in.bam")], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[-1] == "#ref\t4000" and len(out) == rs.n + 1
+    for i, line in enumerate(out[:-1]):
+        name, seq, q, rg, sec = line.split("\t")
+        b0, b1 = int(rs.off[i]), int(rs.off[i + 1])
+        assert name == "r%d" % i
+        assert seq.encode() == rs.seq[b0:b1].tobytes()
+        assert q.encode() == (rs.qual[b0:b1] + 33).tobytes()
+        assert int(rg) == rs.rg[i] and int(sec) == rs.second[i]
+    # --use-oq reads the qualities from the OQ tag (qual+1 in this file)
+    out = subprocess.run([tool, "dump", os.path.join(GOLD, "cli_in.bam"), "use_oq"], capture_output=True, text=True, check=True).stdout.splitlines()
+    q0 = out[0].split("\t")[2].encode()
+    assert q0 == (np.minimum(rs.qual[:150].astype(np.int32) + 1, 93).astype(np.uint8) + 33).tobytes()
+
+
+@pytest.mark.parametrize("inp,gold,flags", [
+    ("cli_in.bam", "cli_bam_out.bam.gz", ["set_oq"]),
+    ("cli_in.bam", "cli_bam_useoq_out.bam.gz", ["use_oq"]),
+    ("cli_in_nooq.bam", "cli_bam_nooq_out.bam.gz", ["set_oq"]),
+])
+def test_bam_writer_reproduces_reference_stream(tool, tmp_path, inp, gold, flags):
+    want = gzip.open(os.path.join(GOLD, gold)).read()
+    _, wr = _records(want)
+    qf = tmp_path / "q.txt"
+    qf.write_bytes(b"\n".join(_read_orientation_quals(r) for r in wr) + b"\n")
+    out = tmp_path / "out.bam"
+    subprocess.run([tool, "rewrite", os.path.join(GOLD, inp), str(qf), str(out)] + flags, check=True)
+    raw = out.read_bytes()
+    assert gzip.decompress(raw) == want
+    # BGZF framing: every member carries the BC extra field and the file ends with the 28-byte EOF block
+    assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[12:14] == b"BC"
+    assert raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def test_fastq_writer_moves_comment_to_plus_line(tool, tmp_path):
+    fq = tmp_path / "in.fq"
+    fq.write_bytes(b"@r0/1 some comment\nACGTN\n+\nIIII#\n@r1/2_RG:Z:x\nGGCC\n+r1\n5555\n")
+    (tmp_path / "q.txt").write_bytes(b"ABCDE\nFGHI\n")
+    out = tmp_path / "out.gz"
+    subprocess.run([tool, "rewrite", str(fq), str(tmp_path / "q.txt"), str(out)], check=True)
+    assert gzip.decompress(out.read_bytes()) == b"@r0/1\nACGTN\n+some comment\nABCDE\n@r1/2_RG:Z:x\nGGCC\n+\nFGHI\n"
+    dump = subprocess.run([tool, "dump", str(fq)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert dump[0].split("\t") == ["r0", "ACGTN", "IIII#", "0", "0"]
+    assert dump[1].split("\t") == ["r1", "GGCC", "5555", "1", "1"]
