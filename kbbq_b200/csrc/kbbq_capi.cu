@@ -88,6 +88,7 @@ struct kbbq_ctx {
     int8_t* d_cy = nullptr;
     int8_t* d_di = nullptr;
     unsigned int* d_work = nullptr;
+    bool count_attr_set = false;
 
     CountView counts() const {
         CountView c;
@@ -117,6 +118,7 @@ struct kbbq_dbatch {
     unsigned long long* d_slot_off = nullptr;
     uint32_t* d_sample_bits = nullptr;
     uint32_t* d_err_bits = nullptr;
+    uint32_t* d_mod = nullptr;  // per read: the base get_errors left modified, or 0xFFFFFFFF (see covariate_count_kernel)
     uint8_t* d_newqual = nullptr;
     BatchView view() const {
         BatchView v;
@@ -158,6 +160,30 @@ int check_launch(kbbq_ctx* ctx, const char* what) {
     ++ctx->launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return KBBQ_OK;
+}
+
+// covariate_count_kernel: rows of the block-private table that fit beside a second resident block, and the launch(es)
+int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, const uint32_t* d_mod) {
+    const int row_cells = KBBQ_HIST_FIXED + 4 * ctx->max_cycle;
+    const long long budget_words = (100 * 1024) / 4 - 2 * KBBQ_HIST_RG;  // 2 blocks/SM inside the 227 KB of an SM
+    int S = (int)std::max(0ll, std::min(64ll, budget_words / (row_cells + 1)));
+    const size_t smem = ((size_t)S + 2 * KBBQ_HIST_RG + (size_t)S * row_cells) * 4;
+    if (!ctx->count_attr_set) {
+        CU(cudaFuncSetAttribute(covariate_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
+        ctx->count_attr_set = true;
+    }
+    const int warps_per_block = KBBQ_HIST_THREADS / 32;
+    const long long need = ((long long)b->n_reads + warps_per_block - 1) / warps_per_block;
+    const int grid = (int)std::max(1ll, std::min(need, (long long)ctx->sm_count * 2));
+    // a block's 32-bit cells must not overflow: at most 2^22 reads (of <= 512 bases) per block and launch
+    const uint64_t per_launch = (uint64_t)grid << 22;
+    for (uint64_t first = 0; first < b->n_reads; first += per_launch) {
+        const uint32_t end = (uint32_t)std::min<uint64_t>(b->n_reads, first + per_launch);
+        covariate_count_kernel<<<grid, KBBQ_HIST_THREADS, smem, ctx->stream>>>(b->view(), ctx->counts(), d_err, d_mod,
+                                                                               (uint32_t)first, end, S);
+        if (int rc = check_launch(ctx, "covariate_count_kernel")) return rc;
+    }
     return KBBQ_OK;
 }
 
@@ -545,7 +571,7 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaStream_t st = ctx ? ctx->stream : nullptr;
     void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
-                    b->d_sample_bits, b->d_err_bits, b->d_newqual};
+                    b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
     delete b;
@@ -731,20 +757,15 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
     if (int rc = filter_ok(ctx, KBBQ_FILTER_TRUSTED)) return rc;
     kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
     if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
-    if (err_bits && !b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
-    if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+    if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+    if (!b->d_mod) CU(cudaMallocAsync(&b->d_mod, std::max<size_t>(b->n_reads, 1) * 4, ctx->stream));
     pass_begin(ctx);
     if (b->n_reads) {
         CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
         pass3_errors_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->counts(), ctx->k, err_bits ? b->d_err_bits : nullptr,
-#if defined(KBBQ_P3_EXPERIMENT)
-            getenv("KBBQ_P3_MODE") ? atoi(getenv("KBBQ_P3_MODE")) : 1,
-#else
-            1,
-#endif
-            ctx->d_work);
+            b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, b->d_err_bits, b->d_mod, ctx->d_work);
         if (int rc = check_launch(ctx, "pass3_errors_kernel")) return rc;
+        if (int rc = launch_count(ctx, b, b->d_err_bits, b->d_mod)) return rc;
     }
     pass_end(ctx);
     return fetch_bits(ctx, b, err_bits);
@@ -757,11 +778,8 @@ int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* er
     if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     if (b->n_words) CU(cudaMemcpyAsync(b->d_err_bits, err_bits, b->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     pass_begin(ctx);
-    if (b->n_reads) {
-        consume_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), ctx->counts(),
-                                                                                                  b->d_err_bits);
-        if (int rc = check_launch(ctx, "consume_kernel")) return rc;
-    }
+    if (b->n_reads)
+        if (int rc = launch_count(ctx, b, b->d_err_bits, nullptr)) return rc;
     pass_end(ctx);
     CU(cudaStreamSynchronize(ctx->stream));  // err_bits is the caller's buffer
     return KBBQ_OK;

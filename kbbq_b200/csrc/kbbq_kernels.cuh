@@ -324,53 +324,170 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
     if (lane == 0 && inserted) atomicAdd(trusted.inserted, inserted);
 }
 
-// ---- covariate counting (covariateutils.cc:30-42,65-76,102-116,147-164) for one read, by one warp -----------------
-// E = read.errors as bit masks; w/nm = the read as consume_read sees it.
-__device__ __forceinline__ void consume_read_warp(const CountView& cv, const unsigned long long* w, const uint32_t* nm,
-                                                  const uint8_t* q, const uint32_t* E, int len, int rg, int sec, int lane) {
-    const int nw = (len + 31) >> 5;
-    int nerr = lane < nw ? __popc(E[lane]) : 0;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) nerr += __shfl_xor_sync(KBBQ_FULL, nerr, d);
-    if (lane == 0) {  // CRGCovariate: {#errors, #bases}; skips are never set (covariateutils.cc:194-197)
-        if (nerr) atomicAdd(cv.rgc + 2 * rg, (unsigned long long)nerr);
-        atomicAdd(cv.rgc + 2 * rg + 1, (unsigned long long)len);
+// ---- covariate counting: CCovariateData::consume_read (covariateutils.cc:30-42,65-76,102-116,147-164,193-202) -------
+// Every base adds to three tables ({errors,total} of its read group x quality, of that row's cycle cell, of that
+// row's dinucleotide cell) and the tables are small and hot: binned qualities put half of all bases on one row.  Sent
+// to global memory that is ~700 M RED operations per 230 Mbases, serialised per address in L2 (measured: 10 ms of a
+// 20 ms pass).  Here each block keeps an associative set of S rows in shared memory -- one row = everything keyed by
+// (read group, quality): its q pair, 16 dinucleotide pairs and 2 x C cycle pairs -- counts there with 32-bit shared
+// atomics, and flushes the rows it used with 64-bit global atomics when it retires.  A row that finds no free slot
+// falls through to global atomics, so any input stays exact.  The launch bounds the reads per block so that no 32-bit
+// cell can overflow.
+#define KBBQ_HIST_THREADS 512
+#define KBBQ_HIST_RG 64            // read groups whose {errors,total} pair is privatised too
+#define KBBQ_HIST_EMPTY 0xFFFFFFFFu
+#define KBBQ_HIST_FIXED 34         // cells of a row before the cycle cells: q pair, 16 dinuc errors, 16 dinuc totals
+
+__device__ __forceinline__ int hist_slot(uint32_t* tags, int S, uint32_t key) {
+    if (S == 0) return -1;
+    uint32_t h = ((key * 0x9E3779B1u) >> 12) % (uint32_t)S;
+#pragma unroll 1
+    for (int probe = 0; probe < 4; ++probe) {
+        const uint32_t t = *reinterpret_cast<volatile uint32_t*>(tags + h);
+        if (t == key) return (int)h;
+        if (t == KBBQ_HIST_EMPTY) {
+            const uint32_t old = atomicCAS(tags + h, KBBQ_HIST_EMPTY, key);
+            if (old == KBBQ_HIST_EMPTY || old == key) return (int)h;
+        }
+        h = h + 1 == (uint32_t)S ? 0 : h + 1;
     }
-    for (int i0 = 0; i0 < len; i0 += 32) {
-        const int i = i0 + lane;
-        const bool in = i < len;
-        const int qi = in ? q[i] : 255;
-        const bool e = in && ((E[i0 >> 5] >> lane) & 1u);
-        const uint32_t emask = __ballot_sync(KBBQ_FULL, e);
-        // CQCovariate: lanes with the same quality add through one leader
-        const uint32_t same_q = __match_any_sync(KBBQ_FULL, qi);
-        const size_t row = (size_t)rg * KBBQ_NQ + qi;
-        if (in && lane == __ffs(same_q) - 1) {
-            atomicAdd(cv.qc + row * 2 + 1, (unsigned long long)__popc(same_q));
-            const int ne = __popc(same_q & emask);
-            if (ne) atomicAdd(cv.qc + row * 2, (unsigned long long)ne);
-        }
-        // CCycleCovariate: cycle = index in read orientation, split by `second`
-        if (in) {
-            unsigned long long* c = cv.cyc + ((row * 2 + sec) * (size_t)cv.max_cycle + i) * 2;
-            atomicAdd(c + 1, 1ull);
-            if (e) atomicAdd(c, 1ull);
-        }
-        // CDinucCovariate: i >= 1, both bases ACGT, qual >= 6
-        int dkey = -1;
-        if (in && i >= 1 && qi >= 6) {
-            const bool n1 = (nm[i >> 5] >> (i & 31)) & 1u, n0 = (nm[(i - 1) >> 5] >> ((i - 1) & 31)) & 1u;
-            if (!n1 && !n0) {
-                const int c1 = (int)((w[i >> 5] >> (2 * (i & 31))) & 3), c0 = (int)((w[(i - 1) >> 5] >> (2 * ((i - 1) & 31))) & 3);
-                dkey = qi * 16 + ((c0 << 2) | c1);
+    return -1;
+}
+
+// err_bits: read.errors as bit masks (kbbq_batch word layout).  mod: per read, 4*index+base of the one base that
+// get_errors left modified in seq (ref quirk, readutils.cc:263-265 vs 568), or 0xFFFFFFFF; nullptr = none.
+__global__ void __launch_bounds__(KBBQ_HIST_THREADS, 2)
+covariate_count_kernel(BatchView b, CountView cv, const uint32_t* __restrict__ err_bits, const uint32_t* __restrict__ mod,
+                       uint32_t first_read, uint32_t end_read, int S) {
+    extern __shared__ uint32_t hist_smem[];
+    const int C = cv.max_cycle, row_cells = KBBQ_HIST_FIXED + 4 * C;
+    uint32_t* tags = hist_smem;
+    uint32_t* rgh = tags + S;
+    uint32_t* rows = rgh + 2 * KBBQ_HIST_RG;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) tags[i] = KBBQ_HIST_EMPTY;
+    for (int i = threadIdx.x; i < 2 * KBBQ_HIST_RG + S * row_cells; i += blockDim.x) rgh[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = first_read + warp; r < end_read; r += nwarps) {
+        const int len = (int)b.len[r];
+        const uint32_t wo = b.word_off[r];
+        const int rg = (int)b.rg[r], sec = b.second[r] ? 1 : 0;
+        const uint32_t md = mod ? mod[r] : 0xFFFFFFFFu;
+        const int nw = (len + 31) >> 5;
+        const uint32_t rowkey0 = (uint32_t)rg * KBBQ_NQ;
+        int nerr = 0;
+        for (int w0 = 0; w0 < nw; w0 += 8) {  // 256 bases at a time: one round of loads, then up to 8 steps of 32 bases
+            const int nwg = nw - w0 < 8 ? nw - w0 : 8;
+            unsigned long long A = 0;
+            uint32_t nm = 0, e = 0, cx = 0;
+            const int wi = w0 + lane;
+            if (lane < nwg) {
+                A = b.bases[wo + wi];
+                nm = b.nmask[wo + wi];
+                e = err_bits[wo + wi];
+                if (wi > 0) cx = (uint32_t)(b.bases[wo + wi - 1] >> 62) | ((b.nmask[wo + wi - 1] >> 31) << 2);
+                if (md != 0xFFFFFFFFu) {
+                    const int mi = (int)(md >> 2), mb = (int)(md & 3u);
+                    if ((mi >> 5) == wi) {
+                        A = (A & ~(3ull << (2 * (mi & 31)))) | ((unsigned long long)mb << (2 * (mi & 31)));
+                        nm &= ~(1u << (mi & 31));
+                    }
+                    if (mi == 32 * wi - 1) cx = (uint32_t)mb;
+                }
+            }
+            uint2 qq = make_uint2(0, 0);
+            if (lane < 4 * nwg) qq = __ldg(reinterpret_cast<const uint2*>(b.qual + (size_t)(wo + w0) * 32) + lane);
+            for (int c = 0; c < nwg; ++c) {
+                const int i = (w0 + c) * 32 + lane;
+                const bool in = i < len;
+                const int src = 4 * c + (lane >> 3);
+                const uint32_t qlo = __shfl_sync(KBBQ_FULL, qq.x, src), qhi = __shfl_sync(KBBQ_FULL, qq.y, src);
+                const int qi = in ? (int)((((lane & 4) ? qhi : qlo) >> (8 * (lane & 3))) & 255u) : 255;
+                const unsigned long long Ac = __shfl_sync(KBBQ_FULL, A, c);
+                const uint32_t nmc = __shfl_sync(KBBQ_FULL, nm, c), emask = __shfl_sync(KBBQ_FULL, e, c);
+                const uint32_t cxc = __shfl_sync(KBBQ_FULL, cx, c);
+                nerr += __popc(emask);
+                const bool er = (emask >> lane) & 1u;
+                // lanes with the same quality share a row: the leader finds (or claims) its slot
+                const uint32_t same_q = __match_any_sync(KBBQ_FULL, qi);
+                const int leader = __ffs(same_q) - 1;
+                const uint32_t key = rowkey0 + (uint32_t)qi;
+                int slot = -1;
+                if (in && lane == leader) slot = hist_slot(tags, S, key);
+                slot = __shfl_sync(KBBQ_FULL, slot, leader);
+                uint32_t* row = rows + (size_t)(slot < 0 ? 0 : slot) * row_cells;
+                if (in && lane == leader) {  // CQCovariate
+                    const int cnt = __popc(same_q), ne = __popc(same_q & emask);
+                    if (slot >= 0) {
+                        atomicAdd(row + 1, (uint32_t)cnt);
+                        if (ne) atomicAdd(row, (uint32_t)ne);
+                    } else {
+                        atomicAdd(cv.qc + (size_t)key * 2 + 1, (unsigned long long)cnt);
+                        if (ne) atomicAdd(cv.qc + (size_t)key * 2, (unsigned long long)ne);
+                    }
+                }
+                if (in) {  // CCycleCovariate: cycle = index in read orientation, split by `second`
+                    if (slot >= 0) {
+                        atomicAdd(row + KBBQ_HIST_FIXED + sec * C + i, 1u);
+                        if (er) atomicAdd(row + KBBQ_HIST_FIXED + 2 * C + sec * C + i, 1u);
+                    } else {
+                        unsigned long long* cc = cv.cyc + (((size_t)key * 2 + sec) * (size_t)C + i) * 2;
+                        atomicAdd(cc + 1, 1ull);
+                        if (er) atomicAdd(cc, 1ull);
+                    }
+                }
+                // CDinucCovariate: i >= 1, both bases ACGT, qual >= 6
+                int dkey = -1;
+                if (in && i >= 1 && qi >= 6) {
+                    const bool n1 = (nmc >> lane) & 1u, n0 = lane ? (nmc >> (lane - 1)) & 1u : (cxc >> 2) & 1u;
+                    if (!n1 && !n0) {
+                        const int c1 = (int)((Ac >> (2 * lane)) & 3), c0 = lane ? (int)((Ac >> (2 * lane - 2)) & 3) : (int)(cxc & 3u);
+                        dkey = qi * 16 + ((c0 << 2) | c1);
+                    }
+                }
+                const uint32_t same_d = __match_any_sync(KBBQ_FULL, dkey);
+                if (dkey >= 0 && lane == __ffs(same_d) - 1) {
+                    const int cnt = __popc(same_d), ne = __popc(same_d & emask), d = dkey & 15;
+                    if (slot >= 0) {
+                        atomicAdd(row + 18 + d, (uint32_t)cnt);
+                        if (ne) atomicAdd(row + 2 + d, (uint32_t)ne);
+                    } else {
+                        unsigned long long* dd = cv.dic + ((size_t)key * 16 + d) * 2;
+                        atomicAdd(dd + 1, (unsigned long long)cnt);
+                        if (ne) atomicAdd(dd, (unsigned long long)ne);
+                    }
+                }
             }
         }
-        const uint32_t same_d = __match_any_sync(KBBQ_FULL, dkey);
-        if (dkey >= 0 && lane == __ffs(same_d) - 1) {
-            unsigned long long* d = cv.dic + ((size_t)rg * KBBQ_NQ * 16 + dkey) * 2;
-            atomicAdd(d + 1, (unsigned long long)__popc(same_d));
-            const int ne = __popc(same_d & emask);
-            if (ne) atomicAdd(d, (unsigned long long)ne);
+        if (lane == 0) {  // CRGCovariate: {#errors, #bases}; skips are never set (covariateutils.cc:194-197)
+            if (rg < KBBQ_HIST_RG) {
+                if (nerr) atomicAdd(rgh + 2 * rg, (uint32_t)nerr);
+                atomicAdd(rgh + 2 * rg + 1, (uint32_t)len);
+            } else {
+                if (nerr) atomicAdd(cv.rgc + 2 * rg, (unsigned long long)nerr);
+                atomicAdd(cv.rgc + 2 * rg + 1, (unsigned long long)len);
+            }
+        }
+    }
+    __syncthreads();
+    // flush what this block counted
+    for (int i = threadIdx.x; i < 2 * KBBQ_HIST_RG; i += blockDim.x)
+        if (rgh[i]) atomicAdd(cv.rgc + i, (unsigned long long)rgh[i]);
+    for (int s = 0; s < S; ++s) {
+        const uint32_t key = tags[s];
+        if (key == KBBQ_HIST_EMPTY) continue;
+        const uint32_t* row = rows + (size_t)s * row_cells;
+        for (int j = threadIdx.x; j < row_cells; j += blockDim.x) {
+            const uint32_t v = row[j];
+            if (!v) continue;
+            unsigned long long* dst;
+            if (j < 2) dst = cv.qc + (size_t)key * 2 + j;
+            else if (j < 18) dst = cv.dic + ((size_t)key * 16 + (j - 2)) * 2;
+            else if (j < KBBQ_HIST_FIXED) dst = cv.dic + ((size_t)key * 16 + (j - 18)) * 2 + 1;
+            else if (j < KBBQ_HIST_FIXED + 2 * C) dst = cv.cyc + ((size_t)key * 2 * C + (j - KBBQ_HIST_FIXED)) * 2 + 1;
+            else dst = cv.cyc + ((size_t)key * 2 * C + (j - KBBQ_HIST_FIXED - 2 * C)) * 2;
+            atomicAdd(dst, (unsigned long long)v);
         }
     }
 }
@@ -413,8 +530,10 @@ struct DevQuery {
 #ifndef KBBQ_P3_MIN_BLOCKS
 #define KBBQ_P3_MIN_BLOCKS 4
 #endif
+// Writes read.errors (err_out, kbbq_batch word layout) and, per read, the base get_errors left modified (mod_out, see
+// covariate_count_kernel); the counting itself is covariate_count_kernel's.
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
-pass3_errors_kernel(BatchView b, BloomView trusted, CountView cv, int k, uint32_t* __restrict__ err_out, int do_consume,
+pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ err_out, uint32_t* __restrict__ mod_out,
                     unsigned int* __restrict__ work_counter) {
     __shared__ ErrScratch scratch[KBBQ_WARPS_PER_BLOCK];
     __shared__ BloomView filter;
@@ -445,48 +564,10 @@ pass3_errors_kernel(BatchView b, BloomView trusted, CountView cv, int k, uint32_
         }
         __syncwarp();
         ErrCaller<DevQuery> ec(q, k, qual, sc);
-#if defined(KBBQ_P3_EXPERIMENT)
-        ErrResult res;
-        res.mod_idx = -1; res.mod_base = -1;
-        if (do_consume & 2) { if (len >= k) { SeqRef P{sc.P_w, sc.P_nm, len}; ec.scan(P, sc.T_orig); } }
-        else res = ec.run(len);
-#else
         const ErrResult res = ec.run(len);
-#endif
         __syncwarp();
-        if (err_out && lane < nw) err_out[wo + lane] = sc.E[lane];
-        if (do_consume & 1) {
-            // consume_read sees the original bases (readutils.cc:568) except for the early-return quirk
-            if (lane < nw) {
-                sc.A_w[lane] = b.bases[wo + lane];
-                sc.A_nm[lane] = b.nmask[wo + lane];
-            }
-            __syncwarp();
-            if (res.mod_idx >= 0) {
-                SeqRef a{sc.A_w, sc.A_nm, len};
-                seq_set(a, res.mod_idx, res.mod_base);
-                __syncwarp();
-            }
-            consume_read_warp(cv, sc.A_w, sc.A_nm, qual, sc.E, len, (int)b.rg[r], b.second[r] ? 1 : 0, lane);
-        }
-        __syncwarp();
-    }
-}
-
-// ---- --fixed mode: caller-supplied error flags, then consume_read (kbbq.cc:367-378) ----------------------------------
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32)
-consume_kernel(BatchView b, CountView cv, const uint32_t* __restrict__ err_bits) {
-    __shared__ uint32_t E_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
-        const int len = (int)b.len[r];
-        const uint32_t wo = b.word_off[r];
-        const int nw = (len + 31) >> 5;
-        if (lane < nw) E_all[wib][lane] = err_bits[wo + lane];
-        __syncwarp();
-        consume_read_warp(cv, b.bases + wo, b.nmask + wo, b.qual + (size_t)wo * 32, E_all[wib], len, (int)b.rg[r],
-                          b.second[r] ? 1 : 0, lane);
+        if (lane < nw) err_out[wo + lane] = sc.E[lane];
+        if (lane == 0) mod_out[r] = res.mod_idx >= 0 ? (uint32_t)(4 * res.mod_idx + res.mod_base) : 0xFFFFFFFFu;
         __syncwarp();
     }
 }

@@ -15,7 +15,7 @@ def test_gpu_pipeline_matches_golden(name):
     rs, g = common.load_pipe(name)
     got = common.run_gpu(rs, int(g["k"]), int(g["genomelen"]), int(g["coverage"]), int(g["seed"]))
     common.compare(got, g, what=name + ": ")
-    assert got["stats"].launches == 5  # rng, insert, trusted, errors, apply
+    assert got["stats"].launches == 6  # rng, insert, trusted, errors, covariate counts, apply
 
 
 @pytest.mark.parametrize("k,cov,L,kw", [
