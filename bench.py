@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -170,13 +170,20 @@ def algorithmic_bytes(n_reads, L, k, sampled_ins, trusted_ins):
         "pass2": n_reads * (P + M + L + nk * 64) + trusted_ins * 128,
         "pass3": n_reads * (P + M + L + nk * 64),
         "pass4": n_reads * (P + M + 2 * L),
+        # per kernel (pass 1 and pass 3 are two kernels each)
+        "rng_sample_kernel": n_reads * 8 * ((nk + 63) // 64),
+        "pass1_insert_kernel": n_reads * (P + M + 8 * ((nk + 63) // 64)) + sampled_ins * 128,
+        "pass2_trusted_kernel": n_reads * (P + M + L + nk * 64) + trusted_ins * 128,
+        "pass3_errors_kernel": n_reads * (P + M + L + nk * 64),
+        "covariate_count_kernel": n_reads * (P + M + L + M),
+        "pass4_apply_kernel": n_reads * (P + M + 2 * L),
     }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,15 +285,14 @@ def main():
     merge_ms = {p: float(np.mean([s.merge_ms[p] for s in stats])) for p in stats[0].merge_ms}
     # per-rank insert counts for the byte model: merged counters / world is the per-rank average
     ab = algorithmic_bytes(rs.n, READ_LEN, K, sampled_ins // world, trusted_ins // world)
-    dom = max(pass_ms, key=pass_ms.get)
+    kernel_ms = {kn: float(np.mean([s.kernel_ms[kn] for s in stats])) for kn in stats[0].kernel_ms}
+    dom = max(kernel_ms, key=kernel_ms.get)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = ab[dom] / (pass_ms[dom] * 1e-3) / 1e9
-    kernel_names = {"pass1": "pass1_insert_kernel (+rng_sample_kernel)", "pass2": "pass2_trusted_kernel",
-                    "pass3": "pass3_errors_kernel", "pass4": "pass4_apply_kernel"}
+    achieved = ab[dom] / (kernel_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -294,9 +300,11 @@ def main():
             traffic = json.load(open(tpath)).get(dom)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab[dom], "ms_per_launch": pass_ms[dom],
+                "algorithmic_bytes_per_launch": ab[dom], "ms_per_launch": kernel_ms[dom],
+                "all_kernels": {kn: {"ms": kernel_ms[kn], "GBps": ab[kn] / (kernel_ms[kn] * 1e-3) / 1e9,
+                                     "frac": ab[kn] / (kernel_ms[kn] * 1e-3) / 1e9 / peak} for kn in kernel_ms},
                 "all_passes": {p: {"ms": pass_ms[p], "GBps": ab[p] / (pass_ms[p] * 1e-3) / 1e9, "frac": ab[p] / (pass_ms[p] * 1e-3) / 1e9 / peak}
                                for p in pass_ms}}
 
@@ -319,7 +327,7 @@ def main():
             "clocks": clock_info,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "breakdown_ms": {"passes": pass_ms, "host": host_ms, "merge": merge_ms},
+            "breakdown_ms": {"passes": pass_ms, "kernels": kernel_ms, "host": host_ms, "merge": merge_ms},
         }))
     rc.close()
     if world > 1:

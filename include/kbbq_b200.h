@@ -109,6 +109,9 @@ int kbbq_sync(kbbq_ctx* ctx);
 void* kbbq_stream(kbbq_ctx* ctx);
 /* device time of the most recent pass call in ms (CUDA events on the context's stream); syncs */
 int kbbq_last_pass_ms(kbbq_ctx* ctx, float* ms);
+/* the kernels of the most recent pass call and their device times (events between the launches): fills up to `max`
+ * entries of names[] (static strings) and ms[], returns how many, or a negative KBBQ_E* code; syncs */
+int kbbq_last_pass_kernels(kbbq_ctx* ctx, int max, const char** names, float* ms);
 /* kernels launched by this context so far */
 uint64_t kbbq_launch_count(kbbq_ctx* ctx);
 
@@ -134,6 +137,10 @@ int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other_device_words,
 
 /* ---- batches -------------------------------------------------------------------------------------------------------- */
 int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
+/* Same, but the quality array (3/4 of the bytes) is copied on a side stream and may still be in flight on return:
+ * pass 1 does not read it and overlaps the copy; passes 2-4 wait for it on the device.  host->qual must stay valid and
+ * unmodified until kbbq_sync() has returned (with pinned memory the copy is truly asynchronous). */
+int kbbq_batch_upload_async(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
 void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b);
 /* number of k-mer slots of the batch = sum over reads of max(0, len-k+1): the draws pass 1 consumes */
 uint64_t kbbq_batch_slots(const kbbq_dbatch* b);

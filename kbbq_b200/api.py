@@ -75,6 +75,7 @@ def lib():
         L.kbbq_stream.restype = vp
         L.kbbq_stream.argtypes = [vp]
         L.kbbq_last_pass_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.kbbq_last_pass_kernels.argtypes = [vp, i32, vp, vp]
         L.kbbq_launch_count.restype = u64
         L.kbbq_launch_count.argtypes = [vp]
         L.kbbq_bloom_create.argtypes = [vp, i32, u64, dbl, u64]
@@ -92,6 +93,7 @@ def lib():
         L.kbbq_bloom_device_counter.argtypes = [vp, i32]
         L.kbbq_bloom_or_from.argtypes = [vp, i32, vp, u64, u64]
         L.kbbq_batch_upload.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
+        L.kbbq_batch_upload_async.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
         L.kbbq_batch_free.argtypes = [vp, vp]
         L.kbbq_batch_slots.restype = u64
         L.kbbq_batch_slots.argtypes = [vp]
@@ -287,6 +289,15 @@ class Context:
         _check(self.L.kbbq_last_pass_ms(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def last_pass_kernels(self) -> dict:
+        """{kernel name: device ms} of the most recent pass call (events between the launches)."""
+        names = (C.c_char_p * 8)()
+        ms = (C.c_float * 8)()
+        n = self.L.kbbq_last_pass_kernels(self.h, 8, names, ms)
+        if n < 0:
+            _check(n)
+        return {names[i].decode(): float(ms[i]) for i in range(n)}
+
     @property
     def launches(self) -> int:
         return int(self.L.kbbq_launch_count(self.h))
@@ -344,9 +355,11 @@ class Context:
 
     # batches
     def upload(self, pb: PackedBatch) -> "DeviceBatch":
+        """The qualities travel on the library's side stream while pass 1 runs (kbbq_batch_upload_async): the
+        DeviceBatch keeps `pb` alive, and pb's arrays must not be modified before the next sync()."""
         s = pb.as_struct()
         h = C.c_void_p()
-        _check(self.L.kbbq_batch_upload(self.h, C.byref(s), C.byref(h)))
+        _check(self.L.kbbq_batch_upload_async(self.h, C.byref(s), C.byref(h)))
         return DeviceBatch(self, h, pb)
 
     # passes

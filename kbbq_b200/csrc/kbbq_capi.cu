@@ -3,6 +3,7 @@
 #include "../../include/kbbq_b200.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -57,6 +58,8 @@ struct Filter {
 
 }  // namespace
 
+#define KBBQ_MAX_PASS_KERNELS 4
+
 struct kbbq_ctx {
     int device = 0;
     int k = 32;
@@ -64,7 +67,11 @@ struct kbbq_ctx {
     int max_cycle = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // side stream: quality arrays travel while pass 1 runs on `stream`
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk[KBBQ_MAX_PASS_KERNELS + 1] = {};  // marks around the kernels of the most recent pass
+    const char* kname[KBBQ_MAX_PASS_KERNELS] = {};
+    int n_marks = 0;
     bool timed = false;
     uint64_t launches = 0;
     Filter filt[2];
@@ -120,6 +127,8 @@ struct kbbq_dbatch {
     uint32_t* d_err_bits = nullptr;
     uint32_t* d_mod = nullptr;  // per read: the base get_errors left modified, or 0xFFFFFFFF (see covariate_count_kernel)
     uint8_t* d_newqual = nullptr;
+    cudaEvent_t qual_ready = nullptr;  // recorded on the copy stream after d_qual's upload
+    bool qual_waited = true;           // false until `stream` has been made to wait for qual_ready
     BatchView view() const {
         BatchView v;
         v.bases = d_bases;
@@ -143,10 +152,27 @@ int use(kbbq_ctx* ctx) {
     return KBBQ_OK;
 }
 
-void pass_begin(kbbq_ctx* ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
+void pass_begin(kbbq_ctx* ctx) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    ctx->n_marks = 0;
+}
 void pass_end(kbbq_ctx* ctx) {
     cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->timed = true;
+}
+// call right before launching kernel `name`; the previous kernel's interval ends here
+void mark_kernel(kbbq_ctx* ctx, const char* name) {
+    if (ctx->n_marks >= KBBQ_MAX_PASS_KERNELS) return;
+    cudaEventRecord(ctx->evk[ctx->n_marks], ctx->stream);
+    ctx->kname[ctx->n_marks++] = name;
+}
+// passes that read the qualities wait (once) for their upload on the copy stream
+int need_quals(kbbq_ctx* ctx, kbbq_dbatch* b) {
+    if (!b->qual_waited) {
+        CU(cudaStreamWaitEvent(ctx->stream, b->qual_ready, 0));
+        b->qual_waited = true;
+    }
+    return KBBQ_OK;
 }
 
 // one warp per read; enough blocks to fill every SM's 64 warp slots, no more than the reads need
@@ -184,6 +210,21 @@ int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, con
                                                                                (uint32_t)first, end, S);
         if (int rc = check_launch(ctx, "covariate_count_kernel")) return rc;
     }
+    return KBBQ_OK;
+}
+
+// d_slot_off[0..n] = exclusive prefix sum of max(0, len[r]-k+1) (the k-mer slots of the reads before r):
+// slot_counts_kernel writes the n counts and a trailing 0, cub scans the n+1 items in place
+int slot_prefix(kbbq_ctx* ctx, const uint32_t* d_len, uint32_t n, unsigned long long* d_slot_off) {
+    slot_counts_kernel<<<(unsigned)(((size_t)n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_len, n, ctx->k, d_slot_off);
+    if (int rc = check_launch(ctx, "slot_counts_kernel")) return rc;
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_slot_off, d_slot_off, (size_t)n + 1, ctx->stream));
+    void* tmp = nullptr;
+    CU(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), ctx->stream));
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_slot_off, d_slot_off, (size_t)n + 1, ctx->stream);
+    cudaFreeAsync(tmp, ctx->stream);
+    if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("slot prefix: ") + cudaGetErrorString(e));
     return KBBQ_OK;
 }
 
@@ -372,8 +413,10 @@ int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) 
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    for (auto& e : c->evk) CU(cudaEventCreate(&e));
     c->n_rgc = (size_t)n_rg * 2;
     c->n_qc = (size_t)n_rg * KBBQ_NQ * 2;
     c->n_cyc = (size_t)n_rg * KBBQ_NQ * 2 * max_cycle * 2;
@@ -407,12 +450,16 @@ void kbbq_ctx_destroy(kbbq_ctx* c) {
     cudaFree(c->d_work);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (auto& e : c->evk) cudaEventDestroy(e);
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int kbbq_sync(kbbq_ctx* ctx) {
     if (int rc = use(ctx)) return rc;
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return KBBQ_OK;
 }
@@ -425,6 +472,20 @@ int kbbq_last_pass_ms(kbbq_ctx* ctx, float* ms) {
     CU(cudaEventSynchronize(ctx->ev1));
     CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
     return KBBQ_OK;
+}
+
+int kbbq_last_pass_kernels(kbbq_ctx* ctx, int max, const char** names, float* ms) {
+    if (int rc = use(ctx)) return rc < 0 ? rc : -rc;
+    if (!ctx->timed) return fail(KBBQ_ESTATE, "no pass has run");
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return fail(KBBQ_ECUDA, "event sync failed");
+    int n = 0;
+    for (int i = 0; i < ctx->n_marks && n < max; ++i, ++n) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->evk[i], i + 1 < ctx->n_marks ? ctx->evk[i + 1] : ctx->ev1);
+        if (names) names[n] = ctx->kname[i];
+        if (ms) ms[n] = t;
+    }
+    return n;
 }
 
 uint64_t kbbq_launch_count(kbbq_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -572,27 +633,41 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     cudaStream_t st = ctx ? ctx->stream : nullptr;
     void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
                     b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual};
+    if (b->qual_ready) {
+        if (ctx && !b->qual_waited) cudaStreamWaitEvent(st, b->qual_ready, 0);  // d_qual is freed in `st`'s order
+        cudaEventDestroy(b->qual_ready);
+    }
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
     delete b;
 }
 
-int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) {
+static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, bool async_qual);
+
+int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) { return batch_upload(ctx, h, out, false); }
+int kbbq_batch_upload_async(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) { return batch_upload(ctx, h, out, true); }
+
+static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, bool async_qual) {
     if (int rc = use(ctx)) return rc;
     if (!h || !out) return fail(KBBQ_EINVAL, "null argument");
     if (h->max_len > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
     if ((int)h->max_len > ctx->max_cycle) return fail(KBBQ_ERANGE, "read longer than the context's max_cycle");
     const uint32_t n = h->n_reads;
-    std::vector<unsigned long long> slot_off((size_t)n + 1);
+    // validation and the slot total in tight host loops; the per-read prefix (slot_off) is made on the device
     unsigned long long slots = 0;
-    for (uint32_t r = 0; r < n; ++r) {
-        slot_off[r] = slots;
-        const uint32_t l = h->len[r];
-        if (l > h->max_len) return fail(KBBQ_ERANGE, "len[r] exceeds max_len");
-        if (h->rg && h->rg[r] >= ctx->n_rg) return fail(KBBQ_ERANGE, "read group id >= n_rg");
-        if ((int)l >= ctx->k) slots += l - ctx->k + 1;
+    {
+        uint32_t longest = 0, biggest_rg = 0;
+        const uint32_t km1 = (uint32_t)ctx->k - 1;
+        for (uint32_t r = 0; r < n; ++r) {
+            const uint32_t l = h->len[r];
+            longest = std::max(longest, l);
+            slots += l > km1 ? l - km1 : 0;
+        }
+        if (h->rg)
+            for (uint32_t r = 0; r < n; ++r) biggest_rg = std::max<uint32_t>(biggest_rg, h->rg[r]);
+        if (longest > h->max_len) return fail(KBBQ_ERANGE, "len[r] exceeds max_len");
+        if (n && biggest_rg >= (uint32_t)ctx->n_rg) return fail(KBBQ_ERANGE, "read group id >= n_rg");
     }
-    slot_off[n] = slots;
     kbbq_dbatch* b = new (std::nothrow) kbbq_dbatch();
     if (!b) return fail(KBBQ_ENOMEM, "out of host memory");
     b->n_reads = n; b->max_len = h->max_len; b->n_words = h->n_words; b->n_slots = slots; b->k = ctx->k;
@@ -617,14 +692,40 @@ int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) {
         CU(cudaMemcpyAsync(b->d_bases, h->bases, h->n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(b->d_nmask, h->nmask, h->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    UP(b->d_qual, h->qual, (size_t)h->n_words * 32);
     UP(b->d_word_off, h->word_off, ((size_t)n + 1) * 4);
     UP(b->d_len, h->len, (size_t)n * 4);
     UP(b->d_rg, h->rg, (size_t)n * 2);
     UP(b->d_second, h->second, (size_t)n);
-    UP(b->d_slot_off, slot_off.data(), ((size_t)n + 1) * 8);
+    UP(b->d_slot_off, (const void*)nullptr, ((size_t)n + 1) * 8);
 #undef UP
-    CU(cudaStreamSynchronize(ctx->stream));  // slot_off is a stack-owned vector
+    if (n) {  // slot_off = exclusive prefix of max(0, len-k+1), n+1 entries
+        if (int rc = slot_prefix(ctx, b->d_len, n, b->d_slot_off)) {
+            kbbq_batch_free(ctx, b);
+            return rc;
+        }
+    }
+    {   // the qualities (3/4 of the bytes) go last and on the copy stream: pass 1 does not read them and starts
+        // as soon as everything above has landed
+        const size_t qbytes = std::max<size_t>((size_t)h->n_words * 32, 16);
+        cudaError_t e2 = cudaMallocAsync(&b->d_qual, qbytes, ctx->stream);  // allocated in `stream` order ...
+        cudaEvent_t alloc_done = nullptr;
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventRecord(alloc_done, ctx->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);  // ... filled in the copy stream's
+        if (e2 == cudaSuccess && !h->n_words) e2 = cudaMemsetAsync(b->d_qual, 0, qbytes, ctx->copy_stream);
+        if (e2 == cudaSuccess && h->n_words)
+            e2 = cudaMemcpyAsync(b->d_qual, h->qual, (size_t)h->n_words * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&b->qual_ready, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventRecord(b->qual_ready, ctx->copy_stream);
+        if (alloc_done) cudaEventDestroy(alloc_done);
+        if (e2 != cudaSuccess) {
+            kbbq_batch_free(ctx, b);
+            return fail(e2 == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA, std::string("batch upload: ") + cudaGetErrorString(e2));
+        }
+        b->qual_waited = false;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));  // the caller may reuse everything but h->qual
+    if (!async_qual) CU(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse h->qual
     *out = b;
     return KBBQ_OK;
 }
@@ -689,9 +790,11 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
         uint64_t st[4];
         std::memcpy(st, ctx->sampler_state0, 32);
         host::rng_advance(st, ctx->sampler_pos);
+        mark_kernel(ctx, "rng_sample_kernel");
         rng_sample_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(st[0], st[1], st[2], st[3], ctx->d_jump,
                                                                                      b->n_slots, ctx->sample_threshold, ctx->sample_all, b->d_sample_bits);
         if (int rc = check_launch(ctx, "rng_sample_kernel")) return rc;
+        mark_kernel(ctx, "pass1_insert_kernel");
         pass1_insert_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
             b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);
         if (int rc = check_launch(ctx, "pass1_insert_kernel")) return rc;
@@ -740,8 +843,10 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     }
     if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+    if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {
+        mark_kernel(ctx, "pass2_trusted_kernel");
         pass2_trusted_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
             b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, ctx->d_thresholds,
             err_bits ? b->d_err_bits : nullptr);
@@ -759,12 +864,15 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
     if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
     if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     if (!b->d_mod) CU(cudaMallocAsync(&b->d_mod, std::max<size_t>(b->n_reads, 1) * 4, ctx->stream));
+    if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {
         CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+        mark_kernel(ctx, "pass3_errors_kernel");
         pass3_errors_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
             b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, b->d_err_bits, b->d_mod, ctx->d_work);
         if (int rc = check_launch(ctx, "pass3_errors_kernel")) return rc;
+        mark_kernel(ctx, "covariate_count_kernel");
         if (int rc = launch_count(ctx, b, b->d_err_bits, b->d_mod)) return rc;
     }
     pass_end(ctx);
@@ -777,9 +885,12 @@ int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* er
     if (!b || !err_bits) return fail(KBBQ_EINVAL, "null argument");
     if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     if (b->n_words) CU(cudaMemcpyAsync(b->d_err_bits, err_bits, b->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
-    if (b->n_reads)
+    if (b->n_reads) {
+        mark_kernel(ctx, "covariate_count_kernel");
         if (int rc = launch_count(ctx, b, b->d_err_bits, nullptr)) return rc;
+    }
     pass_end(ctx);
     CU(cudaStreamSynchronize(ctx->stream));  // err_bits is the caller's buffer
     return KBBQ_OK;
@@ -860,8 +971,10 @@ int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_o
         CU(cudaMallocAsync(&b->d_newqual, std::max<size_t>((size_t)b->n_words * 32, 16), ctx->stream));
         CU(cudaMemsetAsync(b->d_newqual, 0, std::max<size_t>((size_t)b->n_words * 32, 16), ctx->stream));
     }
+    if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {
+        mark_kernel(ctx, "pass4_apply_kernel");
         ModelView mv{ctx->d_base, ctx->d_cy, ctx->d_di, ctx->max_cycle};
         pass4_apply_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), mv, b->d_newqual);
         if (int rc = check_launch(ctx, "pass4_apply_kernel")) return rc;

@@ -144,6 +144,9 @@ __device__ __noinline__ uint32_t coop_probe_call(const unsigned long long* words
 // All 32 lanes must call.
 template <bool INLINE>
 __device__ __forceinline__ uint32_t warp_bloom_query(const BloomView& f, bool valid, uint64_t key) {
+#if defined(KBBQ_P2_PER_LANE)
+    return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(f, key));
+#endif
     const uint32_t vmask = __ballot_sync(KBBQ_FULL, valid);
     if (vmask == 0) return 0;
     const uint64_t blk = valid ? bloom_block(f, key) : 0;
@@ -181,6 +184,14 @@ __device__ __forceinline__ int warp_bloom_insert(const BloomView& f, bool ins, u
     }
     __syncwarp();
     return n;
+}
+
+// ---- batch set-up: k-mer slots per read (max(0, len-k+1)) and a trailing 0, scanned in place into slot_off ---------
+__global__ void slot_counts_kernel(const uint32_t* __restrict__ len, uint32_t n, int k, unsigned long long* __restrict__ out) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    const uint32_t l = r < n ? len[r] : 0u;
+    out[r] = l >= (uint32_t)k ? (unsigned long long)(l - (uint32_t)k + 1) : 0ull;
 }
 
 // ---- pass 1a: the sampling stream ---------------------------------------------------------------------------------
@@ -264,7 +275,10 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
 }
 
 // ---- pass 2: infer_read_errors + find_trusted_kmers (readutils.cc:173-193, bloom.cc:28-67, recalibrateutils.cc:15-40)
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32)
+#ifndef KBBQ_P2_MIN_BLOCKS
+#define KBBQ_P2_MIN_BLOCKS 4  // 64 registers, 32 warps/SM: 5.05 ms vs 6.61 unbounded (78 registers, 24 warps)
+#endif
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P2_MIN_BLOCKS)
 pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, const int* __restrict__ thresholds,
                      uint32_t* __restrict__ err_out) {
     __shared__ int thr[KBBQ_MAX_K + 1];
@@ -573,35 +587,85 @@ pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict_
 }
 
 // ---- pass 4: CReadData::recalibrate (readutils.cc:572-595) as a fused table lookup ---------------------------------
+// One warp per read, one lane per 8 consecutive bases: the qualities move as one 8-byte load and one 8-byte store per
+// lane (a 150-base read is a single warp instruction each way), the 24 table lookups of a lane are independent.
+// The loop is software pipelined two deep -- read r+2's header and read r+1's words are in flight while read r is
+// looked up -- because a warp's own chain (header -> words -> tables -> store) is three memory round trips long.
+struct P4Head {
+    int len, sec;
+    uint32_t wo;
+    size_t rgrow;
+};
+struct P4Data {
+    uint2 qq;
+    uint32_t codes, nflags;  // the lane's 8 bases and the one before them, 2 bits each from bit 0; N flags likewise
+};
+__device__ __forceinline__ P4Head p4_head(const BatchView& b, uint32_t r) {
+    P4Head h;
+    h.len = 0; h.sec = 0; h.wo = 0; h.rgrow = 0;
+    if (r < b.n_reads) {
+        h.len = (int)b.len[r];
+        h.wo = b.word_off[r];
+        h.rgrow = (size_t)b.rg[r] * KBBQ_NQ;
+        h.sec = b.second[r] ? 1 : 0;
+    }
+    return h;
+}
+__device__ __forceinline__ P4Data p4_data(const BatchView& b, const P4Head& h, int i0) {
+    P4Data d;
+    d.qq = make_uint2(0, 0); d.codes = 0; d.nflags = 0;
+    if (i0 < h.len) {
+        const uint32_t w = h.wo + (uint32_t)(i0 >> 5);
+        const int o = i0 & 31;  // 0, 8, 16, 24
+        d.qq = __ldg(reinterpret_cast<const uint2*>(b.qual + (size_t)h.wo * 32 + i0));
+        const unsigned long long bw = b.bases[w];
+        const uint32_t nw = b.nmask[w];
+        if (o) {
+            d.codes = (uint32_t)(bw >> (2 * o - 2)) & 0x3FFFFu;
+            d.nflags = (nw >> (o - 1)) & 0x1FFu;
+        } else {
+            const unsigned long long pw = i0 ? b.bases[w - 1] : 0ull;
+            const uint32_t pn = i0 ? b.nmask[w - 1] : 1u << 31;  // no base before the first: no dinucleotide
+            d.codes = ((uint32_t)bw << 2 | (uint32_t)(pw >> 62)) & 0x3FFFFu;
+            d.nflags = (nw << 1 | pn >> 31) & 0x1FFu;
+        }
+    }
+    return d;
+}
+__device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Head& h, const P4Data& d, int i0, uint8_t* __restrict__ out) {
+    if (i0 >= h.len) return;
+    uint32_t res[2] = {d.qq.x, d.qq.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j;
+        const int qi = (int)((res[j >> 2] >> (8 * (j & 3))) & 255u);
+        if (i < h.len && qi >= 6) {  // minqual: lower qualities pass through unchanged
+            const size_t row = h.rgrow + qi;
+            int v = mv.base[row] + mv.cy[(row * 2 + h.sec) * (size_t)mv.max_cycle + i];
+            if (((d.nflags >> j) & 3u) == 0) {  // this base and the one before it are ACGT (and i > 0)
+                const uint32_t x = (d.codes >> (2 * j)) & 15u;  // previous base in the low pair
+                v += mv.di[row * 16 + (((x & 3u) << 2) | (x >> 2))];
+            }
+            v = v < 0 ? 0 : (v > KBBQ_MAXQ ? KBBQ_MAXQ : v);
+            res[j >> 2] = (res[j >> 2] & ~(255u << (8 * (j & 3)))) | ((uint32_t)v << (8 * (j & 3)));
+        }
+    }
+    *reinterpret_cast<uint2*>(out + (size_t)h.wo * 32 + i0) = make_uint2(res[0], res[1]);
+}
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32)
 pass4_apply_kernel(BatchView b, ModelView mv, uint8_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (warp >= b.n_reads) return;
+    P4Head h0 = p4_head(b, warp);
+    P4Head h1 = p4_head(b, warp + nwarps);
+    P4Data d0 = p4_data(b, h0, 8 * lane);
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
-        const int len = (int)b.len[r];
-        const uint32_t wo = b.word_off[r];
-        const unsigned long long* w = b.bases + wo;
-        const uint32_t* nm = b.nmask + wo;
-        const uint8_t* q = b.qual + (size_t)wo * 32;
-        const size_t rgrow = (size_t)b.rg[r] * KBBQ_NQ;
-        const int sec = b.second[r] ? 1 : 0;
-        for (int i = lane; i < len; i += 32) {
-            const int qi = q[i];
-            int v = qi;
-            if (qi >= 6) {  // minqual: lower qualities pass through unchanged
-                const size_t row = rgrow + qi;
-                v = mv.base[row] + mv.cy[(row * 2 + sec) * (size_t)mv.max_cycle + i];
-                if (i > 0) {
-                    const bool n1 = (nm[i >> 5] >> (i & 31)) & 1u, n0 = (nm[(i - 1) >> 5] >> ((i - 1) & 31)) & 1u;
-                    if (!n1 && !n0) {
-                        const int c1 = (int)((w[i >> 5] >> (2 * (i & 31))) & 3), c0 = (int)((w[(i - 1) >> 5] >> (2 * ((i - 1) & 31))) & 3);
-                        v += mv.di[row * 16 + ((c0 << 2) | c1)];
-                    }
-                }
-                v = v < 0 ? 0 : (v > KBBQ_MAXQ ? KBBQ_MAXQ : v);
-            }
-            out[(size_t)wo * 32 + i] = (uint8_t)v;
-        }
+        const P4Head h2 = p4_head(b, r + 2 * nwarps);  // header two reads ahead
+        const P4Data d1 = p4_data(b, h1, 8 * lane);    // words one read ahead
+        p4_apply(mv, h0, d0, 8 * lane, out);
+        for (int i0 = 256 + 8 * lane; i0 < h0.len; i0 += 256) p4_apply(mv, h0, p4_data(b, h0, i0), i0, out);  // reads > 256 bases
+        h0 = h1; h1 = h2; d0 = d1;
     }
 }
 

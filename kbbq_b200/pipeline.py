@@ -24,6 +24,7 @@ from . import api
 @dataclass
 class RunStats:
     pass_ms: dict = field(default_factory=dict)   # device time per pass (CUDA events), summed over batches
+    kernel_ms: dict = field(default_factory=dict) # device time per kernel (events between launches), summed over batches
     host_ms: dict = field(default_factory=dict)   # host maths between passes
     merge_ms: dict = field(default_factory=dict)  # collectives
     sampled_inserted: int = 0
@@ -83,6 +84,8 @@ class Recalibrator:
             for b in self.batches:
                 outs.append(fn(b))
                 total += ctx.last_pass_ms()
+                for kn, kms in ctx.last_pass_kernels().items():
+                    st.kernel_ms[kn] = st.kernel_ms.get(kn, 0.0) + kms
             st.pass_ms[name] = total
             return outs
 
