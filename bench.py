@@ -36,8 +36,10 @@ SAMPLE_GENOME = 400_000  # bounded CPU sample: 133 k reads, 20 Mbases, ~8 s of s
 METRIC = "bases recalibrated/sec"
 
 
-def workload_name(n):
-    return (f"synthetic {n}x4.6 Mb genome, 50X, 150 bp reads, 2 read groups (BASELINE.json configs[1] shape; "
+def workload_name(n, genome=GENOME, coverage=COVERAGE):
+    which = ("BASELINE.json configs[1] shape" if (genome, coverage) == (GENOME, COVERAGE) else
+             "BASELINE.json configs[2] shape" if (genome, coverage) == (64_000_000, 30) else "custom shape")
+    return (f"synthetic {n}x{genome / 1e6:.1f} Mb genome, {coverage}X, 150 bp reads, 2 read groups ({which}; "
             f"packed 2-bit batches instead of BAM records), k=32")
 
 
@@ -188,6 +190,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--genome", type=int, default=GENOME, help="per-GPU genome length (default: config 2)")
+    ap.add_argument("--coverage", type=int, default=COVERAGE, help="coverage (default: config 2's 50; config 3: --genome 64000000 --coverage 30)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -208,17 +211,19 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         comm = GpuComm(rank, world, local)
 
     # ---- synthetic shard of this rank: reads over the WHOLE (world x per-GPU) genome, distinct seed per rank
     genomelen = args.genome * world
-    n_reads = args.genome * COVERAGE // READ_LEN
-    rs = synth.make_reads(genomelen, COVERAGE, READ_LEN, seed=1000 + rank, n_rg=N_RG, n_reads=n_reads)
+    n_reads = args.genome * args.coverage // READ_LEN
+    rs = synth.make_reads(genomelen, args.coverage, READ_LEN, seed=1000 + rank, n_rg=N_RG, n_reads=n_reads, keep_clean=False)
     pb = api.PackedBatch(rs, pinned=True)
     total_bases = rs.total_bases * world
 
-    rc = Recalibrator(K, N_RG, READ_LEN, genomelen, COVERAGE, SEED, device=local, comm=comm)
+    rc = Recalibrator(K, N_RG, READ_LEN, genomelen, args.coverage, SEED, device=local, comm=comm)
     stream = torch.cuda.ExternalStream(rc.ctx.stream, device=f"cuda:{local}")
 
     def barrier():
@@ -317,7 +322,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64/u8 integer (long double model fit on host)", "data": "synthetic",
-            "config": {"workload": workload_name(world), "reads_per_gpu": rs.n, "bases_per_gpu": rs.total_bases,
+            "config": {"workload": workload_name(world, args.genome, args.coverage), "reads_per_gpu": rs.n, "bases_per_gpu": rs.total_bases,
                        "l2": "packed inputs per GPU (%d MB) exceed the 126 MB L2; both filters are rebuilt from zero every step"
                              % (pb.h2d_bytes // 1_000_000),
                        "sampled_inserts": sampled_ins, "trusted_inserts": trusted_ins},

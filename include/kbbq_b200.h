@@ -135,6 +135,17 @@ void* kbbq_bloom_device_counter(kbbq_ctx* ctx, int which);
 /* words |= other (other: device pointer to an equally sized bit array, e.g. a peer GPU's mapped filter) */
 int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other_device_words, uint64_t first_word, uint64_t n_words);
 
+/* The whole multi-GPU merge of a filter's bit array in one kernel over peer-mapped memory (one process per GPU, all
+ * on one NVLink/NVSwitch box): rank r ORs slice r of every rank's array and writes the result into every rank's array.
+ *   1. every rank:  kbbq_bloom_ipc_handle -> 64 bytes; all-gather them (any transport) into handles[world][64]
+ *   2. every rank:  kbbq_sync, then a barrier              (all inserts of the pass are in memory everywhere)
+ *   3. every rank:  kbbq_bloom_or_allreduce_p2p, kbbq_sync, then a barrier      (all slices written everywhere)
+ * The insert counters are summed separately (kbbq_bloom_device_counter).  world <= 16.  The reference has no
+ * counterpart: it is single-process. */
+#define KBBQ_IPC_HANDLE_BYTES 64
+int kbbq_bloom_ipc_handle(kbbq_ctx* ctx, int which, void* handle64);
+int kbbq_bloom_or_allreduce_p2p(kbbq_ctx* ctx, int which, int rank, int world, const void* handles);
+
 /* ---- batches -------------------------------------------------------------------------------------------------------- */
 int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
 /* Same, but the quality array (3/4 of the bytes) is copied on a side stream and may still be in flight on return:

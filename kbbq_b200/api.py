@@ -92,6 +92,8 @@ def lib():
         L.kbbq_bloom_device_counter.restype = vp
         L.kbbq_bloom_device_counter.argtypes = [vp, i32]
         L.kbbq_bloom_or_from.argtypes = [vp, i32, vp, u64, u64]
+        L.kbbq_bloom_ipc_handle.argtypes = [vp, i32, vp]
+        L.kbbq_bloom_or_allreduce_p2p.argtypes = [vp, i32, i32, i32, vp]
         L.kbbq_batch_upload.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
         L.kbbq_batch_upload_async.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
         L.kbbq_batch_free.argtypes = [vp, vp]
@@ -352,6 +354,17 @@ class Context:
 
     def bloom_or_from(self, which: int, other_ptr: int, first_word: int, n_words: int):
         _check(self.L.kbbq_bloom_or_from(self.h, which, C.c_void_p(other_ptr), first_word, n_words))
+
+    def bloom_ipc_handle(self, which: int) -> np.ndarray:
+        h = np.zeros(64, dtype=np.uint8)
+        _check(self.L.kbbq_bloom_ipc_handle(self.h, which, _p(h)))
+        return h
+
+    def bloom_or_allreduce_p2p(self, which: int, rank: int, world: int, handles: np.ndarray):
+        """handles: uint8[world, 64], every rank's kbbq_bloom_ipc_handle.  Barriers before and after are the caller's."""
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        assert handles.shape == (world, 64)
+        _check(self.L.kbbq_bloom_or_allreduce_p2p(self.h, which, rank, world, _p(handles)))
 
     # batches
     def upload(self, pb: PackedBatch) -> "DeviceBatch":

@@ -43,6 +43,16 @@ struct Filter {
     unsigned long long* d_words = nullptr;
     unsigned long long* d_patterns = nullptr;
     unsigned long long* d_inserted = nullptr;
+    // peer mappings of the other ranks' bit arrays (kbbq_bloom_or_allreduce_p2p), opened once per filter
+    void* peer[KBBQ_MAX_PEERS] = {};
+    int peer_world = 0, peer_rank = -1;
+    void close_peers() {
+        for (int r = 0; r < peer_world; ++r)
+            if (r != peer_rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
+        std::memset(peer, 0, sizeof peer);
+        peer_world = 0;
+        peer_rank = -1;
+    }
     BloomView view() const {
         BloomView v;
         v.words = d_words;
@@ -437,6 +447,7 @@ void kbbq_ctx_destroy(kbbq_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& f : c->filt) {
+        f.close_peers();
         cudaFree(f.d_words);
         cudaFree(f.d_patterns);
         cudaFree(f.d_inserted);
@@ -500,6 +511,7 @@ int kbbq_bloom_create(kbbq_ctx* ctx, int which, uint64_t projected, double fpr, 
     Filter& f = ctx->filt[which];
     if (f.exists) {
         CU(cudaStreamSynchronize(ctx->stream));
+        f.close_peers();
         cudaFree(f.d_words);
         cudaFree(f.d_patterns);
         cudaFree(f.d_inserted);
@@ -624,6 +636,63 @@ int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other, uint64_t fir
     or_words_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<ulonglong2*>(f.d_words + first_word),
                                                    reinterpret_cast<const ulonglong2*>((const unsigned long long*)other + first_word), n2);
     return check_launch(ctx, "or_words_kernel");
+}
+
+int kbbq_bloom_ipc_handle(kbbq_ctx* ctx, int which, void* handle64) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    if (!handle64) return fail(KBBQ_EINVAL, "null handle buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == KBBQ_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->filt[which].d_words));
+    std::memcpy(handle64, &h, sizeof h);
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_or_allreduce_p2p(kbbq_ctx* ctx, int which, int rank, int world, const void* handles) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    if (world < 1 || world > KBBQ_MAX_PEERS || rank < 0 || rank >= world) return fail(KBBQ_EINVAL, "bad rank/world (at most 16 peers)");
+    if (world == 1) return KBBQ_OK;
+    if (!handles) return fail(KBBQ_EINVAL, "null handles");
+    Filter& f = ctx->filt[which];
+    if (f.peer_world != world || f.peer_rank != rank) {
+        f.close_peers();
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) {
+                f.peer[r] = f.d_words;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const char*)handles + (size_t)r * sizeof h, sizeof h);
+            cudaError_t e = cudaIpcOpenMemHandle(&f.peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                f.peer_world = r;  // close what was opened so far
+                f.peer_rank = rank;
+                f.close_peers();
+                return fail(KBBQ_ECUDA, std::string("cudaIpcOpenMemHandle (peer ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+            }
+        }
+        f.peer_world = world;
+        f.peer_rank = rank;
+    }
+    PeerPtrs pp;
+    std::memset(&pp, 0, sizeof pp);
+    for (int s2 = 0; s2 < world; ++s2) pp.p[s2] = reinterpret_cast<ulonglong2*>(f.peer[(rank + s2) % world]);
+    const unsigned long long n2 = f.geom.table_bits / 128;  // table_bits is a multiple of 512
+    const unsigned long long per = (n2 + world - 1) / world;
+    const int grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((per + 255) / 256, (unsigned long long)ctx->sm_count * 8));
+    pass_begin(ctx);
+    mark_kernel(ctx, "or_allreduce_p2p_kernel");
+    switch (world) {
+    case 2: or_allreduce_p2p_kernel<2><<<grid, 256, 0, ctx->stream>>>(pp, rank, world, n2); break;
+    case 4: or_allreduce_p2p_kernel<4><<<grid, 256, 0, ctx->stream>>>(pp, rank, world, n2); break;
+    case 8: or_allreduce_p2p_kernel<8><<<grid, 256, 0, ctx->stream>>>(pp, rank, world, n2); break;
+    default: or_allreduce_p2p_kernel<0><<<grid, 256, 0, ctx->stream>>>(pp, rank, world, n2); break;
+    }
+    if (int rc = check_launch(ctx, "or_allreduce_p2p_kernel")) return rc;
+    pass_end(ctx);
+    return KBBQ_OK;
 }
 
 // ---- batches -------------------------------------------------------------------------------------------------------

@@ -693,4 +693,39 @@ __global__ void or_words_kernel(ulonglong2* __restrict__ dst, const ulonglong2* 
     }
 }
 
+// ---- the whole multi-GPU filter merge in one kernel over peer-mapped memory (NVLink / NVSwitch) -----------------------
+// Bitwise OR has no NCCL reduction.  Every rank owns one slice of the bit array: it reads that slice from every
+// peer's filter (128-bit loads through the switch), ORs them with its own and writes the result back into EVERY
+// rank's filter -- reduce-scatter and all-gather fused, 2(N-1)/N of the array per GPU on the wire, no staging
+// buffer.  Slices are disjoint, so the only synchronisation is a barrier before (all inserts done) and after.
+#define KBBQ_MAX_PEERS 16
+struct PeerPtrs {
+    ulonglong2* p[KBBQ_MAX_PEERS];  // rotated: p[0] = this rank's filter words, p[s] = rank (rank+s) % world's
+};
+template <int WORLD>  // 0 = any world size (pointer array indexed at run time)
+__global__ void __launch_bounds__(256) or_allreduce_p2p_kernel(PeerPtrs pp, int rank, int world_rt, unsigned long long n2) {
+    const int world = WORLD ? WORLD : world_rt;
+    const unsigned long long per = (n2 + world - 1) / world;
+    const unsigned long long lo = per * rank, hi = lo + per < n2 ? lo + per : n2;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+        ulonglong2 v = __ldcg(pp.p[0] + i);
+        if (WORLD) {
+            ulonglong2 x[WORLD ? WORLD : 1];
+#pragma unroll
+            for (int s = 1; s < WORLD; ++s) x[s] = __ldcg(pp.p[s] + i);  // all peer loads in flight together
+#pragma unroll
+            for (int s = 1; s < WORLD; ++s) { v.x |= x[s].x; v.y |= x[s].y; }
+#pragma unroll
+            for (int s = 0; s < WORLD; ++s) __stcg(pp.p[s] + i, v);
+        } else {
+            for (int s = 1; s < world; ++s) {
+                const ulonglong2 y = __ldcg(pp.p[s] + i);
+                v.x |= y.x; v.y |= y.y;
+            }
+            for (int s = 0; s < world; ++s) __stcg(pp.p[s] + i, v);
+        }
+    }
+}
+
 }  // namespace kbbq

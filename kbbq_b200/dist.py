@@ -3,8 +3,11 @@
 One process per GPU; `torch.distributed` is the plumbing.  The path has exactly three exchange steps:
   after pass 1 and pass 2 -- bitwise OR of the Bloom bit arrays and SUM of the insert counters,
   after pass 3          -- SUM of the covariate count tables.
-NCCL has no bitwise-OR reduction, so the OR is done by this repo's own kernel (`kbbq_bloom_or_from`,
-or_words_kernel) over the gathered partial arrays; the sums are plain all-reduces on int64 views.
+NCCL has no bitwise-OR reduction, so the OR is this repo's own: on one NVLink/NVSwitch box, ONE kernel per rank over
+peer-mapped memory (`kbbq_bloom_or_allreduce_p2p`: rank r ORs slice r of every rank's bit array and writes the result
+into every rank's array -- reduce-scatter and all-gather fused, no staging, 2(N-1)/N of the array per GPU on the
+wire); where peer mapping is not available (KBBQ_MERGE=allgather, or the mapping fails) the fallback all-gathers
+slices with NCCL and ORs them locally (`kbbq_bloom_or_from`).  The sums are plain all-reduces on int64 views.
 
 `Comm` only needs a tensor view of the state to merge, so the same code runs over NCCL on device memory (product)
 and over gloo on host memory (the world_size-2 CPU tests, where the oracle port plays the compute engine).
@@ -73,14 +76,45 @@ class Comm:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     # ---- the three exchange steps on a GPU context --------------------------------------------------------------------
+    def _p2p_handles(self, ctx: api.Context, which: int):
+        """every rank's IPC handle of the filter's bit array, or None when this run merges by all-gather"""
+        import os
+
+        if os.environ.get("KBBQ_MERGE", "p2p") != "p2p" or not isinstance(self, GpuComm):
+            return None
+        key = (id(ctx), which, ctx.bloom_device_words(which))
+        cache = self.__dict__.setdefault("_handles", {})
+        if key not in cache:
+            mine = torch.from_numpy(ctx.bloom_ipc_handle(which)).to(f"cuda:{ctx.device}")
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=mine.device)
+            dist.all_gather_into_tensor(allh, mine)
+            cache[key] = allh.cpu().numpy().reshape(self.world, 64)
+        return cache[key]
+
     def merge_filter(self, ctx: api.Context, which: int) -> None:
         if self.world == 1:
             return
         g = ctx.bloom_info(which)
         nbytes = g.table_bits // 8
+        counter = device_tensor(ctx.bloom_device_counter(which), 8, ctx.device).view(torch.int64)
+        handles = self._p2p_handles(ctx, which)
+        if handles is not None and not self.__dict__.get("_p2p_broken"):
+            ctx.sync()          # this rank's inserts are in memory ...
+            self.barrier()      # ... and so are everybody else's
+            try:
+                ctx.bloom_or_allreduce_p2p(which, self.rank, self.world, handles)
+                ok = 1
+            except api.KbbqError as e:  # no peer access between these devices: every rank must agree to fall back
+                print(f"[rank {self.rank}] peer-memory merge unavailable ({e}); using the all-gather merge", flush=True)
+                ok = 0
+            ctx.sync()
+            if self.min_int(ok) == 1:   # doubles as the barrier after: every slice is written everywhere
+                self.sum_reduce_(counter)
+                torch.cuda.current_stream().synchronize()
+                return
+            self._p2p_broken = True
         ctx.sync()  # the library works on its own stream
         words = device_tensor(ctx.bloom_device_words(which), nbytes, ctx.device).view(torch.int64)
-        counter = device_tensor(ctx.bloom_device_counter(which), 8, ctx.device).view(torch.int64)
 
         def or_kernel(first, n, src):
             # src holds words [first, first+n) of a peer; kbbq_bloom_or_from indexes both sides by absolute word
@@ -120,6 +154,12 @@ class GpuComm(Comm):
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def min_int(self, v: int) -> int:
+        t = torch.tensor([v], dtype=torch.int64, device=f"cuda:{self.device}")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
 
     def sum_int(self, v: int) -> int:
         t = torch.tensor([v], dtype=torch.int64, device=f"cuda:{self.device}")

@@ -72,6 +72,7 @@ def make_reads(
     min_len: int | None = None,
     n_reads: int | None = None,
     chunk: int = 1 << 18,
+    keep_clean: bool = True,
 ) -> ReadSet:
     """Appendix-C generator.  ``ragged`` draws lengths uniformly in [min_len, read_len]."""
     rng = np.random.default_rng(seed)
@@ -86,7 +87,7 @@ def make_reads(
     np.cumsum(lens, out=off[1:])
     total = int(off[-1])
     seq = np.empty(total, dtype=np.uint8)
-    clean = np.empty(total, dtype=np.uint8)
+    clean = np.empty(total if keep_clean else 0, dtype=np.uint8)
     qual = np.empty(total, dtype=np.uint8)
     ar = np.arange(read_len, dtype=np.int64)
     for c0 in range(0, n, chunk):
@@ -109,16 +110,18 @@ def make_reads(
         if ragged:
             keep = ar[None, :] < lens[c0:c1, None].astype(np.int64)
             seq[int(off[c0]) : int(off[c1])] = chars[keep]
-            clean[int(off[c0]) : int(off[c1])] = cchars[keep]
+            if keep_clean:
+                clean[int(off[c0]) : int(off[c1])] = cchars[keep]
             qual[int(off[c0]) : int(off[c1])] = q[keep]
         else:
             seq[int(off[c0]) : int(off[c1])] = chars.reshape(-1)
-            clean[int(off[c0]) : int(off[c1])] = cchars.reshape(-1)
+            if keep_clean:
+                clean[int(off[c0]) : int(off[c1])] = cchars.reshape(-1)
             qual[int(off[c0]) : int(off[c1])] = q.reshape(-1)
     idx = np.arange(n)
     second = (idx & 1).astype(np.uint8)
     rg = ((idx // 2) % n_rg).astype(np.int32) if n_rg > 1 else np.zeros(n, dtype=np.int32)
-    return ReadSet(seq=seq, off=off, qual=qual, rg=rg, second=second, n_rg=n_rg, clean_seq=clean)
+    return ReadSet(seq=seq, off=off, qual=qual, rg=rg, second=second, n_rg=n_rg, clean_seq=clean if keep_clean else None)
 
 
 def to_fastq(rs: ReadSet, path: str) -> None:
