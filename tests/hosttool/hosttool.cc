@@ -1,4 +1,5 @@
 // tests/hosttool/hosttool.cc -- TEST TOOL: drives the host mirror's file classes (kbbq_b200/host) without a GPU.
+//   hosttool load FILE                     parse only (timing)
 //   hosttool dump FILE [use_oq]            one line per record: name \t seq \t qual+33 \t rg-id \t second
 //   hosttool rewrite FILE QUALS OUT [set_oq] [use_oq]
 //        QUALS holds one line of new qualities (+33, read orientation) per record; every record is passed through
@@ -22,7 +23,9 @@ int main(int argc, char** argv) {
         std::unique_ptr<htsiter::StoreFile> f;
         if (htsiter::is_bam_file(fn)) f.reset(new htsiter::BamFile(fn, 1, use_oq, set_oq));
         else f.reset(new htsiter::FastqFile(fn, 1));
-        if (mode == "dump") {
+        if (mode == "load") {  // parse only: prints the number of records and bases
+            std::cout << f->store().n() << '\t' << f->store().off.back() << '\n';
+        } else if (mode == "dump") {
             while (f->next() >= 0) {
                 readutils::CReadData r = f->get();
                 std::string q;
