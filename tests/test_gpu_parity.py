@@ -142,3 +142,92 @@ def test_full_size_properties():
     assert np.array_equal(a["newqual"][low], rs.qual[low])
     nbits = int(np.unpackbits(a["sampled_words"].view(np.uint8)).sum())
     assert 0 < nbits <= 7 * a["sampled_inserted"]
+
+
+def _respray(rs, n_rg, qmax, seed):
+    """Replace the binned qualities / few read groups of a synthetic set by many distinct ones."""
+    rng = np.random.default_rng(seed)
+    rs.qual[:] = rng.integers(0, qmax + 1, rs.qual.shape[0], dtype=np.uint8)
+    rs.rg[:] = rng.integers(0, n_rg, rs.n).astype(rs.rg.dtype)
+    rs.n_rg = n_rg
+    return rs
+
+
+def test_covariate_rows_beyond_the_private_table():
+    """covariate_count_kernel keeps ~40 (read group, quality) rows per block in shared memory and privatises 64 read
+    groups; 70 read groups x 94 qualities = 6580 rows force the global-atomic fall-through of every table."""
+    rs = _respray(synth.make_reads(40000, 20, 100, seed=9, n_frac=0.003), 70, 93, 1)
+    errors = (rs.seq != rs.clean_seq).astype(np.uint8)
+    want = P.PortPipeline(rs, 32).consume(errors)
+    ctx = api.Context(32, rs.n_rg, rs.max_len)
+    pb = api.PackedBatch(rs)
+    db = ctx.upload(pb)
+    ctx.consume_errors(db, pb.pack_bits(errors))
+    for a, b, name in zip(ctx.covariates(), want, ("rgc", "qc", "cyc", "dic")):
+        assert np.array_equal(a, b), name
+    dq = ctx.fit_model()
+    dq_want = P.PortPipeline(rs, 32).get_dqs(want)
+    for a, b in zip(dq, dq_want):
+        assert np.array_equal(a, b)
+    assert np.array_equal(pb.unpack_qual(ctx.pass4(db), rs.total_bases), P.PortPipeline(rs, 32).recalibrate(dq_want))
+    db.free()
+    ctx.close()
+
+
+def test_pipeline_with_many_distinct_qualities():
+    """Un-binned qualities 0..45 in 3 read groups (138 rows): whole pipeline vs the port, tie-breaks on quality included."""
+    G, cov, L, k = 60000, 25, 150, 32
+    rs = _respray(synth.make_reads(G, cov, L, seed=17, err_scale=3.0, n_frac=0.002), 3, 45, 2)
+    common.compare(common.run_gpu(rs, k, G, cov, 31337), common.run_port(rs, k, G, cov, 31337))
+
+
+def test_maximum_read_length_and_one_base_more():
+    """512-base reads (KBBQ_ABI_MAX_READ_LEN: 16 words, two rounds of the 256-base groups) go through every pass;
+    513 bases are refused with KBBQ_ERANGE."""
+    G, cov, L, k = 50000, 30, 512, 32
+    rs = synth.make_reads(G, cov, L, seed=23, err_scale=2.0, ragged=True, min_len=400, n_rg=2)
+    common.compare(common.run_gpu(rs, k, G, cov, 7), common.run_port(rs, k, G, cov, 7))
+    long_rs = synth.make_reads(2000, 10, 513, seed=1)
+    with pytest.raises(api.KbbqError) as e:
+        api.PackedBatch(long_rs)
+    assert e.value.code == -5  # KBBQ_ERANGE
+
+
+def test_empty_batch_and_reads_shorter_than_k():
+    """An empty batch is a no-op for every pass; reads shorter than k consume no draw (htsiter.cc:100-105), are
+    skipped by passes 2-3 (the reference underflows there, bloom.cc:30) and still counted and recalibrated."""
+    G, cov, L, k = 30000, 20, 100, 32
+    rs = synth.make_reads(G, cov, L, seed=3, ragged=True, min_len=10)
+    assert (np.diff(rs.off) < k).any()
+    whole = common.run_gpu(rs, k, G, cov, 11, n_batches=1)
+    split = common.run_gpu(rs, k, G, cov, 11, n_batches=4)
+    common.compare(split, whole)
+    lens = np.diff(rs.off).astype(np.int64)
+    assert whole["slots"] == int(np.maximum(lens - k + 1, 0).sum())
+    short = np.repeat(lens < k, lens)
+    assert not whole["pass2_errors"][short].any() and not whole["pass3_errors"][short].any()
+    assert int(whole["rgc"][:, 1].sum()) == rs.total_bases
+    # the port on the reads the reference can process (len >= k) gives the same filters
+    keep = np.flatnonzero(lens >= k)
+    sub = synth.ReadSet(seq=np.concatenate([rs.seq[rs.off[i]:rs.off[i + 1]] for i in keep]),
+                        off=np.concatenate([[0], np.cumsum(lens[keep])]).astype(np.uint64),
+                        qual=np.concatenate([rs.qual[rs.off[i]:rs.off[i + 1]] for i in keep]),
+                        rg=rs.rg[keep], second=rs.second[keep], n_rg=rs.n_rg)
+    # (dropping short reads does not move the others' draws: they own no slot)
+    want = common.run_port(sub, k, G, cov, 11)
+    assert np.array_equal(whole["sampled_words"], want["sampled_words"]) and np.array_equal(whole["trusted_words"], want["trusted_words"])
+    # empty batch
+    ctx = api.Context(k, 1, L)
+    ctx.bloom_create(0, 1000, 0.01)
+    ctx.bloom_create(1, 1000, 0.0005)
+    db = ctx.upload(api.PackedBatch(rs.subset(0, 0)))
+    ctx.sampler_seed(1, 0.5)
+    ctx.pass1(db)
+    ctx.set_thresholds(np.zeros(k + 1, dtype=np.int32))
+    ctx.pass2(db)
+    ctx.pass3(db)
+    ctx.fit_model()
+    ctx.pass4(db)
+    assert ctx.bloom_inserted(0) == 0 and ctx.bloom_inserted(1) == 0 and int(ctx.covariates()[0].sum()) == 0
+    db.free()
+    ctx.close()
