@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -202,11 +203,13 @@ int check_launch(kbbq_ctx* ctx, const char* what) {
 // covariate_count_kernel: rows of the block-private table that fit beside a second resident block, and the launch(es)
 int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, const uint32_t* d_mod) {
     const int row_cells = KBBQ_HIST_FIXED + 4 * ctx->max_cycle;
-    const long long budget_words = (100 * 1024) / 4 - 2 * KBBQ_HIST_RG;  // 2 blocks/SM inside the 227 KB of an SM
+    const long long fixed_words = KBBQ_HIST_DIRECT_RG * KBBQ_NQ + 2 + 2 * KBBQ_HIST_RG;
+    const long long budget_words = (108 * 1024) / 4 - fixed_words;  // 2 blocks/SM inside the 227 KB of an SM
     int S = (int)std::max(0ll, std::min(64ll, budget_words / (row_cells + 1)));
-    const size_t smem = ((size_t)S + 2 * KBBQ_HIST_RG + (size_t)S * row_cells) * 4;
+    if (const char* e = getenv("KBBQ_HIST_S")) S = std::min(S, atoi(e));  // measurement override
+    const size_t smem = ((size_t)fixed_words + (size_t)S + (size_t)S * row_cells) * 4;
     if (!ctx->count_attr_set) {
-        CU(cudaFuncSetAttribute(covariate_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
+        CU(cudaFuncSetAttribute(covariate_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         ctx->count_attr_set = true;
     }
     const int warps_per_block = KBBQ_HIST_THREADS / 32;

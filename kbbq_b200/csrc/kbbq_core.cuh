@@ -127,10 +127,11 @@ KBBQ_HD void seq_set(const SeqRef& s, int i, int c) {
 
 // Canonical key of the k-mer starting at j, with base p (if inside the k-mer) replaced by code c (c < 0: none).
 // Returns false when the k-mer holds a non-ACGT base, i.e. Kmer::valid() would be false (bloom.hh:368).
-template <class S>
+// NM_OPTIONAL: s.nm may be nullptr, meaning the caller knows the sequence holds no N (pass 3 skips the masks then).
+template <bool NM_OPTIONAL = false, class S>
 KBBQ_HD bool kmer_key(const S& s, int j, int k, int p, int c, uint64_t& key) {
     uint64_t v = extract_le(s.w, j, k);
-    uint32_t n = extract_n(s.nm, j, k);
+    uint32_t n = (!NM_OPTIONAL || s.nm) ? extract_n(s.nm, j, k) : 0u;
     if (c >= 0 && p >= j && p < j + k) {
         const int o = p - j;
         v = (v & ~(3ull << (2 * o))) | ((uint64_t)c << (2 * o));
@@ -193,6 +194,12 @@ KBBQ_HD int prev_zero(const uint32_t* m, int from) {
         from = (from & ~31) - 1;
     }
     return -1;
+}
+// number of set bits in [lo, hi) for windows of at most 32 bits (every k-mer window is); reads m[(lo >> 5) + 1]
+KBBQ_HD int count_window32(const uint32_t* m, int lo, int hi) {
+    const uint64_t v = (((uint64_t)m[(lo >> 5) + 1] << 32) | m[lo >> 5]) >> (lo & 31);
+    const uint32_t x = (uint32_t)v & (hi - lo >= 32 ? ~0u : ((1u << (hi - lo)) - 1u));
+    return popc32(x);
 }
 // number of set bits in [lo, hi)
 KBBQ_HD int count_range(const uint32_t* m, int lo, int hi) {

@@ -71,7 +71,9 @@ struct ErrCaller {
     ErrScratch& sc;
     const uint32_t* T = nullptr;  // cached trusted flags of the running call's sequence (see cached_run)
     bool T_mirrored = false;
-    KBBQ_HD ErrCaller(Q q_, int k_, const uint8_t* qual_, ErrScratch& sc_) : q(q_), k(k_), qual(qual_), sc(sc_) {}
+    const bool has_n;  // false: the read holds no non-ACGT base (nor does anything derived from it): key building skips the N masks
+    KBBQ_HD ErrCaller(Q q_, int k_, const uint8_t* qual_, ErrScratch& sc_, bool has_n_ = true)
+        : q(q_), k(k_), qual(qual_), sc(sc_), has_n(has_n_) {}
 
     // THE probe routine.  Lane t asks about the k-mer of s starting at j0 + t*stride with base p replaced:
     //   stride == 1: consecutive k-mers, replacement base c (c < 0: no replacement);
@@ -82,11 +84,11 @@ struct ErrCaller {
                                                   int count, int p, int c, uint32_t cpack) {
         const SeqRef s{w, nm, 0};
         return q.query(count, [&](int t, uint64_t& key) {
-            return kmer_key(s, j0 + t * stride, kk, p, stride ? c : (int)((cpack >> (2 * t)) & 3u), key);
+            return kmer_key<true>(s, j0 + t * stride, kk, p, stride ? c : (int)((cpack >> (2 * t)) & 3u), key);
         });
     }
     KBBQ_HD uint32_t kmers_mask(const SeqRef& s, int j0, int stride, int count, int p, int c, uint32_t cpack) {
-        return kmers_mask_s(q, s.w, s.nm, k, j0, stride, count, p, c, cpack);
+        return kmers_mask_s(q, s.w, has_n ? s.nm : nullptr, k, j0, stride, count, p, c, cpack);
     }
     // number of consecutive trusted k-mers starting at j0, looking no further than j1 (exclusive)
     KBBQ_HD int trusted_run(const SeqRef& s, int j0, int j1, int p, int c) {
@@ -520,7 +522,7 @@ struct ErrCaller {
                         const int i = 32 * w + t;
                         if (i >= len || !bit_get(sc.E, base + i)) return false;
                         const int lo = i - ocwindow + 1 > 0 ? i - ocwindow + 1 : 0;
-                        const int occ2 = 2 * count_range(F, lo, i + 1) - count_range(FQ, lo, i + 1);
+                        const int occ2 = 2 * count_window32(F, lo, i + 1) - count_window32(FQ, lo, i + 1);
                         const int threshold = adjust && i >= ocwindow && i + ocwindow - 1 < len ? base_threshold + 1 : base_threshold;
                         return occ2 > 2 * threshold;
                     });

@@ -316,7 +316,7 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
             if (i < len) {
                 const int lo = i - k + 1 > 0 ? i - k + 1 : 0;
                 const int hi = (i < nk - 1 ? i : nk - 1) + 1;
-                const int in = count_range(Pm, lo, hi);
+                const int in = count_window32(Pm, lo, hi);
                 e = in <= thr[hi - lo] || q[i] <= 2;
             }
             const uint32_t m = __ballot_sync(KBBQ_FULL, e);
@@ -330,7 +330,7 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
             uint64_t key = 0;
-            const bool ins = j < nk && count_range(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key);
+            const bool ins = j < nk && count_window32(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key);
             inserted += warp_bloom_insert(trusted, ins, key, stage);
         }
         __syncwarp();
@@ -345,27 +345,38 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
 // 20 ms pass).  Here each block keeps an associative set of S rows in shared memory -- one row = everything keyed by
 // (read group, quality): its q pair, 16 dinucleotide pairs and 2 x C cycle pairs -- counts there with 32-bit shared
 // atomics, and flushes the rows it used with 64-bit global atomics when it retires.  A row that finds no free slot
-// falls through to global atomics, so any input stays exact.  The launch bounds the reads per block so that no 32-bit
+// (or belongs to a read group beyond the direct table) falls through to global atomics, so any input stays exact.  The launch bounds the reads per block so that no 32-bit
 // cell can overflow.
 #define KBBQ_HIST_THREADS 512
 #define KBBQ_HIST_RG 64            // read groups whose {errors,total} pair is privatised too
 #define KBBQ_HIST_EMPTY 0xFFFFFFFFu
 #define KBBQ_HIST_FIXED 34         // cells of a row before the cycle cells: q pair, 16 dinuc errors, 16 dinuc totals
 
-__device__ __forceinline__ int hist_slot(uint32_t* tags, int S, uint32_t key) {
-    if (S == 0) return -1;
-    uint32_t h = ((key * 0x9E3779B1u) >> 12) % (uint32_t)S;
-#pragma unroll 1
-    for (int probe = 0; probe < 4; ++probe) {
-        const uint32_t t = *reinterpret_cast<volatile uint32_t*>(tags + h);
-        if (t == key) return (int)h;
-        if (t == KBBQ_HIST_EMPTY) {
-            const uint32_t old = atomicCAS(tags + h, KBBQ_HIST_EMPTY, key);
-            if (old == KBBQ_HIST_EMPTY || old == key) return (int)h;
+// Row -> slot through a direct table (one shared load per lookup): slot_of[key] for the first KBBQ_HIST_DIRECT_RG read
+// groups; a row takes the next free slot the first time any warp of the block meets it, and NOSLOT for good once the
+// S slots are gone.  Two lanes of one warp never race for a key (a leader is unique per quality), so the short spin
+// on CLAIMING only ever waits for another warp.
+#define KBBQ_HIST_DIRECT_RG 16
+#define KBBQ_HIST_UNASSIGNED 0xFFFFFFFFu
+#define KBBQ_HIST_CLAIMING 0xFFFFFFFEu
+#define KBBQ_HIST_NOSLOT 0xFFFFFFFDu
+__device__ __forceinline__ int hist_slot(uint32_t* slot_of, uint32_t* tags, uint32_t* n_used, int S, uint32_t key) {
+    if (key >= KBBQ_HIST_DIRECT_RG * KBBQ_NQ) return -1;
+    volatile uint32_t* cell = slot_of + key;
+    uint32_t v = *cell;
+    if (v == KBBQ_HIST_UNASSIGNED) {
+        if (atomicCAS(slot_of + key, KBBQ_HIST_UNASSIGNED, KBBQ_HIST_CLAIMING) == KBBQ_HIST_UNASSIGNED) {
+            const uint32_t n = atomicAdd(n_used, 1u);
+            v = n < (uint32_t)S ? n : KBBQ_HIST_NOSLOT;
+            if (n < (uint32_t)S) tags[n] = key;
+            __threadfence_block();
+            *cell = v;
+        } else {
+            v = KBBQ_HIST_CLAIMING;
         }
-        h = h + 1 == (uint32_t)S ? 0 : h + 1;
     }
-    return -1;
+    while (v == KBBQ_HIST_CLAIMING) v = *cell;
+    return v < (uint32_t)S ? (int)v : -1;
 }
 
 // err_bits: read.errors as bit masks (kbbq_batch word layout).  mod: per read, 4*index+base of the one base that
@@ -375,11 +386,14 @@ covariate_count_kernel(BatchView b, CountView cv, const uint32_t* __restrict__ e
                        uint32_t first_read, uint32_t end_read, int S) {
     extern __shared__ uint32_t hist_smem[];
     const int C = cv.max_cycle, row_cells = KBBQ_HIST_FIXED + 4 * C;
-    uint32_t* tags = hist_smem;
-    uint32_t* rgh = tags + S;
+    uint32_t* slot_of = hist_smem;                                    // [KBBQ_HIST_DIRECT_RG * 94]
+    uint32_t* tags = slot_of + KBBQ_HIST_DIRECT_RG * KBBQ_NQ;         // [S] key of each slot in use (for the flush)
+    uint32_t* n_used = tags + S;                                      // [1] (+1 pad)
+    uint32_t* rgh = n_used + 2;
     uint32_t* rows = rgh + 2 * KBBQ_HIST_RG;
+    for (int i = threadIdx.x; i < KBBQ_HIST_DIRECT_RG * KBBQ_NQ; i += blockDim.x) slot_of[i] = KBBQ_HIST_UNASSIGNED;
     for (int i = threadIdx.x; i < S; i += blockDim.x) tags[i] = KBBQ_HIST_EMPTY;
-    for (int i = threadIdx.x; i < 2 * KBBQ_HIST_RG + S * row_cells; i += blockDim.x) rgh[i] = 0;
+    for (int i = threadIdx.x; i < 2 + 2 * KBBQ_HIST_RG + S * row_cells; i += blockDim.x) n_used[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -428,7 +442,7 @@ covariate_count_kernel(BatchView b, CountView cv, const uint32_t* __restrict__ e
                 const int leader = __ffs(same_q) - 1;
                 const uint32_t key = rowkey0 + (uint32_t)qi;
                 int slot = -1;
-                if (in && lane == leader) slot = hist_slot(tags, S, key);
+                if (in && lane == leader) slot = hist_slot(slot_of, tags, n_used, S, key);
                 slot = __shfl_sync(KBBQ_FULL, slot, leader);
                 uint32_t* row = rows + (size_t)(slot < 0 ? 0 : slot) * row_cells;
                 if (in && lane == leader) {  // CQCovariate
@@ -577,7 +591,8 @@ pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict_
             if (lane == 0) sc.QL[i0 >> 5] = m;
         }
         __syncwarp();
-        ErrCaller<DevQuery> ec(q, k, qual, sc);
+        const bool has_n = __any_sync(KBBQ_FULL, lane < nw && sc.P_nm[lane] != 0u);
+        ErrCaller<DevQuery> ec(q, k, qual, sc, has_n);
         const ErrResult res = ec.run(len);
         __syncwarp();
         if (lane < nw) err_out[wo + lane] = sc.E[lane];

@@ -111,12 +111,12 @@ void emu_pass2(uint32_t n, const uint64_t* bases, const uint32_t* nmask, const u
         for (int i = 0; i < L; ++i) {
             const int lo = i - k + 1 > 0 ? i - k + 1 : 0;
             const int hi = (i < nk - 1 ? i : nk - 1) + 1;
-            if (count_range(Pm, lo, hi) <= thr[hi - lo] || q[i] <= 2) bit_set(Em, i);
+            if (count_window32(Pm, lo, hi) <= thr[hi - lo] || q[i] <= 2) bit_set(Em, i);
         }
         for (int w = 0; w * 32 < L; ++w) err_bits[wo + w] = Em[w];
         for (int j = 0; j < nk; ++j) {
             uint64_t key;
-            if (count_range(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key)) insert_host(tv, key);
+            if (count_window32(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key)) insert_host(tv, key);
         }
     }
 }
@@ -137,7 +137,9 @@ uint64_t emu_get_errors(uint32_t n, const uint64_t* bases, const uint32_t* nmask
         for (int w = 0; w < nw; ++w) { sc.P_w[w] = bases[wo + w]; sc.P_nm[w] = nmask[wo + w]; }
         for (int i = 0; i < L; ++i)
             if (qual[(size_t)wo * 32 + i] <= 6) bit_set(sc.QL, i);
-        ErrCaller<HostQueryRef> ec(HostQueryRef{&q}, k, qual + (size_t)wo * 32, sc);
+        bool has_n = false;  // as the kernel: key building skips the N masks of reads without N
+        for (int w = 0; w < nw; ++w) has_n = has_n || sc.P_nm[w] != 0;
+        ErrCaller<HostQueryRef> ec(HostQueryRef{&q}, k, qual + (size_t)wo * 32, sc, has_n);
         const ErrResult res = ec.run(L);
         for (int w = 0; w < nw; ++w) err_bits[wo + w] = sc.E[w];
         mod_idx[r] = res.mod_idx;
