@@ -73,6 +73,9 @@ typedef struct kbbq_batch {
 
 const char* kbbq_last_error(void);
 int kbbq_device_count(void);
+/* Initialise the CUDA runtime on `device` (primary context creation, the slow part of a fresh process).  Optional:
+ * kbbq_ctx_create does it implicitly; a host may call this from a side thread while it parses its input. */
+int kbbq_device_warmup(int device);
 
 /* ---- host-only helpers (no GPU needed) ------------------------------------------------------------------------ */
 /* bloom::Bloom ctor geometry; KBBQ_EINVAL where the reference throws (bloom.cc:18-21) */

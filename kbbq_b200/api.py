@@ -56,6 +56,7 @@ def lib():
         vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
         L.kbbq_last_error.restype = C.c_char_p
         L.kbbq_device_count.restype = i32
+        L.kbbq_device_warmup.argtypes = [i32]
         L.kbbq_bloom_geometry.argtypes = [u64, dbl, u64, C.POINTER(BloomGeom)]
         L.kbbq_bloom_patterns.argtypes = [C.POINTER(BloomGeom), vp]
         L.kbbq_effective_fpp.restype = dbl

@@ -273,6 +273,14 @@ int kbbq_device_count(void) {
     return n;
 }
 
+int kbbq_device_warmup(int device) {
+    // creates the device's primary context (hundreds of ms to seconds in a fresh process): callable from a side thread
+    // while the caller parses its input
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess)
+        return fail(KBBQ_ECUDA, std::string("no usable CUDA device ") + std::to_string(device) + " (this library has no CPU path)");
+    return KBBQ_OK;
+}
+
 // ---- host-only helpers ---------------------------------------------------------------------------------------------
 int kbbq_bloom_geometry(uint64_t projected, double fpr, uint64_t seed, kbbq_bloom_geom* out) {
     if (!out) return fail(KBBQ_EINVAL, "null output");

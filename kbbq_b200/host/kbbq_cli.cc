@@ -8,11 +8,14 @@
 #include <getopt.h>
 #include <unistd.h>
 
+#include <chrono>
+#include <cstdlib>
 #include <ctime>
 #include <functional>
 #include <iomanip>
 #include <iostream>
 #include <memory>
+#include <thread>
 
 #include "kbbq_host_api.hh"
 
@@ -25,6 +28,19 @@ static std::ostream& put_now(std::ostream& os) {
     std::tm tm = *std::localtime(&t);
     return os << std::put_time(&tm, "[%F %T %Z]");
 }
+
+// KBBQ_HOST_TIMING=1: wall time of each phase on stderr (the reference only stamps whole seconds)
+struct PhaseTimer {
+    const bool on = getenv("KBBQ_HOST_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), start = t0;
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::cerr << "[cli] " << what << " " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " ms (at "
+                  << std::chrono::duration<double, std::milli>(t1 - start).count() << ")" << std::endl;
+        t0 = t1;
+    }
+};
 
 static struct option long_options[] = {
     {"ksize", required_argument, 0, 'k'},   {"use-oq", no_argument, 0, 'u'},        {"set-oq", no_argument, 0, 's'},
@@ -89,8 +105,12 @@ int main(int argc, char* argv[]) {
             if (is_bam) return std::unique_ptr<htsiter::StoreFile>(new htsiter::BamFile(fn, nthreads, use_oq, set_oq));
             return std::unique_ptr<htsiter::StoreFile>(new htsiter::FastqFile(fn, nthreads));
         };
+        PhaseTimer timer;
+        std::thread warmup([] { kbbq_device_warmup(0); });  // CUDA context creation runs while the input is parsed
+        struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warmup};
         std::unique_ptr<htsiter::StoreFile> file = open_file(filename);
         const kbbq::ReadStore& store = file->store();
+        timer.mark("input read + parsed");
         if (store.n() == 0) {
             std::cerr << put_now << " Error: total sequence length in file " << filename << " is 0. Check that the file isn't empty." << std::endl;
             return 1;
@@ -98,6 +118,7 @@ int main(int argc, char* argv[]) {
         const int n_rg = (int)std::max<size_t>(1, readutils::CReadData::rg_to_int.size());
         kbbq::Session session(k, n_rg, (int)std::max<uint32_t>(1, store.max_len));
         covariateutils::CCovariateData data;
+        timer.mark("GPU context");
 
         if (fixedinput == "") {
             if (genomelen == 0) {
@@ -142,6 +163,7 @@ int main(int argc, char* argv[]) {
 
             htsiter::KmerSubsampler subsampler(file.get(), k, alpha, seed);
             recalibrateutils::subsample_kmers(subsampler, subsampled);
+            timer.mark("pack + upload + pass 1");
             std::cerr << put_now << " Sampled " << subsampled.inserted_elements() << " valid kmers." << std::endl;
 
             long double fpr = subsampled.fprate();
@@ -155,8 +177,10 @@ int main(int argc, char* argv[]) {
 
             std::cerr << put_now << " Finding trusted kmers" << std::endl;
             recalibrateutils::find_trusted_kmers(file.get(), trusted, subsampled, thresholds, k);
+            timer.mark("pass 2 (launched)");
             std::cerr << put_now << " Finding errors" << std::endl;
             data = recalibrateutils::get_covariatedata(file.get(), trusted, k);
+            timer.mark("pass 3 + tables to host");
         } else {
             // --fixed: a base is an error when it differs from the same base of the pre-corrected file (kbbq.cc:367-378)
             std::cerr << put_now << " Using fixed file to find errors." << std::endl;
@@ -183,8 +207,10 @@ int main(int argc, char* argv[]) {
 
         std::cerr << put_now << " Training model" << std::endl;
         covariateutils::dq_t dqs = data.get_dqs();
+        timer.mark("model fit");
         std::cerr << put_now << " Recalibrating file" << std::endl;
         recalibrateutils::recalibrate_and_write(file.get(), dqs, "-");
+        timer.mark("pass 4 + format + compress + write");
     } catch (const std::exception& e) {
         std::cerr << put_now << " Error: " << e.what() << std::endl;
         return 1;

@@ -6,6 +6,10 @@
 #include <algorithm>
 #include <cerrno>
 #include <cmath>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <chrono>
 #include <cstring>
 #include <iostream>
 #include <thread>
@@ -210,82 +214,340 @@ static void parse_name(const std::string& full, std::string& rg, bool& second) {
     second = (tail == "/2");
 }
 
-static std::shared_ptr<kbbq::ReadStore> load_fastq(const std::string& filename) {
+// ---- reading the input ------------------------------------------------------------------------------------------------
+// The whole decompressed input is brought into memory once (the reference re-reads the file for every pass).  BGZF
+// input (bgzip'd FASTQ, every BAM) is a sequence of independent gzip members of <= 64 KiB: the members are located by
+// their BSIZE fields and inflated by a pool of threads.  Plain gzip is one serial zlib stream; plain text is read.
+// KBBQ_HOST_TIMING=1: phase times of the host side on stderr
+struct PhaseTimer {
+    const bool on = getenv("KBBQ_HOST_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::cerr << "[host] " << what << " " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " ms" << std::endl;
+        t0 = t1;
+    }
+};
+static int pool_size(int nthreads) {
+    return (int)std::max(1u, nthreads > 0 ? (unsigned)nthreads : std::min(16u, std::thread::hardware_concurrency()));
+}
+template <class F>
+static void parallel_for(size_t n, int nt, F f) {  // f(begin, end, thread index) over contiguous ranges
+    nt = (int)std::min<size_t>((size_t)std::max(nt, 1), std::max<size_t>(n, 1));
+    if (nt <= 1) { f((size_t)0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back([=] { f(n * t / nt, n * (t + 1) / nt, t); });
+    for (auto& t : th) t.join();
+}
+
+static bool read_file(const std::string& filename, std::vector<uint8_t>& raw) {
+    FILE* f = fopen(filename.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz < 0) { fclose(f); return false; }
+    raw.resize((size_t)sz);
+    const size_t got = sz ? fread(raw.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    return got == (size_t)sz;
+}
+
+struct BgzfBlock { size_t cdata, clen, out_off; uint32_t isize; };
+// member boundaries of a BGZF file, or false when some member is not a BGZF block (then zlib reads it serially)
+static bool bgzf_index(const std::vector<uint8_t>& raw, std::vector<BgzfBlock>& blocks, size_t& total) {
+    size_t o = 0;
+    total = 0;
+    while (o < raw.size()) {
+        if (raw.size() - o < 18 || raw[o] != 0x1f || raw[o + 1] != 0x8b || raw[o + 2] != 8 || !(raw[o + 3] & 4)) return false;
+        const size_t xlen = raw[o + 10] | (raw[o + 11] << 8);
+        size_t bsize = 0;
+        for (size_t x = o + 12; x + 4 <= o + 12 + xlen && x + 4 <= raw.size();) {  // extra subfields: SI1 SI2 SLEN data
+            const size_t slen = raw[x + 2] | (raw[x + 3] << 8);
+            if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2 && x + 6 <= raw.size()) bsize = (size_t)(raw[x + 4] | (raw[x + 5] << 8)) + 1;
+            x += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8 || o + bsize > raw.size() || (raw[o + 3] & ~4)) return false;  // other gzip flags: not BGZF
+        BgzfBlock b;
+        b.cdata = o + 12 + xlen;
+        b.clen = bsize - 12 - xlen - 8;
+        std::memcpy(&b.isize, &raw[o + bsize - 4], 4);
+        b.out_off = total;
+        total += b.isize;
+        blocks.push_back(b);
+        o += bsize;
+    }
+    return !blocks.empty();
+}
+
+static std::vector<uint8_t> read_all_decompressed(const std::string& filename, int nthreads) {
+    std::vector<uint8_t> data;
+    std::vector<uint8_t> raw;
+    if (filename != "-" && read_file(filename, raw)) {
+        if (raw.size() < 2 || raw[0] != 0x1f || raw[1] != 0x8b) return raw;  // not compressed
+        std::vector<BgzfBlock> blocks;
+        size_t total = 0;
+        if (bgzf_index(raw, blocks, total)) {
+            data.resize(total);
+            std::vector<char> bad((size_t)pool_size(nthreads), 0);
+            parallel_for(blocks.size(), pool_size(nthreads), [&](size_t lo, size_t hi, int t) {
+                z_stream zs;
+                for (size_t i = lo; i < hi; ++i) {
+                    const BgzfBlock& b = blocks[i];
+                    if (b.isize == 0) continue;
+                    std::memset(&zs, 0, sizeof zs);
+                    if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
+                    zs.next_in = (Bytef*)&raw[b.cdata];
+                    zs.avail_in = (uInt)b.clen;
+                    zs.next_out = &data[b.out_off];
+                    zs.avail_out = b.isize;
+                    const int rc = inflate(&zs, Z_FINISH);
+                    inflateEnd(&zs);
+                    if (rc != Z_STREAM_END || zs.avail_out != 0) { bad[t] = 1; return; }
+                }
+            });
+            for (char c : bad)
+                if (c) throw std::runtime_error("corrupt BGZF block in " + filename);
+            return data;
+        }
+    }
+    // plain gzip (or stdin): one serial stream through zlib
     gzFile gz = filename == "-" ? gzdopen(0, "rb") : gzopen(filename.c_str(), "rb");
     if (!gz) throw std::runtime_error("Error opening file " + filename);
     gzbuffer(gz, 1 << 22);
-    std::vector<char> text;
-    {
-        std::vector<char> buf(1 << 24);
-        int got;
-        while ((got = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) text.insert(text.end(), buf.begin(), buf.begin() + got);
-        gzclose(gz);
+    std::vector<uint8_t> buf(1 << 24);
+    int got;
+    while ((got = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.insert(data.end(), buf.begin(), buf.begin() + got);
+    gzclose(gz);
+    return data;
+}
+
+// Read groups are numbered in order of first appearance in the file (readutils.cc:99-102).  Parsers working on
+// ranges of the file keep a local table each; merging the tables range by range gives the file's order.
+struct RgTable {
+    std::vector<std::string> names;                 // local id -> name, in order of first appearance in the range
+    std::unordered_map<std::string, uint16_t> ids;
+    uint16_t id(const std::string& rg) {
+        auto it = ids.find(rg);
+        if (it != ids.end()) return it->second;
+        if (names.size() >= 65535) throw std::runtime_error("more than 65535 read groups");
+        const uint16_t v = (uint16_t)names.size();
+        names.push_back(rg);
+        ids.emplace(rg, v);
+        return v;
     }
-    auto rs = std::make_shared<kbbq::ReadStore>();
-    rs->path = filename;
-    rs->name_off.push_back(0);
-    rs->comment_off.push_back(0);
-    rs->off.push_back(0);
+};
+static std::vector<std::vector<uint16_t>> merge_rg_tables(const std::vector<RgTable>& parts) {
     readutils::CReadData::rg_to_int.clear();
     readutils::CReadData::rg_to_pu.clear();
-    const char* p = text.data();
-    const char* end = p + text.size();
+    auto& r2i = readutils::CReadData::rg_to_int;
+    std::vector<std::vector<uint16_t>> remap(parts.size());
+    for (size_t t = 0; t < parts.size(); ++t)
+        for (const std::string& rg : parts[t].names) {
+            if (readutils::CReadData::rg_to_pu.count(rg) == 0) {  // ids in order of first appearance, starting at 0
+                const int id = (int)r2i.size();
+                r2i[rg] = id;
+                readutils::CReadData::rg_to_pu[rg] = rg;
+            }
+            remap[t].push_back((uint16_t)r2i[rg]);
+        }
+    return remap;
+}
+
+struct FastqPart {  // what one thread parsed: same columns as ReadStore, offsets relative to the part
+    std::vector<char> names, comments, seq;
+    std::vector<uint8_t> qual;
+    std::vector<uint64_t> name_end, comment_end, seq_end;
+    std::vector<uint16_t> rg;
+    std::vector<uint8_t> second;
+    RgTable rgs;
+    uint32_t max_len = 0;
+    bool strict = true;  // false: something other than 4-line records was seen; the serial kseq-style parser takes over
+    size_t stopped_at = 0;
+};
+
+// kseq_read semantics (kseq.hh) on [p, end): header '@' or '>', name up to the first blank, rest = comment, sequence
+// lines until a line starting with '+', '@' or '>', then as many quality characters as bases.  `strict4` parses only
+// plain 4-line records and gives up (strict = false) on anything else.
+static void parse_fastq_range(const char* base, size_t begin, size_t end_, bool strict4, const std::string& filename, FastqPart& out) {
+    const char* p = base + begin;
+    const char* end = base + end_;
     auto line_end = [&](const char* s) { const char* e = (const char*)memchr(s, '\n', end - s); return e ? e : end; };
+    {   // a 4-line record is name + 2 x bases + a few separators: reserve once instead of growing by doubling
+        const size_t bytes = end_ - begin;
+        out.seq.reserve(bytes / 2 + 64);
+        out.qual.reserve(bytes / 2 + 64);
+        out.names.reserve(bytes / 8 + 64);
+        const size_t recs = bytes / 64 + 16;
+        out.name_end.reserve(recs); out.comment_end.reserve(recs); out.seq_end.reserve(recs); out.rg.reserve(recs); out.second.reserve(recs);
+    }
     while (p < end) {
-        while (p < end && *p != '@' && *p != '>') ++p;  // kseq: skip to the next header
-        if (p >= end) break;
+        if (strict4) {
+            if (*p != '@') { out.strict = false; return; }
+        } else {
+            while (p < end && *p != '@' && *p != '>') ++p;  // kseq: skip to the next header
+            if (p >= end) break;
+        }
+        const char* rec_start = p;
         const char* le = line_end(p);
         const char* he = le;
         if (he > p && he[-1] == '\r') --he;
         const char* ne = p + 1;
         while (ne < he && *ne != ' ' && *ne != '\t') ++ne;
-        rs->names.insert(rs->names.end(), p + 1, ne);
-        if (ne < he) rs->comments.insert(rs->comments.end(), ne + 1, he);
+        const size_t name0 = out.names.size(), comment0 = out.comments.size(), seq0 = out.seq.size();
+        out.names.insert(out.names.end(), p + 1, ne);
+        if (ne < he) out.comments.insert(out.comments.end(), ne + 1, he);
         p = le < end ? le + 1 : end;
         // sequence lines until a line starting with '+', '@' or '>'
+        int seq_lines = 0;
         while (p < end && *p != '+' && *p != '@' && *p != '>') {
             le = line_end(p);
             const char* se = le;
             if (se > p && se[-1] == '\r') --se;
-            rs->seq.insert(rs->seq.end(), p, se);
+            out.seq.insert(out.seq.end(), p, se);
             p = le < end ? le + 1 : end;
+            ++seq_lines;
         }
-        const size_t slen = rs->seq.size() - rs->off.back();
+        const size_t slen = out.seq.size() - seq0;
         size_t qlen = 0;
+        int qual_lines = 0;
         if (p < end && *p == '+') {
             le = line_end(p);
             p = le < end ? le + 1 : end;
+            const size_t q0 = out.qual.size();
+            out.qual.resize(q0 + slen);
             while (p < end && qlen < slen) {
                 le = line_end(p);
                 const char* qe = le;
                 if (qe > p && qe[-1] == '\r') --qe;
-                for (const char* c = p; c < qe; ++c) rs->qual.push_back((uint8_t)(*c - 33));
-                qlen += qe - p;
+                const size_t take = std::min<size_t>((size_t)(qe - p), slen - qlen);
+                for (size_t c = 0; c < take; ++c) out.qual[q0 + qlen + c] = (uint8_t)(p[c] - 33);
+                if ((size_t)(qe - p) > take) qlen = slen + 1;  // longer than the sequence: kseq_read == -2
+                else qlen += take;
                 p = le < end ? le + 1 : end;
+                ++qual_lines;
             }
         }
+        if (strict4 && (seq_lines != 1 || qual_lines != 1 || slen == 0 || qlen != slen)) {
+            out.names.resize(name0); out.comments.resize(comment0); out.seq.resize(seq0); out.qual.resize(seq0);
+            out.strict = false;
+            out.stopped_at = (size_t)(rec_start - base);
+            return;
+        }
         if (qlen != slen) throw std::runtime_error("truncated quality string in " + filename);  // kseq_read == -2
-        rs->name_off.push_back(rs->names.size());
-        rs->comment_off.push_back(rs->comments.size());
-        rs->off.push_back(rs->seq.size());
-        rs->max_len = std::max<uint32_t>(rs->max_len, (uint32_t)slen);
-        std::string name(rs->names.data() + rs->name_off[rs->name_off.size() - 2], rs->names.data() + rs->names.size());
+        out.name_end.push_back(out.names.size());
+        out.comment_end.push_back(out.comments.size());
+        out.seq_end.push_back(out.seq.size());
+        out.max_len = std::max<uint32_t>(out.max_len, (uint32_t)slen);
+        std::string name(out.names.data() + name0, out.names.data() + out.names.size());
         std::string rg;
         bool second;
         parse_name(name, rg, second);
-        auto& r2i = readutils::CReadData::rg_to_int;
-        if (readutils::CReadData::rg_to_pu.count(rg) == 0) {  // ids in order of first appearance, starting at 0
-            const int id = (int)r2i.size();
-            r2i[rg] = id;
-            readutils::CReadData::rg_to_pu[rg] = rg;
-        }
-        rs->rg.push_back((uint16_t)r2i[rg]);
-        rs->second.push_back(second ? 1 : 0);
+        out.rg.push_back(out.rgs.id(rg));
+        out.second.push_back(second ? 1 : 0);
     }
+    out.stopped_at = end_;
+}
+
+// start of the first 4-line record at or after `from`: a line starting with '@' whose third line starts with '+' and
+// whose second and fourth lines have equal lengths (a quality line may start with '@', a sequence line never with '+')
+static size_t next_record_start(const char* base, size_t size, size_t from) {
+    const char* end = base + size;
+    const char* p = base + from;
+    if (from > 0) {  // move to a line start
+        const char* nl = (const char*)memchr(p - 1, '\n', end - (p - 1));
+        if (!nl) return size;
+        p = nl + 1;
+    }
+    auto line_end = [&](const char* s) { const char* e = (const char*)memchr(s, '\n', end - s); return e ? e : end; };
+    for (int tries = 0; p < end && tries < 8; ++tries) {
+        if (*p == '@') {
+            const char* l1 = line_end(p);
+            const char* s0 = l1 < end ? l1 + 1 : end;
+            const char* l2 = line_end(s0);
+            const char* pl = l2 < end ? l2 + 1 : end;
+            if (pl < end && *pl == '+' && s0 < end && *s0 != '@' && *s0 != '+' && *s0 != '>') {
+                const char* l3 = line_end(pl);
+                const char* q0 = l3 < end ? l3 + 1 : end;
+                const char* l4 = line_end(q0);
+                if ((l2 - s0) == (l4 - q0) && l2 > s0) return (size_t)(p - base);
+            }
+        }
+        const char* le = line_end(p);
+        p = le < end ? le + 1 : end;
+    }
+    return size;  // no plausible record start near: the caller falls back to the serial parser
+}
+
+static std::shared_ptr<kbbq::ReadStore> load_fastq(const std::string& filename, int nthreads) {
+    PhaseTimer pt_;
+    const std::vector<uint8_t> text = read_all_decompressed(filename, nthreads);
+    pt_.mark("fastq: read + decompress");
+    const char* base = (const char*)text.data();
+    const size_t size = text.size();
+    const int nt = (int)std::min<size_t>((size_t)pool_size(nthreads), std::max<size_t>(1, size >> 20));  // >= 1 MiB per thread
+    std::vector<FastqPart> parts;
+    bool ok = nt > 1;
+    if (ok) {
+        std::vector<size_t> cut(nt + 1, size);
+        cut[0] = 0;
+        for (int t = 1; t < nt && ok; ++t) {
+            cut[t] = next_record_start(base, size, size * t / nt);
+            if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+        }
+        parts.resize(nt);
+        if (pt_.on) { std::cerr << "[host] fastq cuts:"; for (size_t c : cut) std::cerr << " " << c; std::cerr << std::endl; }
+        parallel_for((size_t)nt, nt, [&](size_t lo, size_t hi, int) {
+            for (size_t t = lo; t < hi; ++t) parse_fastq_range(base, cut[t], cut[t + 1], true, filename, parts[t]);
+        });
+        for (const FastqPart& pt : parts) ok = ok && pt.strict;
+        if (!(size && base[0] == '@')) ok = false;
+    }
+    if (!ok) {  // multi-line records, FASTA-style headers, junk between records ...: one thread, kseq semantics
+        parts.assign(1, FastqPart());
+        parse_fastq_range(base, 0, size, false, filename, parts[0]);
+    }
+    pt_.mark(ok ? "fastq: parse (parallel, 4-line records)" : "fastq: parse (serial, kseq semantics)");
+    // stitch the parts together
+    auto rs = std::make_shared<kbbq::ReadStore>();
+    rs->path = filename;
+    std::vector<RgTable> tables;
+    for (FastqPart& pt : parts) tables.push_back(std::move(pt.rgs));
+    const std::vector<std::vector<uint16_t>> remap = merge_rg_tables(tables);
+    std::vector<size_t> r0(parts.size() + 1, 0), n0(parts.size() + 1, 0), c0(parts.size() + 1, 0), s0(parts.size() + 1, 0);
+    for (size_t t = 0; t < parts.size(); ++t) {
+        r0[t + 1] = r0[t] + parts[t].seq_end.size();
+        n0[t + 1] = n0[t] + parts[t].names.size();
+        c0[t + 1] = c0[t] + parts[t].comments.size();
+        s0[t + 1] = s0[t] + parts[t].seq.size();
+        rs->max_len = std::max(rs->max_len, parts[t].max_len);
+    }
+    const size_t n = r0.back();
+    rs->names.resize(n0.back()); rs->comments.resize(c0.back()); rs->seq.resize(s0.back()); rs->qual.resize(s0.back());
+    rs->name_off.assign(n + 1, 0); rs->comment_off.assign(n + 1, 0); rs->off.assign(n + 1, 0);
+    rs->rg.resize(n); rs->second.resize(n);
+    parallel_for(parts.size(), (int)parts.size(), [&](size_t lo, size_t hi, int) {
+        for (size_t t = lo; t < hi; ++t) {
+            const FastqPart& pt = parts[t];
+            if (!pt.names.empty()) std::memcpy(&rs->names[n0[t]], pt.names.data(), pt.names.size());
+            if (!pt.comments.empty()) std::memcpy(&rs->comments[c0[t]], pt.comments.data(), pt.comments.size());
+            if (!pt.seq.empty()) std::memcpy(&rs->seq[s0[t]], pt.seq.data(), pt.seq.size());
+            if (!pt.qual.empty()) std::memcpy(&rs->qual[s0[t]], pt.qual.data(), pt.qual.size());
+            for (size_t i = 0; i < pt.seq_end.size(); ++i) {
+                rs->name_off[r0[t] + i + 1] = n0[t] + pt.name_end[i];
+                rs->comment_off[r0[t] + i + 1] = c0[t] + pt.comment_end[i];
+                rs->off[r0[t] + i + 1] = s0[t] + pt.seq_end[i];
+                rs->rg[r0[t] + i] = remap[t][pt.rg[i]];
+                rs->second[r0[t] + i] = pt.second[i];
+            }
+        }
+    });
+    pt_.mark("fastq: stitch");
     return rs;
 }
 
-FastqFile::FastqFile(std::string filename, int nthreads) : StoreFile(load_fastq(filename), nthreads) {}
+FastqFile::FastqFile(std::string filename, int nthreads) : StoreFile(load_fastq(filename, nthreads), nthreads) {}
 
 StoreFile::~StoreFile() {
     if (out_) {
@@ -311,7 +573,7 @@ readutils::CReadData StoreFile::get() {
     r.skips.assign(r.seq.size(), false);
     r.errors.assign(r.seq.size(), false);
     r.name.assign(store_->names.data() + store_->name_off[i], store_->names.data() + store_->name_off[i + 1]);
-    if (store_->bam_off.empty()) {  // FASTQ: first '_' field without its /1 or /2 (readutils.cc:74-97); BAM: the qname
+    if (store_->bam_header.empty()) {  // FASTQ: first '_' field without its /1 or /2 (readutils.cc:74-97); BAM: the qname
         r.name = r.name.substr(0, r.name.find('_'));
         if (r.name.size() >= 2 && (r.name.substr(r.name.size() - 2) == "/1" || r.name.substr(r.name.size() - 2) == "/2"))
             r.name = r.name.substr(0, r.name.size() - 2);
@@ -333,7 +595,9 @@ static const size_t kBgzfInput = 0xff00;
 static bool bgzf_block(const char* in, size_t n, std::string& out) {
     z_stream zs;
     std::memset(&zs, 0, sizeof zs);
-    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    // htslib's bgzf_open(.., "w") compresses at zlib's default level; KBBQ_BGZF_LEVEL=0..9 overrides (1 is ~3x faster)
+    static const int level = [] { const char* e = getenv("KBBQ_BGZF_LEVEL"); return e && *e >= '0' && *e <= '9' ? *e - '0' : Z_DEFAULT_COMPRESSION; }();
+    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
     const size_t start = out.size();
     out.resize(start + 18 + deflateBound(&zs, n) + 8);
     unsigned char* o = (unsigned char*)&out[start];
@@ -386,38 +650,77 @@ int StoreFile::write() {
 int StoreFile::write_all(const kbbq::Session& ses, const std::vector<std::vector<uint8_t>>& newq) {
     if (!out_ || flush_pending(false) < 0) return -1;
     const kbbq::ReadStore& rs = *store_;
-    const size_t chunk = 1u << 15;
-    const int nt = (int)std::max(1u, nthreads_ > 0 ? (unsigned)nthreads_ : std::min(16u, std::thread::hardware_concurrency()));
+    // Jobs of 8 Ki records are formatted and compressed by a pool (dynamic hand-out: records and compression ratios
+    // vary), and written by this thread in input order as they complete; at most `window` finished jobs wait.
+    const size_t chunk = 1u << 13;
+    const int nt = pool_size(nthreads_);
     struct Job { size_t b, lo, hi; };
     std::vector<Job> jobs;
     for (size_t b = 0; b < ses.batch_ranges().size(); ++b)
         for (size_t lo = ses.batch_ranges()[b].first; lo < ses.batch_ranges()[b].second; lo += chunk)
             jobs.push_back({b, lo, std::min(ses.batch_ranges()[b].second, lo + chunk)});
-    const size_t wave = (size_t)nt * 4;
-    std::vector<std::string> outs(wave);
-    for (size_t j0 = 0; j0 < jobs.size(); j0 += wave) {
-        const size_t j1 = std::min(jobs.size(), j0 + wave);
-        std::vector<std::thread> th;
-        std::vector<int> ok(nt, 1);
-        for (int t = 0; t < nt; ++t)
-            th.emplace_back([&, t] {
-                std::string text;
-                for (size_t j = j0 + t; j < j1; j += nt) {
-                    const Job& jb = jobs[j];
-                    text.clear();
-                    outs[j - j0].clear();
-                    const size_t first = ses.batch_ranges()[jb.b].first;
-                    for (size_t i = jb.lo; i < jb.hi; ++i)
-                        format_record(i, newq[jb.b].data() + (size_t)ses.word_off(jb.b)[i - first] * 32, text);
-                    if (!bgzf_compress(text, outs[j - j0])) ok[t] = 0;
+    const size_t window = (size_t)nt * 8;
+    std::vector<std::string> outs(jobs.size());
+    std::vector<char> done(jobs.size(), 0);
+    std::mutex mu;
+    std::condition_variable cv_done, cv_room;
+    std::atomic<size_t> next{0};
+    size_t written = 0;  // guarded by mu
+    bool failed = false;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&] {
+            std::string text;
+            for (;;) {
+                const size_t j = next.fetch_add(1);
+                if (j >= jobs.size()) return;
+                {   // do not run further ahead of the writer than the window
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_room.wait(lk, [&] { return failed || j < written + window; });
+                    if (failed) return;
                 }
-            });
-        for (auto& t : th) t.join();
-        for (int t = 0; t < nt; ++t)
-            if (!ok[t]) return -1;
-        for (size_t j = j0; j < j1; ++j)
-            if (fwrite(outs[j - j0].data(), 1, outs[j - j0].size(), (FILE*)out_) != outs[j - j0].size()) return -1;
+                const Job& jb = jobs[j];
+                text.clear();
+                const size_t first = ses.batch_ranges()[jb.b].first;
+                for (size_t i = jb.lo; i < jb.hi; ++i)
+                    format_record(i, newq[jb.b].data() + (size_t)ses.word_off(jb.b)[i - first] * 32, text);
+                std::string z;
+                const bool ok = bgzf_compress(text, z);
+                std::lock_guard<std::mutex> lk(mu);
+                outs[j].swap(z);
+                done[j] = 1;
+                if (!ok) failed = true;
+                cv_done.notify_all();
+                if (!ok) cv_room.notify_all();
+            }
+        });
+    int rc = 0;
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        std::string z;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return failed || done[j]; });
+            if (failed) { rc = -1; break; }
+            z.swap(outs[j]);
+        }
+        if (fwrite(z.data(), 1, z.size(), (FILE*)out_) != z.size()) {
+            std::lock_guard<std::mutex> lk(mu);
+            failed = true;
+            rc = -1;
+            cv_room.notify_all();
+            break;
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        written = j + 1;
+        cv_room.notify_all();
     }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc) failed = true;
+        cv_room.notify_all();
+    }
+    for (auto& t : th) t.join();
+    if (rc) return rc;
     cur_ = rs.n();
     return 0;
 }
@@ -425,31 +728,23 @@ int StoreFile::write_all(const kbbq::Session& ses, const std::vector<std::vector
 void FastqFile::format_record(size_t i, const uint8_t* q, std::string& s) const {
     // "@" + name + "\n" + seq + "\n+" + comment + "\n" + qual + "\n": the comment moves to the '+' line (htsiter.cc:84)
     const kbbq::ReadStore& rs = *store_;
-    s.push_back('@');
-    s.append(rs.names.data() + rs.name_off[i], rs.names.data() + rs.name_off[i + 1]);
-    s.push_back('\n');
-    s.append(rs.seq.data() + rs.off[i], rs.seq.data() + rs.off[i + 1]);
-    s.append("\n+");
-    s.append(rs.comments.data() + rs.comment_off[i], rs.comments.data() + rs.comment_off[i + 1]);
-    s.push_back('\n');
-    const size_t L = rs.off[i + 1] - rs.off[i];
-    for (size_t j = 0; j < L; ++j) s.push_back((char)(q[j] + 33));
-    s.push_back('\n');
+    const size_t nl = rs.name_off[i + 1] - rs.name_off[i], cl = rs.comment_off[i + 1] - rs.comment_off[i], L = rs.off[i + 1] - rs.off[i];
+    const size_t at = s.size();
+    s.resize(at + 1 + nl + 1 + L + 2 + cl + 1 + L + 1);
+    char* o = &s[at];
+    *o++ = '@';
+    std::memcpy(o, rs.names.data() + rs.name_off[i], nl); o += nl;
+    *o++ = '\n';
+    std::memcpy(o, rs.seq.data() + rs.off[i], L); o += L;
+    *o++ = '\n';
+    *o++ = '+';
+    std::memcpy(o, rs.comments.data() + rs.comment_off[i], cl); o += cl;
+    *o++ = '\n';
+    for (size_t j = 0; j < L; ++j) o[j] = (char)(q[j] + 33);
+    o[L] = '\n';
 }
 
 // ---- BAM ---------------------------------------------------------------------------------------------------------------
-static std::vector<uint8_t> gunzip_all(const std::string& filename) {
-    gzFile gz = filename == "-" ? gzdopen(0, "rb") : gzopen(filename.c_str(), "rb");
-    if (!gz) throw std::runtime_error("Error opening file " + filename);
-    gzbuffer(gz, 1 << 22);
-    std::vector<uint8_t> data;
-    std::vector<uint8_t> buf(1 << 24);
-    int got;
-    while ((got = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.insert(data.end(), buf.begin(), buf.begin() + got);
-    gzclose(gz);
-    return data;
-}
-
 bool is_bam_file(const std::string& filename) {
     gzFile gz = gzopen(filename.c_str(), "rb");
     if (!gz) throw std::runtime_error("Error opening file " + filename);
@@ -513,84 +808,119 @@ static BamRec bam_parse(const uint8_t* rec, size_t len) {
     return r;
 }
 
-static std::shared_ptr<kbbq::ReadStore> load_bam(const std::string& filename, bool use_oq) {
-    std::vector<uint8_t> d = gunzip_all(filename);
+static std::shared_ptr<kbbq::ReadStore> load_bam(const std::string& filename, bool use_oq, int nthreads) {
     auto rs = std::make_shared<kbbq::ReadStore>();
     rs->path = filename;
+    PhaseTimer pt_;
+    rs->bam_raw = read_all_decompressed(filename, nthreads);
+    pt_.mark("bam: read + decompress");
+    const std::vector<uint8_t>& d = rs->bam_raw;
     if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) throw std::runtime_error("Error opening file " + filename);
     size_t p = 4;
     int32_t l_text, n_ref;
     std::memcpy(&l_text, &d[p], 4); p += 4 + (size_t)l_text;
+    if (p + 4 > d.size()) throw std::runtime_error("truncated BAM header in " + filename);
     std::memcpy(&n_ref, &d[p], 4); p += 4;
     for (int i = 0; i < n_ref; ++i) {
         int32_t l_name; uint32_t l_ref;
+        if (p + 4 > d.size()) throw std::runtime_error("truncated BAM header in " + filename);
         std::memcpy(&l_name, &d[p], 4); p += 4 + (size_t)l_name;
+        if (p + 4 > d.size()) throw std::runtime_error("truncated BAM header in " + filename);
         std::memcpy(&l_ref, &d[p], 4); p += 4;
         rs->ref_len.push_back(l_ref);
     }
     rs->bam_header.assign(d.begin(), d.begin() + p);
-    rs->name_off.push_back(0); rs->comment_off.push_back(0); rs->off.push_back(0); rs->bam_off.push_back(0);
-    readutils::CReadData::rg_to_int.clear();
-    readutils::CReadData::rg_to_pu.clear();
-    static const char nt16[] = "=ACMGRSVTWYHKDBN";
-    static const int nt16_int[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
+    // record boundaries and column offsets: one cheap serial walk over the block_size chain
+    rs->name_off.push_back(0); rs->comment_off.push_back(0); rs->off.push_back(0);
     while (p + 4 <= d.size()) {
         int32_t block_size;
         std::memcpy(&block_size, &d[p], 4);
         p += 4;
         if (block_size < 32 || p + (size_t)block_size > d.size()) throw std::runtime_error("truncated BAM record in " + filename);
         const uint8_t* rec = &d[p];
-        const BamRec r = bam_parse(rec, (size_t)block_size);
-        const bool rev = r.flag & 16;
-        const std::string name((const char*)r.name);
-        // bam_seq_str (readutils.hh:30-42): forward orientation; a reverse-strand record is complemented, then reversed
-        const size_t L = (size_t)r.l_seq, s0 = rs->seq.size();
-        rs->seq.resize(s0 + L);
-        for (size_t i = 0; i < L; ++i) {
-            const int nib = (r.seq[i >> 1] >> ((~i & 1) << 2)) & 0xf;
-            char c = nt16[nib];
-            if (rev) c = nt16_int[nib] < 4 ? "ACGT"[3 - nt16_int[nib]] : 'N';
-            rs->seq[s0 + (rev ? L - 1 - i : i)] = c;
-        }
-        rs->qual.resize(s0 + L);
-        if (use_oq) {
-            const uint8_t* oq = aux_find(r.aux, r.end, "OQ", nullptr, nullptr);
-            if (!oq) {
-                std::cerr << "Error: --use-oq was specified but unable to read OQ tag on read " << name << std::endl;
-                throw std::invalid_argument("Unable to read OQ tag.");
-            }
-            for (size_t i = 0; i < L; ++i) rs->qual[s0 + (rev ? L - 1 - i : i)] = (uint8_t)(oq[i] - 33);
-        } else {
-            for (size_t i = 0; i < L; ++i) rs->qual[s0 + (rev ? L - 1 - i : i)] = r.qual[i];
-        }
-        const uint8_t* rgz = aux_find(r.aux, r.end, "RG", nullptr, nullptr);
-        if (!rgz) {
-            std::cerr << "Error: Unable to read RG tag on read " << name << std::endl;
-            throw std::invalid_argument("Unable to read RG tag.");
-        }
-        const std::string rg((const char*)rgz);
-        auto& r2i = readutils::CReadData::rg_to_int;
-        if (readutils::CReadData::rg_to_pu.count(rg) == 0) {
-            const int id = (int)r2i.size();
-            r2i[rg] = id;
-            readutils::CReadData::rg_to_pu[rg] = rg;
-        }
-        rs->rg.push_back((uint16_t)r2i[rg]);
-        rs->second.push_back((r.flag & 0x80) ? 1 : 0);
-        rs->names.insert(rs->names.end(), name.begin(), name.end());
-        rs->name_off.push_back(rs->names.size());
+        int32_t l_seq;
+        std::memcpy(&l_seq, rec + 16, 4);
+        const size_t l_name = rec[8] ? strnlen((const char*)rec + 32, rec[8]) : 0;
+        rs->bam_rec_off.push_back(p);
+        rs->bam_rec_len.push_back((uint32_t)block_size);
+        rs->name_off.push_back(rs->name_off.back() + l_name);
         rs->comment_off.push_back(0);
-        rs->off.push_back(rs->seq.size());
-        rs->max_len = std::max<uint32_t>(rs->max_len, (uint32_t)L);
-        rs->bam_blob.insert(rs->bam_blob.end(), rec, rec + block_size);
-        rs->bam_off.push_back(rs->bam_blob.size());
+        rs->off.push_back(rs->off.back() + (size_t)std::max(l_seq, 0));
+        rs->max_len = std::max<uint32_t>(rs->max_len, (uint32_t)std::max(l_seq, 0));
         p += (size_t)block_size;
     }
+    pt_.mark("bam: record index");
+    const size_t n = rs->bam_rec_off.size();
+    rs->names.resize(rs->name_off.back());
+    rs->seq.resize(rs->off.back());
+    rs->qual.resize(rs->off.back());
+    rs->rg.resize(n);
+    rs->second.resize(n);
+    // the records themselves, converted by a pool of threads
+    const int nt = (int)std::min<size_t>((size_t)pool_size(nthreads), std::max<size_t>(1, n >> 12));
+    std::vector<RgTable> tables((size_t)nt);
+    std::vector<std::string> errors((size_t)nt);
+    std::vector<size_t> lo_of((size_t)nt + 1, n);
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";
+    static const int nt16_int[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
+    parallel_for(n, nt, [&](size_t lo, size_t hi, int t) {
+        lo_of[t] = lo;
+        for (size_t i = lo; i < hi; ++i) {
+            const uint8_t* rec = &d[rs->bam_rec_off[i]];
+            const BamRec r = bam_parse(rec, rs->bam_rec_len[i]);
+            const bool rev = r.flag & 16;
+            const size_t L = (size_t)std::max(r.l_seq, 0), s0 = rs->off[i];
+            if (r.aux > r.end) { errors[t] = "truncated BAM record in " + filename; return; }
+            std::memcpy(rs->names.data() + rs->name_off[i], r.name, rs->name_off[i + 1] - rs->name_off[i]);
+            // bam_seq_str (readutils.hh:30-42): forward orientation; a reverse-strand record is complemented, then reversed
+            for (size_t j = 0; j < L; ++j) {
+                const int nib = (r.seq[j >> 1] >> ((~j & 1) << 2)) & 0xf;
+                char c = nt16[nib];
+                if (rev) c = nt16_int[nib] < 4 ? "ACGT"[3 - nt16_int[nib]] : 'N';
+                rs->seq[s0 + (rev ? L - 1 - j : j)] = c;
+            }
+            if (use_oq) {
+                const uint8_t* oq = aux_find(r.aux, r.end, "OQ", nullptr, nullptr);
+                if (!oq || strnlen((const char*)oq, (size_t)(r.end - oq)) < L) {
+                    errors[t] = std::string("Error: --use-oq was specified but unable to read OQ tag on read ") + std::string((const char*)r.name) +
+                                "\nUnable to read OQ tag.";
+                    return;
+                }
+                for (size_t j = 0; j < L; ++j) rs->qual[s0 + (rev ? L - 1 - j : j)] = (uint8_t)(oq[j] - 33);
+            } else {
+                for (size_t j = 0; j < L; ++j) rs->qual[s0 + (rev ? L - 1 - j : j)] = r.qual[j];
+            }
+            const uint8_t* rgz = aux_find(r.aux, r.end, "RG", nullptr, nullptr);
+            if (!rgz) {
+                errors[t] = std::string("Error: Unable to read RG tag on read ") + std::string((const char*)r.name) + "\nUnable to read RG tag.";
+                return;
+            }
+            rs->rg[i] = tables[t].id(std::string((const char*)rgz));
+            rs->second[i] = (r.flag & 0x80) ? 1 : 0;
+        }
+    });
+    for (const std::string& e : errors)
+        if (!e.empty()) {  // the reference prints the first line and throws std::invalid_argument with the second (readutils.cc:17-52)
+            const size_t nl = e.find('\n');
+            if (nl != std::string::npos) {
+                std::cerr << e.substr(0, nl) << std::endl;
+                throw std::invalid_argument(e.substr(nl + 1));
+            }
+            throw std::runtime_error(e);
+        }
+    pt_.mark("bam: convert records");
+    const std::vector<std::vector<uint16_t>> remap = merge_rg_tables(tables);
+    parallel_for((size_t)nt, nt, [&](size_t lo, size_t hi, int) {
+        for (size_t t = lo; t < hi; ++t) {
+            const size_t end = t + 1 < (size_t)nt ? lo_of[t + 1] : n;
+            for (size_t i = lo_of[t]; i < end && i < n; ++i) rs->rg[i] = remap[t][rs->rg[i]];
+        }
+    });
     return rs;
 }
 
 BamFile::BamFile(std::string filename, int nthreads, bool use_oq, bool set_oq)
-    : StoreFile(load_bam(filename, use_oq), nthreads), use_oq_(use_oq), set_oq_(set_oq) {}
+    : StoreFile(load_bam(filename, use_oq, nthreads), nthreads), use_oq_(use_oq), set_oq_(set_oq) {}
 
 void BamFile::format_header(std::string& out) const { out.append((const char*)store_->bam_header.data(), store_->bam_header.size()); }
 
@@ -598,8 +928,8 @@ void BamFile::format_record(size_t i, const uint8_t* newq, std::string& out) con
     // BamFile::recalibrate + write (htsiter.cc:11-35,45): optional OQ tag from the record's current qualities, then the
     // new qualities, reversed back for a reverse-strand record
     const kbbq::ReadStore& rs = *store_;
-    const uint8_t* rec = rs.bam_blob.data() + rs.bam_off[i];
-    const size_t len = rs.bam_off[i + 1] - rs.bam_off[i];
+    const uint8_t* rec = rs.bam_raw.data() + rs.bam_rec_off[i];
+    const size_t len = rs.bam_rec_len[i];
     const BamRec r = bam_parse(rec, len);
     const size_t L = (size_t)r.l_seq;
     std::string body((const char*)rec, len);

@@ -11,6 +11,7 @@
 #include <array>
 #include <cstdint>
 #include <memory>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -24,19 +25,52 @@
 
 namespace kbbq {
 
+// A column of the ReadStore: like std::vector for what the store needs, but resize() leaves new bytes uninitialised --
+// the loaders fill every byte from several threads, and zero-filling hundreds of MB first would be a serial pass of
+// page faults in the calling thread.
+template <class T>
+class Column {
+public:
+    Column() = default;
+    Column(const Column&) = delete;
+    Column& operator=(const Column&) = delete;
+    void resize(size_t n) {
+        if (n > cap_) {
+            T* p = static_cast<T*>(::operator new(n * sizeof(T)));
+            if (n_) std::memcpy(p, p_.get(), n_ * sizeof(T));
+            p_.reset(p);
+            cap_ = n;
+        }
+        n_ = n;
+    }
+    T* data() { return p_.get(); }
+    const T* data() const { return p_.get(); }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T& operator[](size_t i) { return p_.get()[i]; }
+    const T& operator[](size_t i) const { return p_.get()[i]; }
+
+private:
+    struct Free { void operator()(T* p) const { ::operator delete(p); } };
+    std::unique_ptr<T, Free> p_;
+    size_t n_ = 0, cap_ = 0;
+};
+
 // Everything parsed from the input, kept for all passes: the reference's per-record kseq_t / CReadData, columnar.
 struct ReadStore {
     std::string path;
-    std::vector<char> names, comments, seq;  // concatenated, no terminators
-    std::vector<uint8_t> qual;               // phred
+    Column<char> names, comments, seq;  // concatenated, no terminators
+    Column<uint8_t> qual;               // phred
     std::vector<uint64_t> name_off, comment_off, off;  // n+1 each
     std::vector<uint16_t> rg;
     std::vector<uint8_t> second;
     size_t n() const { return off.empty() ? 0 : off.size() - 1; }
     uint32_t max_len = 0;
-    // BAM input only: the header as it was read, every record's bytes (core + data, without block_size), strand flags
-    std::vector<uint8_t> bam_header, bam_blob;
-    std::vector<uint64_t> bam_off;
+    // BAM input only: the header as it was read, the whole uncompressed stream, and where each record's body (core +
+    // data, without its block_size field) sits in it; reference lengths from the header
+    std::vector<uint8_t> bam_header, bam_raw;
+    std::vector<uint64_t> bam_rec_off;
+    std::vector<uint32_t> bam_rec_len;
     std::vector<uint64_t> ref_len;
 };
 

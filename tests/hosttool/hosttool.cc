@@ -15,14 +15,15 @@ int main(int argc, char** argv) {
     if (argc < 3) return 2;
     const std::string mode = argv[1], fn = argv[2];
     bool set_oq = false, use_oq = false;
+    const int nthreads = getenv("HOSTTOOL_THREADS") ? atoi(getenv("HOSTTOOL_THREADS")) : 0;  // 0 = the library default
     for (int i = 3; i < argc; ++i) {
         if (!strcmp(argv[i], "set_oq")) set_oq = true;
         if (!strcmp(argv[i], "use_oq")) use_oq = true;
     }
     try {
         std::unique_ptr<htsiter::StoreFile> f;
-        if (htsiter::is_bam_file(fn)) f.reset(new htsiter::BamFile(fn, 1, use_oq, set_oq));
-        else f.reset(new htsiter::FastqFile(fn, 1));
+        if (htsiter::is_bam_file(fn)) f.reset(new htsiter::BamFile(fn, nthreads, use_oq, set_oq));
+        else f.reset(new htsiter::FastqFile(fn, nthreads));
         if (mode == "load") {  // parse only: prints the number of records and bases
             std::cout << f->store().n() << '\t' << f->store().off.back() << '\n';
         } else if (mode == "dump") {
