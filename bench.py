@@ -216,10 +216,12 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         comm = GpuComm(rank, world, local)
 
-    # ---- synthetic shard of this rank: reads over the WHOLE (world x per-GPU) genome, distinct seed per rank
+    # ---- synthetic shard of this rank: reads over the WHOLE (world x per-GPU) genome -- one genome shared by all ranks
+    #      (genome_seed), a distinct read stream per rank
     genomelen = args.genome * world
     n_reads = args.genome * args.coverage // READ_LEN
-    rs = synth.make_reads(genomelen, args.coverage, READ_LEN, seed=1000 + rank, n_rg=N_RG, n_reads=n_reads, keep_clean=False)
+    rs = synth.make_reads(genomelen, args.coverage, READ_LEN, seed=1000 + rank, n_rg=N_RG, n_reads=n_reads, keep_clean=False,
+                          genome_seed=None if world == 1 else 999)
     pb = api.PackedBatch(rs, pinned=True)
     total_bases = rs.total_bases * world
 

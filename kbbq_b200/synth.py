@@ -73,10 +73,14 @@ def make_reads(
     n_reads: int | None = None,
     chunk: int = 1 << 18,
     keep_clean: bool = True,
+    genome_seed: int | None = None,
 ) -> ReadSet:
-    """Appendix-C generator.  ``ragged`` draws lengths uniformly in [min_len, read_len]."""
+    """Appendix-C generator.  ``ragged`` draws lengths uniformly in [min_len, read_len].
+    ``genome_seed``: draw the genome from its own stream, so that several calls with different ``seed`` (the shards of
+    a multi-GPU run) sample reads from the SAME genome."""
     rng = np.random.default_rng(seed)
-    genome = rng.integers(0, 4, genome_len, dtype=np.uint8)
+    grng = rng if genome_seed is None else np.random.default_rng(genome_seed)
+    genome = grng.integers(0, 4, genome_len, dtype=np.uint8)
     n = genome_len * coverage // read_len if n_reads is None else n_reads
     if ragged:
         lo = read_len // 2 if min_len is None else min_len
