@@ -77,6 +77,7 @@ struct kbbq_ctx {
     int n_rg = 1;
     int max_cycle = 0;
     int sm_count = 148;
+    int l2_bytes = 126 << 20;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // side stream: quality arrays travel while pass 1 runs on `stream`
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -239,6 +240,12 @@ int slot_prefix(kbbq_ctx* ctx, const uint32_t* d_len, uint32_t n, unsigned long 
     cudaFreeAsync(tmp, ctx->stream);
     if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("slot prefix: ") + cudaGetErrorString(e));
     return KBBQ_OK;
+}
+
+// insert kernels read a block before OR-ing into it once the filter no longer fits the L2 (see warp_bloom_insert)
+bool test_first(const kbbq_ctx* ctx, int which) {
+    if (const char* e = getenv("KBBQ_TEST_FIRST")) return atoi(e) != 0;  // measurement override
+    return ctx->filt[which].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4;
 }
 
 int filter_ok(kbbq_ctx* ctx, int which) {
@@ -425,6 +432,7 @@ int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) 
     c->n_rg = n_rg;
     c->max_cycle = max_cycle;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&c->l2_bytes, cudaDevAttrL2CacheSize, device);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     {   // batch buffers come from the stream-ordered pool and stay cached in it: cudaMalloc/cudaFree of hundreds of MB
         // per batch cost up to a second each on this driver
@@ -875,8 +883,12 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
                                                                                      b->n_slots, ctx->sample_threshold, ctx->sample_all, b->d_sample_bits);
         if (int rc = check_launch(ctx, "rng_sample_kernel")) return rc;
         mark_kernel(ctx, "pass1_insert_kernel");
-        pass1_insert_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);
+        if (test_first(ctx, KBBQ_FILTER_SAMPLED))
+            pass1_insert_kernel<true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);
+        else
+            pass1_insert_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);
         if (int rc = check_launch(ctx, "pass1_insert_kernel")) return rc;
     }
     pass_end(ctx);
@@ -927,9 +939,14 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
     pass_begin(ctx);
     if (b->n_reads) {
         mark_kernel(ctx, "pass2_trusted_kernel");
-        pass2_trusted_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, ctx->d_thresholds,
-            err_bits ? b->d_err_bits : nullptr);
+        if (test_first(ctx, KBBQ_FILTER_TRUSTED))
+            pass2_trusted_kernel<true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, ctx->d_thresholds,
+                err_bits ? b->d_err_bits : nullptr);
+        else
+            pass2_trusted_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, ctx->d_thresholds,
+                err_bits ? b->d_err_bits : nullptr);
         if (int rc = check_launch(ctx, "pass2_trusted_kernel")) return rc;
     }
     pass_end(ctx);
