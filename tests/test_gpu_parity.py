@@ -231,3 +231,56 @@ def test_empty_batch_and_reads_shorter_than_k():
     assert ctx.bloom_inserted(0) == 0 and ctx.bloom_inserted(1) == 0 and int(ctx.covariates()[0].sum()) == 0
     db.free()
     ctx.close()
+
+
+def test_human_scale_filters_address_every_block():
+    """BASELINE.json configs[3]: a 3.1 Gb genome sizes the two filters at 26 GB and 43 GB (kbbq.cc:264-266), i.e. tables
+    far beyond 4 GiB and 2^29 blocks.  No oracle can hold them on this host, so the check is structural: geometry as the
+    reference computes it, every inserted key found again, each key's 64-byte block (hash_ap(key, salt_[0]) % n_blocks,
+    bloom.hh:99-106) holding exactly its pattern's bits when read back from device memory, and nothing else set."""
+    import torch
+    from kbbq_b200.dist import device_tensor
+    from oracle import port
+
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 80 << 30:
+        pytest.skip("needs ~70 GB of free HBM")
+    genomelen, cov = 3_100_000_000, 30
+    alpha = np.longdouble(7) / np.longdouble(cov)
+    approx = int(np.longdouble(genomelen) * cov * alpha)
+    rng = np.random.default_rng(11)
+    keys = np.unique(rng.integers(0, 2**64, 4096, dtype=np.uint64))
+    others = rng.integers(0, 2**64, 100000, dtype=np.uint64)
+    ctx = api.Context(32, 1, 150)
+    for which, fpr, n_salts in ((api.FILTER_SAMPLED, 0.01, 7), (api.FILTER_TRUSTED, 0.0005, 11)):
+        g = ctx.bloom_create(which, approx, fpr)
+        assert g.n_salts == n_salts and g.table_bits == g.n_blocks * 512 and g.table_bits // 8 > (20 << 30)
+        want = api.bloom_geometry(approx, fpr)
+        assert (g.table_bits, g.n_blocks, list(g.salts[:n_salts])) == (want.table_bits, want.n_blocks, list(want.salts[:n_salts]))
+        ctx.bloom_insert_keys(which, keys)
+        assert ctx.bloom_inserted(which) == len(keys)
+        assert ctx.bloom_query_keys(which, keys).all()
+        assert ctx.bloom_query_keys(which, others).mean() < 1e-3     # a near-empty table answers "no"
+        pat = api.bloom_patterns(g).reshape(65536, 8)
+        words = device_tensor(ctx.bloom_device_words(which), g.table_bits // 8, 0).view(torch.int64)
+        salt0, salt1 = int(g.salts[0]), int(g.salts[1])
+        blocks = {}
+        for key in keys.tolist():
+            blk = port.lib().ko_hash_ap8(key, salt0) % g.n_blocks
+            p = port.lib().ko_hash_ap8(key, salt1) & 0xFFFF
+            blocks[blk] = blocks.get(blk, np.zeros(8, dtype=np.uint64)) | pat[p]
+        assert max(blocks) * 64 > (16 << 30)                          # byte offsets beyond 16 GiB are exercised ...
+        for blk, bits in blocks.items():
+            got = words[blk * 8: blk * 8 + 8].cpu().numpy().view(np.uint64)
+            assert np.array_equal(got, bits), blk
+        # ... and the table holds nothing but those bits
+        total = int(sum(int(np.unpackbits(b.view(np.uint8)).sum()) for b in blocks.values()))
+        nz = 0
+        step = 1 << 27                                                 # 1 GiB of int64 words at a time
+        for lo in range(0, words.numel(), step):
+            w = words[lo: lo + step]
+            nzw = w[w != 0]
+            if nzw.numel():
+                nz += int(np.unpackbits(nzw.cpu().numpy().view(np.uint8)).sum())
+        assert nz == total
+    ctx.close()
