@@ -99,6 +99,7 @@ class Recalibrator:
             t0 = time.perf_counter()
             comm.merge_filter(ctx, api.FILTER_SAMPLED)
             st.merge_ms["sampled"] = (time.perf_counter() - t0) * 1e3
+            self._note_merge_kernel(st)
         # fprate -> phit -> thresholds (kbbq.cc:304-313)
         t0 = time.perf_counter()
         st.thresholds = ctx.compute_thresholds(self.alpha_ld)
@@ -109,6 +110,7 @@ class Recalibrator:
             t0 = time.perf_counter()
             comm.merge_filter(ctx, api.FILTER_TRUSTED)
             st.merge_ms["trusted"] = (time.perf_counter() - t0) * 1e3
+            self._note_merge_kernel(st)
         # pass 3
         e3 = timed_pass("pass3", lambda b: ctx.pass3(b, want_errors))
         if comm is not None:
@@ -126,6 +128,12 @@ class Recalibrator:
         st.launches = ctx.launches - launches0
         self.last_errors2, self.last_errors3, self.last_quals = e2, e3, quals
         return st
+
+    def _note_merge_kernel(self, st: RunStats) -> None:
+        """device time of the peer-memory merge kernel, when that is what merged the filter (it is timed like a pass)"""
+        for kn, kms in self.ctx.last_pass_kernels().items():
+            if kn == "or_allreduce_p2p_kernel":
+                st.kernel_ms[kn] = st.kernel_ms.get(kn, 0.0) + kms
 
     def close(self):
         self.clear_batches()
