@@ -3,6 +3,7 @@
 #include "../../include/kbbq_b200.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -246,10 +247,61 @@ int slot_prefix(kbbq_ctx* ctx, const uint32_t* d_len, uint32_t n, unsigned long 
     return KBBQ_OK;
 }
 
-// insert kernels read a block before OR-ing into it once the filter no longer fits the L2 (see warp_bloom_insert)
-bool test_first(const kbbq_ctx* ctx, int which) {
-    if (const char* e = getenv("KBBQ_TEST_FIRST")) return atoi(e) != 0;  // measurement override
-    return ctx->filt[which].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4;
+// How the pass-1 / pass-2 kernels insert (kbbq_kernels.cuh: INS_*): directly while the filter fits the L2, through a
+// sorted staging array once it does not (and the staging arrays fit a sane share of the device).
+// KBBQ_INSERT_MODE=0|1|2 overrides (measurement, tests).
+int insert_mode(const kbbq_ctx* ctx, int which, uint64_t n_slots) {
+    if (const char* e = getenv("KBBQ_INSERT_MODE")) return atoi(e);
+    if (ctx->filt[which].geom.table_bits / 8 <= (size_t)ctx->l2_bytes * 3 / 4) return INS_DIRECT;
+    return n_slots * 16 <= (24ull << 30) ? INS_STAGED : INS_TEST_FIRST;
+}
+
+struct Staging {  // device buffers of one staged-insert launch; released in stream order
+    unsigned long long *items = nullptr, *sorted = nullptr, *cursor = nullptr;
+    uint64_t capacity = 0;
+};
+int staging_begin(kbbq_ctx* ctx, uint64_t n_slots, int grid_warps, Staging& st) {
+    // every insert takes one item; closing a granule wastes at most 31 of its 512 items (a warp appends <= 32 at a time),
+    // and every warp leaves its last granule partly used
+    st.capacity = n_slots + n_slots / 8 + (uint64_t)(grid_warps + 1) * KBBQ_STAGE_GRANULE * 2;
+    CU(cudaMallocAsync(&st.items, st.capacity * 8, ctx->stream));
+    CU(cudaMallocAsync(&st.sorted, st.capacity * 8, ctx->stream));
+    CU(cudaMallocAsync(&st.cursor, 8, ctx->stream));
+    CU(cudaMemsetAsync(st.cursor, 0, 8, ctx->stream));
+    return KBBQ_OK;
+}
+void staging_free(kbbq_ctx* ctx, Staging& st) {
+    if (st.items) cudaFreeAsync(st.items, ctx->stream);
+    if (st.sorted) cudaFreeAsync(st.sorted, ctx->stream);
+    if (st.cursor) cudaFreeAsync(st.cursor, ctx->stream);
+    st = Staging();
+}
+// sort the staged (block, pattern) items by block range and apply them to filter `which`
+int staging_apply(kbbq_ctx* ctx, int which, Staging& st) {
+    unsigned long long n_items = 0;
+    CU(cudaMemcpyAsync(&n_items, st.cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_items > st.capacity) return fail(KBBQ_ECUDA, "staged inserts overflowed their buffer");
+    if (n_items == 0) return KBBQ_OK;
+    const Filter& f = ctx->filt[which];
+    // buckets of 2^18 blocks = 16 MiB of table: sort on the block bits above them (items are (block << 16) | pattern)
+    int top = 0;
+    while ((1ull << top) < f.geom.n_blocks) ++top;
+    const int begin_bit = 16 + 18, end_bit = std::max(16 + top, begin_bit + 1);
+    const unsigned long long* src = st.items;
+    if (16 + top > begin_bit) {
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, st.items, st.sorted, n_items, begin_bit, end_bit, ctx->stream));
+        void* tmp = nullptr;
+        CU(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), ctx->stream));
+        cudaError_t e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, st.items, st.sorted, n_items, begin_bit, end_bit, ctx->stream);
+        cudaFreeAsync(tmp, ctx->stream);
+        if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("staged insert sort: ") + cudaGetErrorString(e));
+        src = st.sorted;
+    }
+    mark_kernel(ctx, "bloom_insert_sorted_kernel");
+    bloom_insert_sorted_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f.view(), src, n_items);
+    return check_launch(ctx, "bloom_insert_sorted_kernel");
 }
 
 int filter_ok(kbbq_ctx* ctx, int which) {
@@ -879,21 +931,35 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
     if (b->n_slots) {
         const uint64_t chunks = (b->n_slots + 1023) / 1024;
         if (!b->d_sample_bits) CU(cudaMallocAsync(&b->d_sample_bits, chunks * 32 * 4, ctx->stream));
-        uint64_t st[4];
-        std::memcpy(st, ctx->sampler_state0, 32);
-        host::rng_advance(st, ctx->sampler_pos);
+        uint64_t rs[4];
+        std::memcpy(rs, ctx->sampler_state0, 32);
+        host::rng_advance(rs, ctx->sampler_pos);
         mark_kernel(ctx, "rng_sample_kernel");
-        rng_sample_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(st[0], st[1], st[2], st[3], ctx->d_jump,
+        rng_sample_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(rs[0], rs[1], rs[2], rs[3], ctx->d_jump,
                                                                                      b->n_slots, ctx->sample_threshold, ctx->sample_all, b->d_sample_bits);
         if (int rc = check_launch(ctx, "rng_sample_kernel")) return rc;
         mark_kernel(ctx, "pass1_insert_kernel");
-        if (test_first(ctx, KBBQ_FILTER_SAMPLED))
-            pass1_insert_kernel<true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);
+        const int grid = read_grid(ctx, b->n_reads);
+        const int mode = insert_mode(ctx, KBBQ_FILTER_SAMPLED, b->n_slots);
+        Staging st;
+        StageSink sink{nullptr, nullptr};
+        if (mode == INS_STAGED) {
+            if (int rc = staging_begin(ctx, b->n_slots, grid * KBBQ_WARPS_PER_BLOCK, st)) return rc;
+            sink = StageSink{st.items, st.cursor};
+        }
+        const BloomView fv = ctx->filt[KBBQ_FILTER_SAMPLED].view();
+        if (mode == INS_STAGED)
+            pass1_insert_kernel<INS_STAGED><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
+        else if (mode == INS_TEST_FIRST)
+            pass1_insert_kernel<INS_TEST_FIRST><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
         else
-            pass1_insert_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->k, b->d_sample_bits);
+            pass1_insert_kernel<INS_DIRECT><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
         if (int rc = check_launch(ctx, "pass1_insert_kernel")) return rc;
+        if (mode == INS_STAGED) {
+            const int rc = staging_apply(ctx, KBBQ_FILTER_SAMPLED, st);
+            staging_free(ctx, st);
+            if (rc) return rc;
+        }
     }
     pass_end(ctx);
     ctx->sampler_pos += b->n_slots;
@@ -943,15 +1009,28 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
     pass_begin(ctx);
     if (b->n_reads) {
         mark_kernel(ctx, "pass2_trusted_kernel");
-        if (test_first(ctx, KBBQ_FILTER_TRUSTED))
-            pass2_trusted_kernel<true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, ctx->d_thresholds,
-                err_bits ? b->d_err_bits : nullptr);
+        const int grid = read_grid(ctx, b->n_reads);
+        const int mode = insert_mode(ctx, KBBQ_FILTER_TRUSTED, b->n_slots);
+        Staging st;
+        StageSink sink{nullptr, nullptr};
+        if (mode == INS_STAGED) {
+            if (int rc = staging_begin(ctx, b->n_slots, grid * KBBQ_WARPS_PER_BLOCK, st)) return rc;
+            sink = StageSink{st.items, st.cursor};
+        }
+        const BloomView sv = ctx->filt[KBBQ_FILTER_SAMPLED].view(), tv = ctx->filt[KBBQ_FILTER_TRUSTED].view();
+        uint32_t* eo = err_bits ? b->d_err_bits : nullptr;
+        if (mode == INS_STAGED)
+            pass2_trusted_kernel<INS_STAGED><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink);
+        else if (mode == INS_TEST_FIRST)
+            pass2_trusted_kernel<INS_TEST_FIRST><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink);
         else
-            pass2_trusted_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-                b->view(), ctx->filt[KBBQ_FILTER_SAMPLED].view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, ctx->d_thresholds,
-                err_bits ? b->d_err_bits : nullptr);
+            pass2_trusted_kernel<INS_DIRECT><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink);
         if (int rc = check_launch(ctx, "pass2_trusted_kernel")) return rc;
+        if (mode == INS_STAGED) {
+            const int rc = staging_apply(ctx, KBBQ_FILTER_TRUSTED, st);
+            staging_free(ctx, st);
+            if (rc) return rc;
+        }
     }
     pass_end(ctx);
     return fetch_bits(ctx, b, err_bits);

@@ -167,6 +167,54 @@ struct InsertStage {
 // it, which halves the DRAM traffic of a filter that does not fit the L2 (the launch picks the variant by table size;
 // for an L2-resident filter the extra load only costs issue slots).  Same bits either way: OR is idempotent, and a
 // stale read can only cause a redundant atomic, never a missed one.
+// Insert modes of the pass-1 and pass-2 kernels (a template parameter; the launch picks by filter size):
+//   INS_DIRECT      atomicOr straight into the table -- filters that sit in the L2
+//   INS_TEST_FIRST  the same, reading the block first (above)
+//   INS_STAGED      do not touch the table: append (block, pattern) to a staging array; the host then sorts the
+//                   array by block range (cub radix sort on the bucket bits) and bloom_insert_sorted_kernel applies it,
+//                   so that at any moment all SMs update one L2-sized slice of an HBM-sized table instead of scattering
+//                   128-byte line fills and dirty write-backs over all of it.  Same bits: OR is order independent.
+enum { INS_DIRECT = 0, INS_TEST_FIRST = 1, INS_STAGED = 2 };
+#define KBBQ_STAGE_GRANULE 512                  // items a warp reserves at a time from the staging array
+#define KBBQ_STAGE_SENTINEL 0xFFFFFFFFFFFFFFFFull  // filler of unused reservation tails; sorts last, applies nothing
+
+struct StageSink {
+    unsigned long long* items;     // staging array: (block << 16) | pattern
+    unsigned long long* cursor;    // items reserved so far (a multiple of the granule)
+};
+struct StageCursor {  // per warp, in registers (uniform across the lanes)
+    unsigned long long base;
+    uint32_t used;
+};
+// append the (block, pattern) of the lanes with `ins` set; returns how many.  All 32 lanes must call.
+__device__ __forceinline__ int warp_stage_insert(const BloomView& f, const StageSink& sink, StageCursor& cur, bool ins, uint64_t key) {
+    const uint32_t imask = __ballot_sync(KBBQ_FULL, ins);
+    if (imask == 0) return 0;
+    const int lane = threadIdx.x & 31, n = __popc(imask);
+    if (cur.used + (uint32_t)n > KBBQ_STAGE_GRANULE) {  // close the granule with filler, reserve the next one
+        for (uint32_t i = cur.used + lane; i < KBBQ_STAGE_GRANULE; i += 32) sink.items[cur.base + i] = KBBQ_STAGE_SENTINEL;
+        unsigned long long nb = 0;
+        if (lane == 0) nb = atomicAdd(sink.cursor, (unsigned long long)KBBQ_STAGE_GRANULE);
+        cur.base = __shfl_sync(KBBQ_FULL, nb, 0);
+        cur.used = 0;
+    }
+    if (ins) {
+        const int rank = __popc(imask & ((1u << lane) - 1));
+        sink.items[cur.base + cur.used + rank] = ((unsigned long long)bloom_block(f, key) << 16) | bloom_pattern(f, key);
+    }
+    cur.used += (uint32_t)n;
+    return n;
+}
+__device__ __forceinline__ void warp_stage_open(const StageSink& sink, StageCursor& cur) {
+    unsigned long long nb = 0;
+    if ((threadIdx.x & 31) == 0) nb = atomicAdd(sink.cursor, (unsigned long long)KBBQ_STAGE_GRANULE);
+    cur.base = __shfl_sync(KBBQ_FULL, nb, 0);
+    cur.used = 0;
+}
+__device__ __forceinline__ void warp_stage_close(const StageSink& sink, const StageCursor& cur) {
+    for (uint32_t i = cur.used + (threadIdx.x & 31); i < KBBQ_STAGE_GRANULE; i += 32) sink.items[cur.base + i] = KBBQ_STAGE_SENTINEL;
+}
+
 template <bool TEST_FIRST>
 __device__ __forceinline__ int warp_bloom_insert(const BloomView& f, bool ins, uint64_t key, InsertStage& stage) {
     const uint32_t imask = __ballot_sync(KBBQ_FULL, ins);
@@ -256,14 +304,17 @@ __global__ void __launch_bounds__(128) rng_sample_kernel(uint64_t s0, uint64_t s
 }
 
 // ---- pass 1b: insert the sampled k-mers (recalibrateutils.cc:7-13) ---------------------------------------------------
-template <bool TEST_FIRST>
+template <int MODE>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel(BatchView b, BloomView f, int k,
-                                                                                  const uint32_t* __restrict__ sample_bits) {
+                                                                                  const uint32_t* __restrict__ sample_bits,
+                                                                                  StageSink sink) {
     __shared__ InsertStage stage_all[KBBQ_WARPS_PER_BLOCK];
     InsertStage& stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
+    StageCursor cur{0, 0};
+    if (MODE == INS_STAGED) warp_stage_open(sink, cur);
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
         const int len = (int)b.len[r];
         const int nk = len - k + 1;
@@ -280,9 +331,11 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
                 if ((__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u)
                     ins = kmer_key(s, j, k, 0, -1, key);  // an invalid k-mer still consumed its draw
             }
-            inserted += warp_bloom_insert<TEST_FIRST>(f, ins, key, stage);
+            if (MODE == INS_STAGED) inserted += warp_stage_insert(f, sink, cur, ins, key);
+            else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(f, ins, key, stage);
         }
     }
+    if (MODE == INS_STAGED) warp_stage_close(sink, cur);
     if (lane == 0 && inserted) atomicAdd(f.inserted, inserted);
 }
 
@@ -290,10 +343,10 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
 #ifndef KBBQ_P2_MIN_BLOCKS
 #define KBBQ_P2_MIN_BLOCKS 4  // 64 registers, 32 warps/SM: 5.05 ms vs 6.61 unbounded (78 registers, 24 warps)
 #endif
-template <bool TEST_FIRST>
+template <int MODE>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P2_MIN_BLOCKS)
 pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, const int* __restrict__ thresholds,
-                     uint32_t* __restrict__ err_out) {
+                     uint32_t* __restrict__ err_out, StageSink sink) {
     __shared__ int thr[KBBQ_MAX_K + 1];
     __shared__ uint32_t Pm_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
     __shared__ uint32_t Em_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
@@ -306,6 +359,8 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
     uint32_t* Em = Em_all[wib];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
+    StageCursor cur{0, 0};
+    if (MODE == INS_STAGED) warp_stage_open(sink, cur);
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
         const int len = (int)b.len[r];
         const int nk = len - k + 1;
@@ -344,10 +399,12 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
             const int j = j0 + lane;
             uint64_t key = 0;
             const bool ins = j < nk && count_window32(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key);
-            inserted += warp_bloom_insert<TEST_FIRST>(trusted, ins, key, stage);
+            if (MODE == INS_STAGED) inserted += warp_stage_insert(trusted, sink, cur, ins, key);
+            else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(trusted, ins, key, stage);
         }
         __syncwarp();
     }
+    if (MODE == INS_STAGED) warp_stage_close(sink, cur);
     if (lane == 0 && inserted) atomicAdd(trusted.inserted, inserted);
 }
 
@@ -694,6 +751,25 @@ pass4_apply_kernel(BatchView b, ModelView mv, uint8_t* __restrict__ out) {
         p4_apply(mv, h0, d0, 8 * lane, out);
         for (int i0 = 256 + 8 * lane; i0 < h0.len; i0 += 256) p4_apply(mv, h0, p4_data(b, h0, i0), i0, out);  // reads > 256 bases
         h0 = h1; h1 = h2; d0 = d1;
+    }
+}
+
+// ---- applying a sorted staging array (INS_STAGED): four lanes per item, items in block order -----------------------
+__global__ void __launch_bounds__(256) bloom_insert_sorted_kernel(BloomView f, const unsigned long long* __restrict__ items,
+                                                                  unsigned long long n) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = ((unsigned long long)gridDim.x * blockDim.x) >> 2;
+    const int sub = (int)(threadIdx.x & 3);
+    for (unsigned long long i = t >> 2; i < n; i += stride) {
+        const unsigned long long it = __ldg(items + i);
+        if (it == KBBQ_STAGE_SENTINEL) continue;
+        ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(f.patterns + (it & 0xFFFFull) * 8) + sub);
+        unsigned long long* B = f.words + (it >> 16) * 8 + 2 * sub;
+        const ulonglong2 have = __ldcg(reinterpret_cast<const ulonglong2*>(B));
+        p.x &= ~have.x;
+        p.y &= ~have.y;
+        if (p.x) atomicOr(B, p.x);
+        if (p.y) atomicOr(B + 1, p.y);
     }
 }
 

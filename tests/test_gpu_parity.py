@@ -284,3 +284,14 @@ def test_human_scale_filters_address_every_block():
                 nz += int(np.unpackbits(nzw.cpu().numpy().view(np.uint8)).sum())
         assert nz == total
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_insert_modes_for_large_filters_give_the_same_bits(mode, monkeypatch):
+    """Filters larger than the L2 are filled through other code paths (kbbq_kernels.cuh INS_TEST_FIRST: read before OR;
+    INS_STAGED: stage (block, pattern), radix-sort by block range, apply): forced here on a small input, every
+    intermediate and the filters' words must still equal the oracle's."""
+    monkeypatch.setenv("KBBQ_INSERT_MODE", mode)
+    G, cov, L, k = 80000, 30, 150, 32
+    rs = synth.make_reads(G, cov, L, seed=61, n_rg=2, n_frac=0.002, ragged=True, min_len=40)
+    common.compare(common.run_gpu(rs, k, G, cov, 2024, n_batches=2), common.run_port(rs, k, G, cov, 2024))
