@@ -7,6 +7,7 @@ import collections
 import csv
 import json
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -43,8 +44,8 @@ with open(os.path.join(ROOT, "profiles", tag + "_kernels.csv"), "w", newline="")
     w = csv.writer(fh)
     w.writerow([n + (" [" + units[i] + "]" if units[i] else "") for i, n in idx])
     for r in rows[2:]:
-        w.writerow([r[i].split("(")[0] if n == "kernel" else r[i] for i, n in idx])
-        name = r[hdr.index("Kernel Name")].split("(")[0].replace("kbbq::", "")
+        w.writerow([r[i].split("(")[0].replace("void ", "") if n == "kernel" else r[i] for i, n in idx])
+        name = re.sub(r"<.*", "", r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("kbbq::", ""))
         rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         traffic[name] = float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
