@@ -69,6 +69,12 @@ typedef struct kbbq_batch {
     const uint32_t* len;      /* [n_reads] */
     const uint16_t* rg;       /* [n_reads] dense read-group id, CReadData::get_rg_int() (readutils.hh:62) */
     const uint8_t* second;    /* [n_reads] CReadData::second */
+    /* optional, may be NULL: [2*n_words] per word w, qmask[2w] = bit i set when qual[32w+i] <= 2 (INFER_ERROR_BAD_QUAL,
+     * readutils.hh:16) and qmask[2w+1] = bit i set when qual[32w+i] <= 6 (get_errors' minqual, readutils.cc:238);
+     * kbbq_quality_masks makes them.  They are all pass 2 needs of the qualities, so a batch that brings them lets pass 2
+     * start before the quality array itself has arrived (kbbq_batch_upload_async); without them the library derives
+     * them on the device from `qual`. */
+    const uint32_t* qmask;
 } kbbq_batch;
 
 const char* kbbq_last_error(void);
@@ -103,6 +109,8 @@ int kbbq_fit_model_host(int n_rg, int max_cycle, const uint64_t* rgc, const uint
 int kbbq_pack_size(uint64_t n, const uint64_t* off, uint64_t* n_words, uint32_t* max_len);
 int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint8_t* qual, uint64_t* bases,
                     uint32_t* nmask, uint8_t* qual_out, uint32_t* word_off, uint32_t* len, int n_threads);
+/* kbbq_batch::qmask from a packed quality array: qmask[2*n_words] from qual[32*n_words] */
+int kbbq_quality_masks(uint64_t n_words, const uint8_t* qual, uint32_t* qmask, int n_threads);
 
 /* ---- context ---------------------------------------------------------------------------------------------------- */
 int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out);

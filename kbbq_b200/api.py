@@ -38,7 +38,7 @@ class _Batch(C.Structure):
     _fields_ = [
         ("n_reads", C.c_uint32), ("max_len", C.c_uint32), ("n_words", C.c_uint64), ("bases", C.c_void_p),
         ("nmask", C.c_void_p), ("qual", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
-        ("rg", C.c_void_p), ("second", C.c_void_p),
+        ("rg", C.c_void_p), ("second", C.c_void_p), ("qmask", C.c_void_p),
     ]
 
 
@@ -70,6 +70,7 @@ def lib():
         L.kbbq_fit_model_host.argtypes = [i32, i32] + [vp] * 9
         L.kbbq_pack_size.argtypes = [u64, vp, C.POINTER(u64), C.POINTER(u32)]
         L.kbbq_pack_reads.argtypes = [u64] + [vp] * 8 + [i32]
+        L.kbbq_quality_masks.argtypes = [u64, vp, vp, i32]
         L.kbbq_ctx_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
         L.kbbq_ctx_destroy.argtypes = [vp]
         L.kbbq_sync.argtypes = [vp]
@@ -174,7 +175,7 @@ def fit_model_host(rgc, qc, cyc, dic):
 class PackedBatch:
     """Host-side packed read batch (the kbbq_batch layout)."""
 
-    def __init__(self, rs, n_threads: int = 8, pinned: bool = False):
+    def __init__(self, rs, n_threads: int = 8, pinned: bool = False, qmask: bool = True):
         n = rs.n
         nw = C.c_uint64(0)
         ml = C.c_uint32(0)
@@ -195,25 +196,36 @@ class PackedBatch:
         self.bases = alloc(max(self.n_words, 1), np.uint64)
         self.nmask = alloc(max(self.n_words, 1), np.uint32)
         self.qual = alloc(max(self.n_words, 1) * 32, np.uint8)
-        self.word_off = np.zeros(n + 1, dtype=np.uint32)
-        self.len = np.zeros(max(n, 1), dtype=np.uint32)
-        self.rg = np.ascontiguousarray(rs.rg, dtype=np.uint16) if n else np.zeros(1, dtype=np.uint16)
-        self.second = np.ascontiguousarray(rs.second, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
+        # the per-read arrays are pinned too: a pageable source turns cudaMemcpyAsync into a staged, blocking copy
+        self.word_off = alloc(n + 1, np.uint32)
+        self.len = alloc(max(n, 1), np.uint32)
+        self.rg = alloc(max(n, 1), np.uint16)
+        self.second = alloc(max(n, 1), np.uint8)
+        if n:
+            self.rg[:] = rs.rg
+            self.second[:] = rs.second
         seq = np.ascontiguousarray(rs.seq, dtype=np.uint8)
         qual = np.ascontiguousarray(rs.qual, dtype=np.uint8)
         _check(lib().kbbq_pack_reads(n, _p(seq), _p(off), _p(qual), _p(self.bases), _p(self.nmask), _p(self.qual),
                                      _p(self.word_off), _p(self.len), n_threads))
+        # qual <= 2 / qual <= 6 bit masks: with them pass 2 does not wait for the quality array (qmask=False: the
+        # library derives them on the device)
+        self.qmask = None
+        if qmask and not os.environ.get("KBBQ_NO_HOST_QMASK"):  # (the variable: tests of the device-derived masks)
+            self.qmask = alloc(max(self.n_words, 1) * 2, np.uint32)
+            _check(lib().kbbq_quality_masks(self.n_words, _p(self.qual), _p(self.qmask), n_threads))
 
     def as_struct(self) -> _Batch:
         b = _Batch()
         b.n_reads, b.max_len, b.n_words = self.n_reads, self.max_len, self.n_words
         b.bases, b.nmask, b.qual = _p(self.bases), _p(self.nmask), _p(self.qual)
         b.word_off, b.len, b.rg, b.second = _p(self.word_off), _p(self.len), _p(self.rg), _p(self.second)
+        b.qmask = _p(self.qmask)
         return b
 
     @property
     def h2d_bytes(self) -> int:
-        return self.n_words * (8 + 4 + 32) + (self.n_reads + 1) * 4 + self.n_reads * (4 + 2 + 1)
+        return self.n_words * (8 + 4 + 32 + (8 if self.qmask is not None else 0)) + (self.n_reads + 1) * 4 + self.n_reads * (4 + 2 + 1)
 
     def unpack_bits(self, bits: np.ndarray, total_bases: int) -> np.ndarray:
         """bit masks in word layout -> one byte per base, reads concatenated (the oracle's layout)."""

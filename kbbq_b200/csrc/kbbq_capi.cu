@@ -135,6 +135,8 @@ struct kbbq_dbatch {
     unsigned long long* d_bases = nullptr;
     uint32_t* d_nmask = nullptr;
     uint8_t* d_qual = nullptr;
+    uint2* d_qmask = nullptr;        // per word: qual <= 2 / qual <= 6 bit masks
+    bool qmask_needs_quals = false;  // derived on the device from d_qual (the host brought none): ready with qual_ready
     uint32_t* d_word_off = nullptr;
     uint32_t* d_len = nullptr;
     uint16_t* d_rg = nullptr;
@@ -151,6 +153,7 @@ struct kbbq_dbatch {
         v.bases = d_bases;
         v.nmask = d_nmask;
         v.qual = d_qual;
+        v.qmask = d_qmask;
         v.word_off = d_word_off;
         v.len = d_len;
         v.rg = d_rg;
@@ -469,6 +472,34 @@ int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint
     return KBBQ_OK;
 }
 
+int kbbq_quality_masks(uint64_t n_words, const uint8_t* qual, uint32_t* qmask, int n_threads) {
+    if (n_words && (!qual || !qmask)) return fail(KBBQ_EINVAL, "null argument");
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t w = lo; w < hi; ++w) {
+            const uint8_t* q = qual + w * 32;
+            uint32_t m2 = 0, m6 = 0;
+            for (int i = 0; i < 32; ++i) {
+                m2 |= (uint32_t)(q[i] <= 2) << i;
+                m6 |= (uint32_t)(q[i] <= 6) << i;
+            }
+            qmask[2 * w] = m2;
+            qmask[2 * w + 1] = m6;
+        }
+    };
+    if (n_threads <= 1 || n_words < (1u << 16)) {
+        work(0, n_words);
+    } else {
+        std::vector<std::thread> th;
+        const uint64_t per = (n_words + n_threads - 1) / n_threads;
+        for (int t = 0; t < n_threads; ++t) {
+            const uint64_t lo = std::min<uint64_t>(n_words, (uint64_t)t * per), hi = std::min<uint64_t>(n_words, lo + per);
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto& t : th) t.join();
+    }
+    return KBBQ_OK;
+}
+
 // ---- context -------------------------------------------------------------------------------------------------------
 int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) {
     if (!out) return fail(KBBQ_EINVAL, "null output");
@@ -775,7 +806,7 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (!b) return;
     if (ctx) cudaSetDevice(ctx->device);
     cudaStream_t st = ctx ? ctx->stream : nullptr;
-    void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
+    void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_qmask, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
                     b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual};
     if (b->qual_ready) {
         if (ctx && !b->qual_waited) cudaStreamWaitEvent(st, b->qual_ready, 0);  // d_qual is freed in `st`'s order
@@ -797,24 +828,9 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
     if (h->max_len > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
     if ((int)h->max_len > ctx->max_cycle) return fail(KBBQ_ERANGE, "read longer than the context's max_cycle");
     const uint32_t n = h->n_reads;
-    // validation and the slot total in tight host loops; the per-read prefix (slot_off) is made on the device
-    unsigned long long slots = 0;
-    {
-        uint32_t longest = 0, biggest_rg = 0;
-        const uint32_t km1 = (uint32_t)ctx->k - 1;
-        for (uint32_t r = 0; r < n; ++r) {
-            const uint32_t l = h->len[r];
-            longest = std::max(longest, l);
-            slots += l > km1 ? l - km1 : 0;
-        }
-        if (h->rg)
-            for (uint32_t r = 0; r < n; ++r) biggest_rg = std::max<uint32_t>(biggest_rg, h->rg[r]);
-        if (longest > h->max_len) return fail(KBBQ_ERANGE, "len[r] exceeds max_len");
-        if (n && biggest_rg >= (uint32_t)ctx->n_rg) return fail(KBBQ_ERANGE, "read group id >= n_rg");
-    }
     kbbq_dbatch* b = new (std::nothrow) kbbq_dbatch();
     if (!b) return fail(KBBQ_ENOMEM, "out of host memory");
-    b->n_reads = n; b->max_len = h->max_len; b->n_words = h->n_words; b->n_slots = slots; b->k = ctx->k;
+    b->n_reads = n; b->max_len = h->max_len; b->n_words = h->n_words; b->k = ctx->k;
     const size_t nw = std::max<uint64_t>(h->n_words, 1);
 #define UP(dst, src, bytes)                                                                   \
     do {                                                                                      \
@@ -836,6 +852,8 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
         CU(cudaMemcpyAsync(b->d_bases, h->bases, h->n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(b->d_nmask, h->nmask, h->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (h->qmask) UP(b->d_qmask, h->qmask, (size_t)h->n_words * 8);  // early: all pass 2 needs of the qualities
+    else UP(b->d_qmask, (const void*)nullptr, (size_t)h->n_words * 8);
     UP(b->d_word_off, h->word_off, ((size_t)n + 1) * 4);
     UP(b->d_len, h->len, (size_t)n * 4);
     UP(b->d_rg, h->rg, (size_t)n * 2);
@@ -859,6 +877,12 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
         if (e2 == cudaSuccess && !h->n_words) e2 = cudaMemsetAsync(b->d_qual, 0, qbytes, ctx->copy_stream);
         if (e2 == cudaSuccess && h->n_words)
             e2 = cudaMemcpyAsync(b->d_qual, h->qual, (size_t)h->n_words * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e2 == cudaSuccess && !h->qmask && h->n_words) {  // no masks from the host: derive them where the qualities land
+            qual_masks_kernel<<<(unsigned)((h->n_words * 32 + 255) / 256), 256, 0, ctx->copy_stream>>>(b->d_qual, h->n_words, b->d_qmask);
+            e2 = cudaGetLastError();
+            ++ctx->launches;
+            b->qmask_needs_quals = true;
+        }
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&b->qual_ready, cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaEventRecord(b->qual_ready, ctx->copy_stream);
         if (alloc_done) cudaEventDestroy(alloc_done);
@@ -867,6 +891,29 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
             return fail(e2 == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA, std::string("batch upload: ") + cudaGetErrorString(e2));
         }
         b->qual_waited = false;
+    }
+    // validation and the slot total in tight host loops, while the copies above are in flight (the per-read prefix,
+    // slot_off, is made on the device)
+    {
+        unsigned long long slots = 0;
+        uint32_t longest = 0, biggest_rg = 0;
+        const uint32_t km1 = (uint32_t)ctx->k - 1;
+        for (uint32_t r = 0; r < n; ++r) {
+            const uint32_t l = h->len[r];
+            longest = std::max(longest, l);
+            slots += l > km1 ? l - km1 : 0;
+        }
+        if (h->rg)
+            for (uint32_t r = 0; r < n; ++r) biggest_rg = std::max<uint32_t>(biggest_rg, h->rg[r]);
+        b->n_slots = slots;
+        const char* bad = longest > h->max_len ? "len[r] exceeds max_len"
+                          : (n && biggest_rg >= (uint32_t)ctx->n_rg) ? "read group id >= n_rg" : nullptr;
+        if (bad) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->copy_stream);
+            kbbq_batch_free(ctx, b);
+            return fail(KBBQ_ERANGE, bad);
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));  // the caller may reuse everything but h->qual
     if (!async_qual) CU(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse h->qual
@@ -1005,7 +1052,8 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     }
     if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
-    if (int rc = need_quals(ctx, b)) return rc;
+    if (b->qmask_needs_quals)  // pass 2 reads the quality MASKS only; they are already there when the host brought them
+        if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {
         mark_kernel(ctx, "pass2_trusted_kernel");

@@ -17,6 +17,7 @@ struct BatchView {
     const unsigned long long* bases;
     const uint32_t* nmask;
     const uint8_t* qual;
+    const uint2* qmask;  // per word: .x = bases with qual <= 2, .y = bases with qual <= 6 (kbbq_batch::qmask)
     const uint32_t* word_off;
     const uint32_t* len;
     const uint16_t* rg;
@@ -245,6 +246,15 @@ __device__ __forceinline__ int warp_bloom_insert(const BloomView& f, bool ins, u
     return n;
 }
 
+// ---- batch set-up: quality masks from the quality bytes when the host did not bring them (one warp per word) ---------
+__global__ void qual_masks_kernel(const uint8_t* __restrict__ qual, unsigned long long n_words, uint2* __restrict__ out) {
+    const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_words) return;
+    const uint8_t q = qual[w * 32 + (threadIdx.x & 31)];
+    const uint32_t m2 = __ballot_sync(KBBQ_FULL, q <= 2), m6 = __ballot_sync(KBBQ_FULL, q <= 6);
+    if ((threadIdx.x & 31) == 0) out[w] = make_uint2(m2, m6);
+}
+
 // ---- batch set-up: k-mer slots per read (max(0, len-k+1)) and a trailing 0, scanned in place into slot_off ---------
 __global__ void slot_counts_kernel(const uint32_t* __restrict__ len, uint32_t n, int k, unsigned long long* __restrict__ out) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,7 +377,6 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         if (nk <= 0) continue;  // out of contract in the reference (bloom.cc:30 underflows)
         const uint32_t wo = b.word_off[r];
         const CSeqRef s{b.bases + wo, b.nmask + wo, len};
-        const uint8_t* q = b.qual + (size_t)wo * 32;
         // kmer_present (bloom.cc:35-47)
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
@@ -385,7 +394,7 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
                 const int lo = i - k + 1 > 0 ? i - k + 1 : 0;
                 const int hi = (i < nk - 1 ? i : nk - 1) + 1;
                 const int in = count_window32(Pm, lo, hi);
-                e = in <= thr[hi - lo] || q[i] <= 2;
+                e = in <= thr[hi - lo] || ((b.qmask[wo + (i0 >> 5)].x >> lane) & 1u);  // qual[i] <= 2
             }
             const uint32_t m = __ballot_sync(KBBQ_FULL, e);
             if (lane == 0) {
@@ -654,11 +663,9 @@ pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict_
             sc.P_w[lane] = lane < nw ? b.bases[wo + lane] : 0ull;
             sc.P_nm[lane] = lane < nw ? b.nmask[wo + lane] : 0u;
             sc.E[lane] = 0;
-        }
-        for (int i0 = 0; i0 <= len; i0 += 32) {  // low-quality flags for the overcorrection half weight
-            const int i = i0 + lane;
-            const uint32_t m = __ballot_sync(KBBQ_FULL, i < len && qual[i] <= 6);
-            if (lane == 0) sc.QL[i0 >> 5] = m;
+            // low-quality flags for the overcorrection half weight (bits past the read's end cleared)
+            const int left = len - 32 * lane;
+            sc.QL[lane] = lane < nw ? b.qmask[wo + lane].y & (left >= 32 ? ~0u : ((1u << left) - 1u)) : 0u;
         }
         __syncwarp();
         const bool has_n = __any_sync(KBBQ_FULL, lane < nw && sc.P_nm[lane] != 0u);

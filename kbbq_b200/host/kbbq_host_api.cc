@@ -68,6 +68,7 @@ void Session::ensure_resident(const ReadStore& rs) {
         hb.n_reads = (uint32_t)m; hb.max_len = ml; hb.n_words = nw;
         hb.bases = bases.data(); hb.nmask = nmask.data(); hb.qual = qual.data(); hb.word_off = word_off.data();
         hb.len = len.data(); hb.rg = rs.rg.data() + lo; hb.second = rs.second.data() + lo;
+        hb.qmask = nullptr;  // derived on the device: this upload is synchronous anyway
         kbbq_dbatch* db = nullptr;
         CK(kbbq_batch_upload(ctx_, &hb, &db));
         batches_.push_back(db);

@@ -295,3 +295,34 @@ def test_insert_modes_for_large_filters_give_the_same_bits(mode, monkeypatch):
     G, cov, L, k = 80000, 30, 150, 32
     rs = synth.make_reads(G, cov, L, seed=61, n_rg=2, n_frac=0.002, ragged=True, min_len=40)
     common.compare(common.run_gpu(rs, k, G, cov, 2024, n_batches=2), common.run_port(rs, k, G, cov, 2024))
+
+
+def test_quality_masks_derived_on_the_device(monkeypatch):
+    """kbbq_batch::qmask is optional: without it the library derives the qual <= 2 / qual <= 6 masks from the quality
+    array on the device (qual_masks_kernel) and pass 2 waits for the qualities."""
+    monkeypatch.setenv("KBBQ_NO_HOST_QMASK", "1")
+    G, cov, L, k = 60000, 25, 100, 32
+    rs = synth.make_reads(G, cov, L, seed=71, n_rg=2, ragged=True, min_len=50)
+    assert api.PackedBatch(rs).qmask is None
+    common.compare(common.run_gpu(rs, k, G, cov, 5150, n_batches=2), common.run_port(rs, k, G, cov, 5150))
+
+
+def test_upload_rejects_out_of_range_metadata():
+    """KBBQ_ERANGE for a read group id the context has no tables for and for a read longer than the batch claims; the
+    failed upload leaves the context usable."""
+    rs = synth.make_reads(20000, 10, 100, seed=4, n_rg=2)
+    ctx = api.Context(32, 1, 100)             # tables for ONE read group
+    with pytest.raises(api.KbbqError) as e:
+        ctx.upload(api.PackedBatch(rs))
+    assert e.value.code == -5 and "read group" in str(e.value)
+    pb = api.PackedBatch(rs)
+    pb.rg[:] = 0
+    pb.max_len = 50                            # the reads are 100 long
+    with pytest.raises(api.KbbqError) as e:
+        ctx.upload(pb)
+    assert e.value.code == -5
+    pb.max_len = 100
+    db = ctx.upload(pb)
+    assert db.slots == rs.n * (100 - 32 + 1)
+    db.free()
+    ctx.close()
