@@ -146,6 +146,12 @@ void* kbbq_bloom_device_counter(kbbq_ctx* ctx, int which);
 /* words |= other (other: device pointer to an equally sized bit array, e.g. a peer GPU's mapped filter) */
 int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other_device_words, uint64_t first_word, uint64_t n_words);
 
+/* Save / restore a filter (parameters, insert counter, bit array laid out as the reference's bit_table_): checkpoint
+ * between passes, fixtures across runs.  kbbq_bloom_load (re)creates filter `which` from the file's parameters.
+ * The reference never serialises its filters. */
+int kbbq_bloom_save(kbbq_ctx* ctx, int which, const char* path);
+int kbbq_bloom_load(kbbq_ctx* ctx, int which, const char* path);
+
 /* The whole multi-GPU merge of a filter's bit array in one kernel over peer-mapped memory (one process per GPU, all
  * on one NVLink/NVSwitch box): rank r ORs slice r of every rank's array and writes the result into every rank's array.
  *   1. every rank:  kbbq_bloom_ipc_handle -> 64 bytes; all-gather them (any transport) into handles[world][64]

@@ -94,6 +94,8 @@ def lib():
         L.kbbq_bloom_device_counter.restype = vp
         L.kbbq_bloom_device_counter.argtypes = [vp, i32]
         L.kbbq_bloom_or_from.argtypes = [vp, i32, vp, u64, u64]
+        L.kbbq_bloom_save.argtypes = [vp, i32, C.c_char_p]
+        L.kbbq_bloom_load.argtypes = [vp, i32, C.c_char_p]
         L.kbbq_bloom_ipc_handle.argtypes = [vp, i32, vp]
         L.kbbq_bloom_or_allreduce_p2p.argtypes = [vp, i32, i32, i32, vp]
         L.kbbq_batch_upload.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
@@ -367,6 +369,12 @@ class Context:
 
     def bloom_or_from(self, which: int, other_ptr: int, first_word: int, n_words: int):
         _check(self.L.kbbq_bloom_or_from(self.h, which, C.c_void_p(other_ptr), first_word, n_words))
+
+    def bloom_save(self, which: int, path: str):
+        _check(self.L.kbbq_bloom_save(self.h, which, os.fsencode(path)))
+
+    def bloom_load(self, which: int, path: str):
+        _check(self.L.kbbq_bloom_load(self.h, which, os.fsencode(path)))
 
     def bloom_ipc_handle(self, which: int) -> np.ndarray:
         h = np.zeros(64, dtype=np.uint8)

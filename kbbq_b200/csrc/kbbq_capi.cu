@@ -744,6 +744,75 @@ int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other, uint64_t fir
     return check_launch(ctx, "or_words_kernel");
 }
 
+// ---- filter (de)serialisation: checkpointing a pass, cross-run fixtures --------------------------------------------
+// File: "KBBQBF1\0", the kbbq_bloom_geom the filter was created with, the insert counter, then the bit array exactly
+// as the reference's bit_table_ (bloom.hh:33) lays it out.
+int kbbq_bloom_save(kbbq_ctx* ctx, int which, const char* path) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    if (!path) return fail(KBBQ_EINVAL, "null path");
+    Filter& f = ctx->filt[which];
+    FILE* fh = fopen(path, "wb");
+    if (!fh) return fail(KBBQ_EINVAL, std::string("cannot open ") + path);
+    kbbq_bloom_geom g;
+    geom_to_c(f.geom, &g);
+    uint64_t inserted = 0;
+    bool ok = fwrite("KBBQBF1", 1, 8, fh) == 8 && fwrite(&g, sizeof g, 1, fh) == 1;
+    cudaError_t e = cudaMemcpyAsync(&inserted, f.d_inserted, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ok = ok && e == cudaSuccess && fwrite(&inserted, 8, 1, fh) == 1;
+    const size_t total = f.geom.table_bits / 8, chunk = (size_t)64 << 20;
+    std::vector<unsigned char> buf(std::min(total, chunk));
+    for (size_t off = 0; ok && off < total; off += chunk) {  // 64 MiB at a time: the human-scale filters are tens of GB
+        const size_t n = std::min(chunk, total - off);
+        e = cudaMemcpyAsync(buf.data(), (const unsigned char*)f.d_words + off, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        ok = e == cudaSuccess && fwrite(buf.data(), 1, n, fh) == n;
+    }
+    ok = (fclose(fh) == 0) && ok;
+    if (!ok) return fail(e != cudaSuccess ? KBBQ_ECUDA : KBBQ_EINVAL, std::string("writing ") + path + " failed");
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_load(kbbq_ctx* ctx, int which, const char* path) {
+    if (int rc = use(ctx)) return rc;
+    if (which != 0 && which != 1) return fail(KBBQ_EINVAL, "filter id must be 0 or 1");
+    if (!path) return fail(KBBQ_EINVAL, "null path");
+    FILE* fh = fopen(path, "rb");
+    if (!fh) return fail(KBBQ_EINVAL, std::string("cannot open ") + path);
+    char magic[8];
+    kbbq_bloom_geom g;
+    uint64_t inserted = 0;
+    if (fread(magic, 1, 8, fh) != 8 || std::memcmp(magic, "KBBQBF1", 8) != 0 || fread(&g, sizeof g, 1, fh) != 1 ||
+        fread(&inserted, 8, 1, fh) != 1) {
+        fclose(fh);
+        return fail(KBBQ_EINVAL, std::string(path) + " is not a kbbq_b200 filter file");
+    }
+    if (int rc = kbbq_bloom_create(ctx, which, g.projected, g.fpr, g.seed)) { fclose(fh); return rc; }
+    Filter& f = ctx->filt[which];
+    if (f.geom.table_bits != g.table_bits || f.geom.n_blocks != g.n_blocks || f.geom.n_salts != g.n_salts ||
+        std::memcmp(f.geom.salts, g.salts, sizeof(uint32_t) * g.n_salts) != 0) {
+        fclose(fh);
+        return fail(KBBQ_EINVAL, "the file's filter geometry is not what its parameters give on this build");
+    }
+    const size_t total = f.geom.table_bits / 8, chunk = (size_t)64 << 20;
+    std::vector<unsigned char> buf(std::min(total, chunk));
+    bool ok = true;
+    cudaError_t e = cudaSuccess;
+    for (size_t off = 0; ok && off < total; off += chunk) {
+        const size_t n = std::min(chunk, total - off);
+        ok = fread(buf.data(), 1, n, fh) == n;
+        if (ok) e = cudaMemcpyAsync((unsigned char*)f.d_words + off, buf.data(), n, cudaMemcpyHostToDevice, ctx->stream);
+        if (ok && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        ok = ok && e == cudaSuccess;
+    }
+    fclose(fh);
+    if (ok) e = cudaMemcpyAsync(f.d_inserted, &inserted, 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (ok && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (!ok || e != cudaSuccess) return fail(e != cudaSuccess ? KBBQ_ECUDA : KBBQ_EINVAL, std::string("reading ") + path + " failed");
+    return KBBQ_OK;
+}
+
 int kbbq_bloom_ipc_handle(kbbq_ctx* ctx, int which, void* handle64) {
     if (int rc = use(ctx)) return rc;
     if (int rc = filter_ok(ctx, which)) return rc;

@@ -1,5 +1,8 @@
 """Parity tests proper: the sm_100a kernels, called through the C ABI, against the oracle and the golden fixtures.
 Bit-exact everywhere: Bloom bit arrays, insert counters, error flags, covariate tables, model tables, new qualities."""
+import ctypes
+import os
+
 import numpy as np
 import pytest
 
@@ -348,3 +351,38 @@ def test_randomised_shapes_match_port(case):
     seed = int(rng.integers(1, 2**32))
     common.compare(common.run_gpu(rs, k, G, cov, seed, n_batches=int(rng.integers(1, 4))), common.run_port(rs, k, G, cov, seed),
                    what=f"case {case} k={k} L={L} cov={cov} {kw}: ")
+
+
+def test_filter_save_and_load_round_trip(tmp_path):
+    """kbbq_bloom_save / kbbq_bloom_load: a filter built by pass 1 survives the file and serves pass 2 in a new context
+    exactly as the original does (same words, counter, false-positive rate, thresholds, trusted filter)."""
+    G, cov, L, k, seed = 50000, 20, 100, 32, 77
+    rs = synth.make_reads(G, cov, L, seed=13, n_frac=0.001)
+    want = common.run_port(rs, k, G, cov, seed)
+    alpha = np.longdouble(7) / np.longdouble(cov)
+    approx = int(np.longdouble(G) * cov * alpha)
+    a = api.Context(k, 1, L)
+    a.bloom_create(api.FILTER_SAMPLED, approx, 0.01)
+    da = a.upload(api.PackedBatch(rs))
+    a.sampler_seed(seed, float(alpha))
+    a.pass1(da)
+    path = str(tmp_path / "sampled.kbf")
+    a.bloom_save(api.FILTER_SAMPLED, path)
+    assert os.path.getsize(path) == 8 + ctypes.sizeof(api.BloomGeom) + 8 + a.bloom_info(0).table_bits // 8
+    da.free()
+    a.close()
+    b = api.Context(k, 1, L)
+    b.bloom_load(api.FILTER_SAMPLED, path)
+    assert np.array_equal(b.bloom_words(0), want["sampled_words"]) and b.bloom_inserted(0) == want["sampled_inserted"]
+    assert b.bloom_fprate(0) == want["sampled_fpr"]
+    b.bloom_create(api.FILTER_TRUSTED, approx, 0.0005)
+    db = b.upload(api.PackedBatch(rs))
+    assert np.array_equal(b.compute_thresholds(alpha), want["thresholds"])
+    b.pass2(db)
+    assert np.array_equal(b.bloom_words(1), want["trusted_words"]) and b.bloom_inserted(1) == want["trusted_inserted"]
+    with open(path, "r+b") as fh:
+        fh.write(b"NOTAKBBQ")
+    with pytest.raises(api.KbbqError):
+        b.bloom_load(api.FILTER_SAMPLED, path)
+    db.free()
+    b.close()
