@@ -83,6 +83,7 @@ struct kbbq_ctx {
     cudaStream_t copy_stream = nullptr;  // side stream: quality arrays travel while pass 1 runs on `stream`
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evk[KBBQ_MAX_PASS_KERNELS + 1] = {};  // marks around the kernels of the most recent pass
+    cudaEvent_t evp[4] = {};                          // pass 4: piece i computed
     const char* kname[KBBQ_MAX_PASS_KERNELS] = {};
     int n_marks = 0;
     bool timed = false;
@@ -146,6 +147,9 @@ struct kbbq_dbatch {
     uint32_t* d_err_bits = nullptr;
     uint32_t* d_mod = nullptr;  // per read: the base get_errors left modified, or 0xFFFFFFFF (see covariate_count_kernel)
     uint8_t* d_newqual = nullptr;
+    // pass 4 hands its output to the host in KBBQ_P4_PARTS pieces, each copied while the next is computed
+    uint32_t part_read[5] = {0, 0, 0, 0, 0};   // read boundaries of the pieces
+    uint64_t part_word[5] = {0, 0, 0, 0, 0};   // ... and their word offsets (from the host's word_off at upload)
     cudaEvent_t qual_ready = nullptr;  // recorded on the copy stream after d_qual's upload
     bool qual_waited = true;           // false until `stream` has been made to wait for qual_ready
     BatchView view() const {
@@ -533,6 +537,7 @@ int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) 
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     for (auto& e : c->evk) CU(cudaEventCreate(&e));
+    for (auto& e : c->evp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->n_rgc = (size_t)n_rg * 2;
     c->n_qc = (size_t)n_rg * KBBQ_NQ * 2;
     c->n_cyc = (size_t)n_rg * KBBQ_NQ * 2 * max_cycle * 2;
@@ -569,6 +574,7 @@ void kbbq_ctx_destroy(kbbq_ctx* c) {
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     for (auto& e : c->evk) cudaEventDestroy(e);
+    for (auto& e : c->evp) cudaEventDestroy(e);
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
@@ -900,6 +906,10 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
     kbbq_dbatch* b = new (std::nothrow) kbbq_dbatch();
     if (!b) return fail(KBBQ_ENOMEM, "out of host memory");
     b->n_reads = n; b->max_len = h->max_len; b->n_words = h->n_words; b->k = ctx->k;
+    for (int i = 0; i <= 4; ++i) {
+        b->part_read[i] = (uint32_t)((uint64_t)n * i / 4);
+        b->part_word[i] = n ? h->word_off[b->part_read[i]] : 0;
+    }
     const size_t nw = std::max<uint64_t>(h->n_words, 1);
 #define UP(dst, src, bytes)                                                                   \
     do {                                                                                      \
@@ -1270,14 +1280,36 @@ int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_o
     }
     if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
+    const bool fetch = qual_out && b->n_words;
     if (b->n_reads) {
         mark_kernel(ctx, "pass4_apply_kernel");
         ModelView mv{ctx->d_base, ctx->d_cy, ctx->d_di, ctx->max_cycle};
-        pass4_apply_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), mv, b->d_newqual);
-        if (int rc = check_launch(ctx, "pass4_apply_kernel")) return rc;
+        // with a host destination the batch goes in four pieces: piece i travels on the copy stream while piece i+1 is
+        // looked up (the D2H copy is 5x the kernel, so this hides the kernel, not the copy)
+        const int parts = fetch && b->n_reads >= (1u << 16) ? 4 : 1;
+        for (int i = 0; i < parts; ++i) {
+            const uint32_t r0 = parts == 1 ? 0 : b->part_read[i], r1 = parts == 1 ? b->n_reads : b->part_read[i + 1];
+            if (r1 > r0) {
+                pass4_apply_kernel<<<read_grid(ctx, r1 - r0), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), mv, b->d_newqual, r0, r1);
+                if (int rc = check_launch(ctx, "pass4_apply_kernel")) return rc;
+            }
+            if (parts > 1) {
+                const uint64_t w0 = b->part_word[i], w1 = b->part_word[i + 1];
+                CU(cudaEventRecord(ctx->evp[i], ctx->stream));
+                CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->evp[i], 0));
+                if (w1 > w0)
+                    CU(cudaMemcpyAsync(qual_out + w0 * 32, b->d_newqual + w0 * 32, (size_t)(w1 - w0) * 32, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
+        }
+        pass_end(ctx);
+        if (parts > 1) {
+            CU(cudaStreamSynchronize(ctx->copy_stream));
+            return KBBQ_OK;
+        }
+    } else {
+        pass_end(ctx);
     }
-    pass_end(ctx);
-    if (qual_out && b->n_words) {
+    if (fetch) {
         CU(cudaMemcpyAsync(qual_out, b->d_newqual, (size_t)b->n_words * 32, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }

@@ -745,9 +745,11 @@ __device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Head& h, c
     *reinterpret_cast<uint2*>(out + (size_t)h.wo * 32 + i0) = make_uint2(res[0], res[1]);
 }
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32)
-pass4_apply_kernel(BatchView b, ModelView mv, uint8_t* __restrict__ out) {
+pass4_apply_kernel(BatchView b, ModelView mv, uint8_t* __restrict__ out, uint32_t first_read, uint32_t end_read) {
     const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = first_read + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    b.n_reads = end_read;  // the launch covers reads [first_read, end_read): p4_head yields empty reads past the end
     if (warp >= b.n_reads) return;
     P4Head h0 = p4_head(b, warp);
     P4Head h1 = p4_head(b, warp + nwarps);
