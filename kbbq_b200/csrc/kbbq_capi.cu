@@ -97,6 +97,7 @@ struct kbbq_ctx {
     unsigned long long sample_threshold = 0;  // draw x is sampled iff take_all or x < threshold (see kbbq_sampler_seed)
     int sample_all = 0;
     unsigned long long* d_jump = nullptr;  // 26 matrices: 2^(10+b) steps
+    unsigned long long* d_lane_jump = nullptr;  // 32 matrices: lane x 1024 steps
     // thresholds
     bool have_thresholds = false;
     int* d_thresholds = nullptr;
@@ -564,6 +565,7 @@ void kbbq_ctx_destroy(kbbq_ctx* c) {
         cudaFree(f.d_inserted);
     }
     cudaFree(c->d_jump);
+    cudaFree(c->d_lane_jump);
     cudaFree(c->d_thresholds);
     cudaFree(c->d_counts);
     cudaFree(c->d_base);
@@ -1036,6 +1038,18 @@ int kbbq_sampler_seed(kbbq_ctx* ctx, uint32_t seed, double alpha) {
         const host::JumpTables& jt = host::jump_tables();
         CU(cudaMalloc(&ctx->d_jump, (size_t)26 * 1024 * 8));
         CU(cudaMemcpyAsync(ctx->d_jump, jt.matrix(10), (size_t)26 * 1024 * 8, cudaMemcpyHostToDevice, ctx->stream));
+        // lane_jump[l] = (1024 steps)^l: column c of matrix l is column c of matrix l-1 advanced by 1024 steps
+        std::vector<uint64_t> lj((size_t)32 * 1024, 0);
+        for (int c = 0; c < 256; ++c) lj[(size_t)c * 4 + (c >> 6)] = 1ull << (c & 63);  // identity
+        for (int l = 1; l < 32; ++l)
+            for (int c = 0; c < 256; ++c) {
+                uint64_t v[4];
+                std::memcpy(v, &lj[((size_t)(l - 1) * 256 + c) * 4], 32);
+                host::rng_advance(v, 1024);
+                std::memcpy(&lj[((size_t)l * 256 + c) * 4], v, 32);
+            }
+        CU(cudaMalloc(&ctx->d_lane_jump, lj.size() * 8));
+        CU(cudaMemcpyAsync(ctx->d_lane_jump, lj.data(), lj.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return KBBQ_OK;
@@ -1061,7 +1075,7 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
         std::memcpy(rs, ctx->sampler_state0, 32);
         host::rng_advance(rs, ctx->sampler_pos);
         mark_kernel(ctx, "rng_sample_kernel");
-        rng_sample_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(rs[0], rs[1], rs[2], rs[3], ctx->d_jump,
+        rng_sample_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, ctx->stream>>>(rs[0], rs[1], rs[2], rs[3], ctx->d_jump, ctx->d_lane_jump,
                                                                                      b->n_slots, ctx->sample_threshold, ctx->sample_all, b->d_sample_bits);
         if (int rc = check_launch(ctx, "rng_sample_kernel")) return rc;
         mark_kernel(ctx, "pass1_insert_kernel");

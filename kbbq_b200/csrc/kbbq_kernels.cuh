@@ -269,17 +269,47 @@ __global__ void slot_counts_kernel(const uint32_t* __restrict__ len, uint32_t n,
 // (columns of 4 words; jump[b] = 2^(10+b) steps), then produces 1024 consecutive decisions as 32 mask words.
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
 
+// The jump is shared work: the 32 lanes of a warp own consecutive chunks, so they first advance the stream TOGETHER to
+// the warp's first chunk (one matrix-vector product per set high bit of the chunk index, 8 state bits per lane, XOR
+// reduced by shuffles: ~150 instructions instead of ~2000 per product), then every lane applies its own matrix of
+// lane x 1024 steps (`lane_jump`, 32 precomputed matrices) -- one product with uniform control flow, because all lanes
+// hold the same state at that point -- instead of up to five divergent ones.
 __global__ void __launch_bounds__(128) rng_sample_kernel(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3,
                                                          const unsigned long long* __restrict__ jump,
+                                                         const unsigned long long* __restrict__ lane_jump,
                                                          unsigned long long n_slots, unsigned long long threshold,
                                                          int take_all, uint32_t* __restrict__ bits) {
+    const int lane = threadIdx.x & 31;
     const unsigned long long chunk = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long first = chunk * 1024ull;
-    if (first >= n_slots) return;
+    const unsigned long long base = chunk - lane;  // the warp's first chunk
+    if (base * 1024ull >= n_slots) return;         // whole warp past the end
     uint64_t s[4] = {s0, s1, s2, s3};
-    for (int b = 0; (chunk >> b) != 0; ++b) {
-        if (!((chunk >> b) & 1)) continue;
-        const unsigned long long* cols = jump + (size_t)b * 1024;
+    // together: to chunk `base` (its low five bits are zero)
+    for (int b = 5; (base >> b) != 0; ++b) {
+        if (!((base >> b) & 1)) continue;
+        const unsigned long long* cols = jump + (size_t)b * 1024 + (size_t)(8 * lane) * 4;
+        const uint64_t word = lane < 8 ? s[0] : lane < 16 ? s[1] : lane < 24 ? s[2] : s[3];
+        uint32_t m = (uint32_t)(word >> (8 * (lane & 7))) & 0xFFu;
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        while (m) {
+            const int c = __ffs((int)m) - 1;
+            m &= m - 1;
+            const ulonglong2* col = reinterpret_cast<const ulonglong2*>(cols + (size_t)c * 4);
+            const ulonglong2 x = __ldg(col), y = __ldg(col + 1);
+            a0 ^= x.x; a1 ^= x.y; a2 ^= y.x; a3 ^= y.y;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            a0 ^= __shfl_xor_sync(KBBQ_FULL, a0, d);
+            a1 ^= __shfl_xor_sync(KBBQ_FULL, a1, d);
+            a2 ^= __shfl_xor_sync(KBBQ_FULL, a2, d);
+            a3 ^= __shfl_xor_sync(KBBQ_FULL, a3, d);
+        }
+        s[0] = a0; s[1] = a1; s[2] = a2; s[3] = a3;
+    }
+    // each lane: lane x 1024 further steps
+    if (lane) {
+        const unsigned long long* cols = lane_jump + (size_t)lane * 1024;
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -294,6 +324,8 @@ __global__ void __launch_bounds__(128) rng_sample_kernel(uint64_t s0, uint64_t s
         }
         s[0] = a0; s[1] = a1; s[2] = a2; s[3] = a3;
     }
+    const unsigned long long first = chunk * 1024ull;
+    if (first >= n_slots) return;
     for (int w = 0; w < 32; ++w) {
         uint32_t word = 0;
 #pragma unroll 4
