@@ -1160,12 +1160,22 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         }
         const BloomView sv = ctx->filt[KBBQ_FILTER_SAMPLED].view(), tv = ctx->filt[KBBQ_FILTER_TRUSTED].view();
         uint32_t* eo = err_bits ? b->d_err_bits : nullptr;
-        if (mode == INS_STAGED)
-            pass2_trusted_kernel<INS_STAGED><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink);
-        else if (mode == INS_TEST_FIRST)
-            pass2_trusted_kernel<INS_TEST_FIRST><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink);
-        else
-            pass2_trusted_kernel<INS_DIRECT><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink);
+        // one hash computation per k-mer for both filters when their salts agree (same seed: always, in the reference)
+        const bool shared_hash = sv.salt0 == tv.salt0 && sv.salt1 == tv.salt1 && !getenv("KBBQ_P2_SEPARATE_HASH");
+        const int max_kmers = std::max(1, (int)b->max_len - ctx->k + 1);
+        const size_t smem = shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0;
+        const int threads = KBBQ_WARPS_PER_BLOCK * 32;
+#define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers)
+        if (shared_hash) {
+            if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, true);
+            else if (mode == INS_TEST_FIRST) P2_LAUNCH(INS_TEST_FIRST, true);
+            else P2_LAUNCH(INS_DIRECT, true);
+        } else {
+            if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, false);
+            else if (mode == INS_TEST_FIRST) P2_LAUNCH(INS_TEST_FIRST, false);
+            else P2_LAUNCH(INS_DIRECT, false);
+        }
+#undef P2_LAUNCH
         if (int rc = check_launch(ctx, "pass2_trusted_kernel")) return rc;
         if (mode == INS_STAGED) {
             const int rc = staging_apply(ctx, KBBQ_FILTER_TRUSTED, st);

@@ -68,6 +68,10 @@ KBBQ_HD uint64_t bloom_block(const BloomView& b, uint64_t key) {
     const uint32_t h = hash_ap8(key, b.salt0);
     return b.n_blocks <= 0xFFFFFFFFull ? (uint64_t)fastmod_u32(h, b.fastmod_m, b.n_blocks) : (uint64_t)h;
 }
+// the same from an already computed hash_ap8(key, salt0)
+KBBQ_HD uint64_t bloom_block_of_hash(const BloomView& b, uint32_t h) {
+    return b.n_blocks <= 0xFFFFFFFFull ? (uint64_t)fastmod_u32(h, b.fastmod_m, b.n_blocks) : (uint64_t)h;
+}
 KBBQ_HD uint32_t bloom_pattern(const BloomView& b, uint64_t key) { return hash_ap8(key, b.salt1) & (KBBQ_NUM_PATTERNS - 1); }
 
 // reverse the 32 two-bit groups of a word

@@ -156,6 +156,13 @@ __device__ __forceinline__ uint32_t warp_bloom_query(const BloomView& f, bool va
     return coop_probe_call(f.words, f.patterns, blk, pat, vmask);
 }
 
+// the same for lanes that bring their (block, pattern) themselves
+__device__ __forceinline__ uint32_t warp_bloom_query_bp(const BloomView& f, bool valid, uint64_t blk, uint32_t pat) {
+    const uint32_t vmask = __ballot_sync(KBBQ_FULL, valid);
+    if (vmask == 0) return 0;
+    return coop_probe_impl<4>(f.words, f.patterns, valid ? blk : 0, valid ? pat : 0, vmask);
+}
+
 // pattern_blocked_bf::insert (bloom.hh:255-267) for the lanes with `ins` set; returns how many were inserted.
 // The (block, pattern) pairs are first compacted through `stage` (32 x 12 bytes of per-warp shared memory) so that
 // sparse inserts (pass 1 samples ~14-35 % of the k-mers) still fill every round.  All 32 lanes must call.
@@ -188,7 +195,7 @@ struct StageCursor {  // per warp, in registers (uniform across the lanes)
     uint32_t used;
 };
 // append the (block, pattern) of the lanes with `ins` set; returns how many.  All 32 lanes must call.
-__device__ __forceinline__ int warp_stage_insert(const BloomView& f, const StageSink& sink, StageCursor& cur, bool ins, uint64_t key) {
+__device__ __forceinline__ int warp_stage_insert_bp(const StageSink& sink, StageCursor& cur, bool ins, uint64_t blk, uint32_t pat) {
     const uint32_t imask = __ballot_sync(KBBQ_FULL, ins);
     if (imask == 0) return 0;
     const int lane = threadIdx.x & 31, n = __popc(imask);
@@ -201,10 +208,13 @@ __device__ __forceinline__ int warp_stage_insert(const BloomView& f, const Stage
     }
     if (ins) {
         const int rank = __popc(imask & ((1u << lane) - 1));
-        sink.items[cur.base + cur.used + rank] = ((unsigned long long)bloom_block(f, key) << 16) | bloom_pattern(f, key);
+        sink.items[cur.base + cur.used + rank] = ((unsigned long long)blk << 16) | pat;
     }
     cur.used += (uint32_t)n;
     return n;
+}
+__device__ __forceinline__ int warp_stage_insert(const BloomView& f, const StageSink& sink, StageCursor& cur, bool ins, uint64_t key) {
+    return warp_stage_insert_bp(sink, cur, ins, ins ? bloom_block(f, key) : 0, ins ? bloom_pattern(f, key) : 0);
 }
 __device__ __forceinline__ void warp_stage_open(const StageSink& sink, StageCursor& cur) {
     unsigned long long nb = 0;
@@ -217,15 +227,15 @@ __device__ __forceinline__ void warp_stage_close(const StageSink& sink, const St
 }
 
 template <bool TEST_FIRST>
-__device__ __forceinline__ int warp_bloom_insert(const BloomView& f, bool ins, uint64_t key, InsertStage& stage) {
+__device__ __forceinline__ int warp_bloom_insert_bp(const BloomView& f, bool ins, uint64_t blk, uint32_t pat, InsertStage& stage) {
     const uint32_t imask = __ballot_sync(KBBQ_FULL, ins);
     if (imask == 0) return 0;
     const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
     const int n = __popc(imask);
     if (ins) {
         const int rank = __popc(imask & ((1u << lane) - 1));
-        stage.blk[rank] = bloom_block(f, key);
-        stage.pat[rank] = bloom_pattern(f, key);
+        stage.blk[rank] = blk;
+        stage.pat[rank] = pat;
     }
     __syncwarp();
     for (int base = 0; base < n; base += 8) {
@@ -244,6 +254,10 @@ __device__ __forceinline__ int warp_bloom_insert(const BloomView& f, bool ins, u
     }
     __syncwarp();
     return n;
+}
+template <bool TEST_FIRST>
+__device__ __forceinline__ int warp_bloom_insert(const BloomView& f, bool ins, uint64_t key, InsertStage& stage) {
+    return warp_bloom_insert_bp<TEST_FIRST>(f, ins, ins ? bloom_block(f, key) : 0, ins ? bloom_pattern(f, key) : 0, stage);
 }
 
 // ---- batch set-up: quality masks from the quality bytes when the host did not bring them (one warp per word) ---------
@@ -385,10 +399,14 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
 #ifndef KBBQ_P2_MIN_BLOCKS
 #define KBBQ_P2_MIN_BLOCKS 4  // 64 registers, 32 warps/SM: 5.05 ms vs 6.61 unbounded (78 registers, 24 warps)
 #endif
-template <int MODE>
+// SHARED_HASH: both filters were built with the same seed, so salt_[0] and salt_[1] agree (the reference's filters
+// always do: bloom.hh:389, kbbq.cc:265-266) and a k-mer's block hash and pattern number are computed once, for the
+// query of `sampled`, and kept in shared memory for the insert into `trusted` (dynamic: 8 bytes per k-mer and warp).
+template <int MODE, bool SHARED_HASH>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P2_MIN_BLOCKS)
 pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, const int* __restrict__ thresholds,
-                     uint32_t* __restrict__ err_out, StageSink sink) {
+                     uint32_t* __restrict__ err_out, StageSink sink, int max_kmers) {
+    extern __shared__ uint2 p2_hash[];  // [warps][max_kmers]: .x = hash_ap8(key, salt0), .y = pattern (0xFFFFFFFF: invalid k-mer)
     __shared__ int thr[KBBQ_MAX_K + 1];
     __shared__ uint32_t Pm_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
     __shared__ uint32_t Em_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
@@ -399,6 +417,7 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t* Pm = Pm_all[wib];
     uint32_t* Em = Em_all[wib];
+    uint2* HP = p2_hash + (size_t)wib * (SHARED_HASH ? max_kmers : 0);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
     StageCursor cur{0, 0};
@@ -414,7 +433,14 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
             const int j = j0 + lane;
             uint64_t key = 0;
             const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
-            const uint32_t m = warp_bloom_query<true>(sampled, valid, key);
+            uint32_t m;
+            if (SHARED_HASH) {
+                const uint32_t h = hash_ap8(key, sampled.salt0), pat = valid ? bloom_pattern(sampled, key) : 0xFFFFFFFFu;
+                if (j < nk) HP[j] = make_uint2(h, pat);
+                m = warp_bloom_query_bp(sampled, valid, bloom_block_of_hash(sampled, h), pat);
+            } else {
+                m = warp_bloom_query<true>(sampled, valid, key);
+            }
             if (lane == 0) Pm[j0 >> 5] = m;
         }
         __syncwarp();
@@ -438,10 +464,18 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         // a k-mer is trusted when it is valid and none of its k bases is flagged (recalibrateutils.cc:26-36)
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
-            uint64_t key = 0;
-            const bool ins = j < nk && count_window32(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key);
-            if (MODE == INS_STAGED) inserted += warp_stage_insert(trusted, sink, cur, ins, key);
-            else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(trusted, ins, key, stage);
+            if (SHARED_HASH) {
+                const uint2 hp = j < nk ? HP[j] : make_uint2(0u, 0xFFFFFFFFu);
+                const bool ins = j < nk && hp.y != 0xFFFFFFFFu && count_window32(Em, j, j + k) == 0;
+                const uint64_t blk = bloom_block_of_hash(trusted, hp.x);
+                if (MODE == INS_STAGED) inserted += warp_stage_insert_bp(sink, cur, ins, blk, hp.y);
+                else inserted += warp_bloom_insert_bp<MODE == INS_TEST_FIRST>(trusted, ins, blk, hp.y, stage);
+            } else {
+                uint64_t key = 0;
+                const bool ins = j < nk && count_window32(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key);
+                if (MODE == INS_STAGED) inserted += warp_stage_insert(trusted, sink, cur, ins, key);
+                else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(trusted, ins, key, stage);
+            }
         }
         __syncwarp();
     }
