@@ -145,9 +145,6 @@ __device__ __noinline__ uint32_t coop_probe_call(const unsigned long long* words
 // All 32 lanes must call.
 template <bool INLINE>
 __device__ __forceinline__ uint32_t warp_bloom_query(const BloomView& f, bool valid, uint64_t key) {
-#if defined(KBBQ_P2_PER_LANE)
-    return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(f, key));
-#endif
     const uint32_t vmask = __ballot_sync(KBBQ_FULL, valid);
     if (vmask == 0) return 0;
     const uint64_t blk = valid ? bloom_block(f, key) : 0;
@@ -678,11 +675,7 @@ struct DevQuery {
         const int lane = threadIdx.x & 31;
         uint64_t key = 0;
         const bool valid = lane < count && fn(lane, key);
-#if defined(KBBQ_P3_PROBE_INLINE)
-        return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(*f, key));
-#else
         return probe_ballot(f, valid, key);
-#endif
 #else
         (void)count; (void)fn;
         return 0;

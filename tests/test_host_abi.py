@@ -206,3 +206,25 @@ def test_emulated_kernel_logic_matches_port(k, cov, L, kw):
     # the early-return quirk: reads whose seq differs after get_errors are exactly those the kernel logic reports
     changed = np.unique(np.searchsorted(rs.off, np.flatnonzero(seq_after != rs.seq), side="right") - 1)
     assert np.array_equal(changed, np.flatnonzero(mi >= 0))
+
+
+def test_quality_masks_helper():
+    """kbbq_quality_masks: per packed word, bit i of qmask[2w] is qual <= 2 and of qmask[2w+1] is qual <= 6."""
+    rs = synth.make_reads(3000, 10, 77, seed=2, ragged=True, min_len=40)
+    rs.qual[:] = np.random.default_rng(0).integers(0, 12, rs.qual.shape[0], dtype=np.uint8)
+    for threads in (1, 4):
+        pb = api.PackedBatch(rs, n_threads=threads)
+        q = pb.qual.reshape(-1, 32)
+        want2 = (q <= 2).astype(np.uint64) @ (1 << np.arange(32, dtype=np.uint64))
+        want6 = (q <= 6).astype(np.uint64) @ (1 << np.arange(32, dtype=np.uint64))
+        got = pb.qmask.reshape(-1, 2)
+        assert np.array_equal(got[:, 0].astype(np.uint64), want2) and np.array_equal(got[:, 1].astype(np.uint64), want6)
+    assert pb.as_struct().qmask is not None
+
+
+def test_device_warmup_fails_loudly_without_a_gpu():
+    L = api.lib()
+    if L.kbbq_device_count() > 0:
+        assert L.kbbq_device_warmup(0) == 0
+    else:
+        assert L.kbbq_device_warmup(0) == -3 and b"no CPU path" in L.kbbq_last_error()

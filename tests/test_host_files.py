@@ -92,3 +92,61 @@ def test_fastq_writer_moves_comment_to_plus_line(tool, tmp_path):
     dump = subprocess.run([tool, "dump", str(fq)], capture_output=True, text=True, check=True).stdout.splitlines()
     assert dump[0].split("\t") == ["r0", "ACGTN", "IIII#", "0", "0"]
     assert dump[1].split("\t") == ["r1", "GGCC", "5555", "1", "1"]
+
+
+def _dump(tool, path, threads):
+    env = dict(os.environ, HOSTTOOL_THREADS=str(threads))
+    return subprocess.run([tool, "dump", str(path)], capture_output=True, text=True, check=True, env=env).stdout
+
+
+def test_parallel_fastq_parse_equals_serial(tool, tmp_path):
+    """A plain 4-line FASTQ large enough to be cut into ranges (>= 1 MiB per thread) parses to the same records with
+    1 and 8 threads, read groups numbered in file order although they first appear in different ranges; qualities that
+    begin with '@' or '+' do not confuse the search for record starts."""
+    rng = np.random.default_rng(5)
+    n, L = 30000, 100
+    with open(tmp_path / "big.fq", "wb") as fh:
+        for i in range(n):
+            seq = bytes(rng.choice(list(b"ACGTN"), L, p=[.245, .245, .245, .245, .02]).astype(np.uint8))
+            qual = bytearray((rng.integers(0, 41, L) + 33).astype(np.uint8).tobytes())
+            if i % 7 == 0:
+                qual[0] = ord("@")
+            if i % 11 == 0:
+                qual[0] = ord("+")
+            rg = "late" if i > 2 * n // 3 else ("mid" if i > n // 3 else "early")
+            fh.write(b"@r%d/%d_RG:Z:%s some comment %d\n" % (i, 1 + (i & 1), rg.encode(), i) + seq + b"\n+\n" + bytes(qual) + b"\n")
+    assert os.path.getsize(tmp_path / "big.fq") > 4 << 20
+    one, eight = _dump(tool, tmp_path / "big.fq", 1), _dump(tool, tmp_path / "big.fq", 8)
+    assert one == eight and one.count("\n") == n
+    lines = one.splitlines()
+    assert lines[0].split("\t")[3] == "0" and lines[n // 2].split("\t")[3] == "1" and lines[-1].split("\t")[3] == "2"
+    # bgzip-style input (independent 64 KiB members) goes through the parallel inflater and gives the same records
+    bam_like = tmp_path / "big.fq.gz"
+    raw = (tmp_path / "big.fq").read_bytes()
+    import struct, zlib
+    with open(bam_like, "wb") as fh:
+        for p in range(0, len(raw), 0xFF00):
+            chunk = raw[p:p + 0xFF00]
+            co = zlib.compressobj(1, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", 18 + len(comp) + 8 - 1) + comp + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    assert _dump(tool, bam_like, 8) == one
+    # and plain gzip (one serial stream) too
+    with gzip.open(tmp_path / "plain.fq.gz", "wb", compresslevel=1) as g:
+        g.write(raw)
+    assert _dump(tool, tmp_path / "plain.fq.gz", 8) == one
+
+
+def test_multi_line_and_crlf_fastq_fall_back_to_kseq_semantics(tool, tmp_path):
+    """Anything but plain 4-line records takes the serial parser: wrapped sequence/quality lines, CRLF, FASTA-style junk."""
+    body = b"".join(b"@x%d c%d\r\nACGTACGTAC\r\nGTACGTNN\r\n+\r\nIIIIIIIIII\r\nIIIIII##\r\n" % (i, i) for i in range(40000))
+    (tmp_path / "wrapped.fq").write_bytes(body)
+    assert os.path.getsize(tmp_path / "wrapped.fq") > 2 << 20
+    out = _dump(tool, tmp_path / "wrapped.fq", 8).splitlines()
+    assert len(out) == 40000
+    assert out[0].split("\t")[:3] == ["x0", "ACGTACGTACGTACGTNN", "IIIIIIIIIIIIIIII##"]
+    assert out[-1].split("\t")[:3] == ["x39999", "ACGTACGTACGTACGTNN", "IIIIIIIIIIIIIIII##"]
+    (tmp_path / "short_qual.fq").write_bytes(b"@a\nACGT\n+\nIII\n")
+    r = subprocess.run([tool, "dump", str(tmp_path / "short_qual.fq")], capture_output=True, text=True)
+    assert r.returncode == 1 and "truncated quality" in r.stderr
