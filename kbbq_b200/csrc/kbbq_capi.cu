@@ -264,11 +264,22 @@ int insert_mode(const kbbq_ctx* ctx, int which, uint64_t n_slots) {
     return n_slots * 16 <= (24ull << 30) ? INS_STAGED : INS_TEST_FIRST;
 }
 
-struct Staging {  // device buffers of one staged-insert launch; released in stream order
+struct Staging {  // device buffers of one staged-insert launch; released in stream order when it goes out of scope
+    kbbq_ctx* ctx = nullptr;
     unsigned long long *items = nullptr, *sorted = nullptr, *cursor = nullptr;
     uint64_t capacity = 0;
+    Staging() = default;
+    Staging(const Staging&) = delete;
+    Staging& operator=(const Staging&) = delete;
+    ~Staging() {
+        if (!ctx) return;
+        if (items) cudaFreeAsync(items, ctx->stream);
+        if (sorted) cudaFreeAsync(sorted, ctx->stream);
+        if (cursor) cudaFreeAsync(cursor, ctx->stream);
+    }
 };
 int staging_begin(kbbq_ctx* ctx, uint64_t n_slots, int grid_warps, Staging& st) {
+    st.ctx = ctx;
     // every insert takes one item; closing a granule wastes at most 31 of its 512 items (a warp appends <= 32 at a time),
     // and every warp leaves its last granule partly used
     st.capacity = n_slots + n_slots / 8 + (uint64_t)(grid_warps + 1) * KBBQ_STAGE_GRANULE * 2;
@@ -277,12 +288,6 @@ int staging_begin(kbbq_ctx* ctx, uint64_t n_slots, int grid_warps, Staging& st) 
     CU(cudaMallocAsync(&st.cursor, 8, ctx->stream));
     CU(cudaMemsetAsync(st.cursor, 0, 8, ctx->stream));
     return KBBQ_OK;
-}
-void staging_free(kbbq_ctx* ctx, Staging& st) {
-    if (st.items) cudaFreeAsync(st.items, ctx->stream);
-    if (st.sorted) cudaFreeAsync(st.sorted, ctx->stream);
-    if (st.cursor) cudaFreeAsync(st.cursor, ctx->stream);
-    st = Staging();
 }
 // sort the staged (block, pattern) items by block range and apply them to filter `which`
 int staging_apply(kbbq_ctx* ctx, int which, Staging& st) {
@@ -1096,9 +1101,7 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
             pass1_insert_kernel<INS_DIRECT><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
         if (int rc = check_launch(ctx, "pass1_insert_kernel")) return rc;
         if (mode == INS_STAGED) {
-            const int rc = staging_apply(ctx, KBBQ_FILTER_SAMPLED, st);
-            staging_free(ctx, st);
-            if (rc) return rc;
+            if (int rc = staging_apply(ctx, KBBQ_FILTER_SAMPLED, st)) return rc;
         }
     }
     pass_end(ctx);
@@ -1178,9 +1181,7 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
 #undef P2_LAUNCH
         if (int rc = check_launch(ctx, "pass2_trusted_kernel")) return rc;
         if (mode == INS_STAGED) {
-            const int rc = staging_apply(ctx, KBBQ_FILTER_TRUSTED, st);
-            staging_free(ctx, st);
-            if (rc) return rc;
+            if (int rc = staging_apply(ctx, KBBQ_FILTER_TRUSTED, st)) return rc;
         }
     }
     pass_end(ctx);
