@@ -194,12 +194,23 @@ int main(int argc, char* argv[]) {
             for (size_t b = 0; b < session.batches().size(); ++b) {
                 std::vector<uint32_t> bits(std::max<uint64_t>(session.n_words(b), 1), 0);
                 const size_t first = session.batch_ranges()[b].first;
-                for (size_t i = first; i < session.batch_ranges()[b].second && i < fx.n(); ++i) {
-                    const size_t L = store.off[i + 1] - store.off[i];
-                    const uint32_t wo = session.word_off(b)[i - first];
-                    for (size_t j = 0; j < L; ++j)
-                        if (store.seq[store.off[i] + j] != fx.seq[fx.off[i] + j]) bits[wo + (j >> 5)] |= 1u << (j & 31);
-                }
+                const size_t last = std::min(session.batch_ranges()[b].second, fx.n());
+                // character comparison like the reference's std::not_equal_to<char>; a read owns its words of `bits`, so
+                // ranges of reads go to threads.  (The reference stops consuming at the end of the shorter file and reads
+                // past a shorter fixed read; here reads without a partner, and bases past its end, count as error-free.)
+                const unsigned nt = std::max(1u, std::min(16u, nthreads > 0 ? (unsigned)nthreads : std::thread::hardware_concurrency()));
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nt; ++t)
+                    th.emplace_back([&, t] {
+                        const size_t span = last > first ? last - first : 0;
+                        for (size_t i = first + span * t / nt; i < first + span * (t + 1) / nt; ++i) {
+                            const size_t L = std::min<size_t>(store.off[i + 1] - store.off[i], fx.off[i + 1] - fx.off[i]);
+                            const uint32_t wo = session.word_off(b)[i - first];
+                            for (size_t j = 0; j < L; ++j)
+                                if (store.seq[store.off[i] + j] != fx.seq[fx.off[i] + j]) bits[wo + (j >> 5)] |= 1u << (j & 31);
+                        }
+                    });
+                for (auto& t : th) t.join();
                 if (kbbq_consume_errors(session.ctx(), session.batches()[b], bits.data()) != KBBQ_OK) kbbq::throw_last(-3);
             }
             data = recalibrateutils::download_covariates(session, n_rg, (int)std::max<uint32_t>(1, store.max_len));
