@@ -127,3 +127,47 @@ def compare(got, want, ml=None, what=""):
         assert np.array_equal(got[key], want[key]), f"{what}{key} differs"
     assert np.array_equal(pad_cycle(got["cyc"], ml), pad_cycle(want["cyc"], ml)), f"{what}cycle counts differ"
     assert np.array_equal(pad_cycle(got["cydq"], ml), pad_cycle(want["cydq"], ml)), f"{what}cycle dq differ"
+
+
+def random_case(case):
+    """The deterministic shape sweep shared by the GPU-vs-port test (tests/test_gpu_parity.py) and the
+    port-vs-reference test (tests/test_oracle.py): (rs, k, genomelen, coverage, seed, n_batches, description)."""
+    from kbbq_b200 import synth
+
+    rng = np.random.default_rng(9000 + case)
+    k = int(rng.choice([12, 16, 21, 25, 31, 32]))
+    L = int(rng.choice([2 * k, 75, 100, 151, 200, 300]))
+    L = max(L, 2 * k)
+    cov = int(rng.choice([8, 15, 30, 60]))
+    G = int(rng.choice([20000, 50000]))
+    kw = dict(err_scale=float(rng.choice([0.5, 1.5, 4.0, 8.0])), n_frac=float(rng.choice([0.0, 0.001, 0.01])),
+              n_rg=int(rng.choice([1, 2, 5])), ragged=bool(rng.integers(0, 2)))
+    if kw["ragged"]:
+        kw["min_len"] = int(rng.integers(k, L + 1))
+    rs = synth.make_reads(G, cov, L, seed=300 + case, **kw)
+    if case % 3 == 0:  # un-binned qualities: more rows, more quality tie-breaks
+        rs.qual[:] = np.random.default_rng(case).integers(0, 42, rs.qual.shape[0], dtype=np.uint8)
+    seed = int(rng.integers(1, 2**32))
+    return rs, k, G, cov, seed, int(rng.integers(1, 4)), f"case {case} k={k} L={L} cov={cov} {kw}: "
+
+
+def run_ref(rs, k, genomelen, coverage, seed):
+    """The whole pipeline through the UNMODIFIED reference (oracle/_ref); a dict shaped like run_port's."""
+    from oracle import refharness as R
+
+    alpha_ld = np.longdouble(7.0) / np.longdouble(coverage)
+    approx = int(np.longdouble(genomelen) * coverage * alpha_ld)
+    rp = R.RefPipeline(rs, k)
+    rsam, rtru = R.RefBloom(approx, 0.01), R.RefBloom(approx, 0.0005)
+    want = {"slots": rp.subsample(rsam, float(alpha_ld), seed), "sampled_inserted": rsam.inserted,
+            "sampled_words": rsam.words(), "sampled_fpr": rsam.fprate()}
+    want["thresholds"] = rp.thresholds(rsam, 7.0, float(coverage))
+    want["pass2_errors"] = rp.infer_errors(rsam, want["thresholds"])
+    rp.find_trusted(rtru, rsam, want["thresholds"])
+    want["trusted_inserted"], want["trusted_words"] = rtru.inserted, rtru.words()
+    want["pass3_errors"], seq_after = rp.get_errors(rtru, want_seq=True)
+    want["seq_after_diff"] = np.flatnonzero(seq_after != rs.seq).astype(np.int64)
+    want["rgc"], want["qc"], want["cyc"], want["dic"] = rp.covariates(rtru)
+    want["meanq"], want["rgdq"], want["qdq"], want["cydq"], want["didq"] = rp.get_dqs()
+    want["newqual"] = rp.recalibrate()
+    return want

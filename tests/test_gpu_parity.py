@@ -333,24 +333,11 @@ def test_upload_rejects_out_of_range_metadata():
 
 @pytest.mark.parametrize("case", range(12))
 def test_randomised_shapes_match_port(case):
-    """A deterministic sweep over k, read length, coverage, error rate, N rate, ragged lengths and read-group count:
+    """A deterministic sweep over k, read length, coverage, error rate, N rate, ragged lengths and read-group count
+    (tests/common.py:random_case; tests/test_oracle.py pins the port to the unmodified reference on the same cases):
     every intermediate of the GPU run must equal the oracle port's, whatever path through get_errors the reads take."""
-    rng = np.random.default_rng(9000 + case)
-    k = int(rng.choice([12, 16, 21, 25, 31, 32]))
-    L = int(rng.choice([2 * k, 75, 100, 151, 200, 300]))
-    L = max(L, 2 * k)
-    cov = int(rng.choice([8, 15, 30, 60]))
-    G = int(rng.choice([20000, 50000]))
-    kw = dict(err_scale=float(rng.choice([0.5, 1.5, 4.0, 8.0])), n_frac=float(rng.choice([0.0, 0.001, 0.01])),
-              n_rg=int(rng.choice([1, 2, 5])), ragged=bool(rng.integers(0, 2)))
-    if kw["ragged"]:
-        kw["min_len"] = int(rng.integers(k, L + 1))
-    rs = synth.make_reads(G, cov, L, seed=300 + case, **kw)
-    if case % 3 == 0:  # un-binned qualities: more rows, more quality tie-breaks
-        rs.qual[:] = np.random.default_rng(case).integers(0, 42, rs.qual.shape[0], dtype=np.uint8)
-    seed = int(rng.integers(1, 2**32))
-    common.compare(common.run_gpu(rs, k, G, cov, seed, n_batches=int(rng.integers(1, 4))), common.run_port(rs, k, G, cov, seed),
-                   what=f"case {case} k={k} L={L} cov={cov} {kw}: ")
+    rs, k, G, cov, seed, n_batches, what = common.random_case(case)
+    common.compare(common.run_gpu(rs, k, G, cov, seed, n_batches=n_batches), common.run_port(rs, k, G, cov, seed), what=what)
 
 
 def test_filter_save_and_load_round_trip(tmp_path):

@@ -104,6 +104,18 @@ def test_port_matches_reference(k, cov, L, kw):
 
 
 @needs_ref
+@pytest.mark.parametrize("case", range(12))
+def test_port_matches_reference_on_the_randomised_sweep(case):
+    """The shapes the GPU is checked on against the port (tests/test_gpu_parity.py) are the shapes the port is checked on
+    against the unmodified reference here: the chain reference -> port -> kernels has no untested link."""
+    rs, k, G, cov, seed, _, what = common.random_case(case)
+    want = common.run_ref(rs, k, G, cov, seed)
+    got = common.run_port(rs, k, G, cov, seed)
+    common.compare(got, want, what=what)
+    assert np.array_equal(got["seq_after_diff"], want["seq_after_diff"])
+
+
+@needs_ref
 def test_port_fixed_mode_matches_reference():
     """--fixed (kbbq.cc:367-378): errors = read differs from the pre-corrected read, then consume_read."""
     rs = synth.make_reads(30000, 20, 100, seed=5, n_rg=2, n_frac=0.002)
