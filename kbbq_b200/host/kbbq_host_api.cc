@@ -59,9 +59,15 @@ void Session::ensure_resident(const ReadStore& rs) {
         uint64_t nw = 0;
         uint32_t ml = 0;
         CK(kbbq_pack_size(m, off.data(), &nw, &ml));
-        std::vector<uint64_t> bases(std::max<uint64_t>(nw, 1));
-        std::vector<uint32_t> nmask(std::max<uint64_t>(nw, 1)), word_off(m + 1), len(std::max<size_t>(m, 1));
-        std::vector<uint8_t> qual(std::max<uint64_t>(nw, 1) * 32);
+        // kbbq_pack_reads writes every word and byte (padding included): no need to zero 350 MB first
+        Column<uint64_t> bases;
+        Column<uint32_t> nmask;
+        Column<uint8_t> qual;
+        bases.resize(std::max<uint64_t>(nw, 1));
+        nmask.resize(std::max<uint64_t>(nw, 1));
+        qual.resize(std::max<uint64_t>(nw, 1) * 32);
+        if (nw == 0) { bases[0] = 0; nmask[0] = 0; std::memset(qual.data(), 0, 32); }
+        std::vector<uint32_t> word_off(m + 1), len(std::max<size_t>(m, 1));
         CK(kbbq_pack_reads(m, rs.seq.data() + rs.off[lo], off.data(), rs.qual.data() + rs.off[lo], bases.data(), nmask.data(),
                            qual.data(), word_off.data(), len.data(), nt));
         kbbq_batch hb;
