@@ -192,6 +192,9 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* b, uint32_t* err_b
 int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* b, uint32_t* err_bits);
 /* --fixed mode (kbbq.cc:367-378): error flags supplied by the caller, then CCovariateData::consume_read */
 int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* err_bits);
+/* the same for the first n_first reads of the batch only: main()'s loop stops consuming where the shorter of the two
+ * files ends (kbbq.cc:370) */
+int kbbq_consume_errors_n(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* err_bits, uint32_t n_first);
 int kbbq_covariates_reset(kbbq_ctx* ctx);
 int kbbq_covariates_download(kbbq_ctx* ctx, uint64_t* rgc, uint64_t* qc, uint64_t* cyc, uint64_t* dic);
 /* device pointer + size in uint64 words of the four count tables laid out back to back (for a sum all-reduce) */

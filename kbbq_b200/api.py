@@ -111,6 +111,7 @@ def lib():
         L.kbbq_pass2_find_trusted.argtypes = [vp, vp, vp]
         L.kbbq_pass3_covariates.argtypes = [vp, vp, vp]
         L.kbbq_consume_errors.argtypes = [vp, vp, vp]
+        L.kbbq_consume_errors_n.argtypes = [vp, vp, vp, u32]
         L.kbbq_covariates_reset.argtypes = [vp]
         L.kbbq_covariates_download.argtypes = [vp, vp, vp, vp, vp]
         L.kbbq_covariates_device.restype = vp

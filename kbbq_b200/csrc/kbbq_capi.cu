@@ -215,7 +215,7 @@ int check_launch(kbbq_ctx* ctx, const char* what) {
 }
 
 // covariate_count_kernel: rows of the block-private table that fit beside a second resident block, and the launch(es)
-int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, const uint32_t* d_mod) {
+int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, const uint32_t* d_mod, uint32_t n_reads) {
     const int row_cells = KBBQ_HIST_FIXED + 4 * ctx->max_cycle;
     const long long fixed_words = KBBQ_HIST_DIRECT_RG * KBBQ_NQ + 2 + 2 * KBBQ_HIST_RG;
     const long long budget_words = (108 * 1024) / 4 - fixed_words;  // 2 blocks/SM inside the 227 KB of an SM
@@ -227,12 +227,12 @@ int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, con
         ctx->count_attr_set = true;
     }
     const int warps_per_block = KBBQ_HIST_THREADS / 32;
-    const long long need = ((long long)b->n_reads + warps_per_block - 1) / warps_per_block;
+    const long long need = ((long long)n_reads + warps_per_block - 1) / warps_per_block;
     const int grid = (int)std::max(1ll, std::min(need, (long long)ctx->sm_count * 2));
     // a block's 32-bit cells must not overflow: at most 2^22 reads (of <= 512 bases) per block and launch
     const uint64_t per_launch = (uint64_t)grid << 22;
-    for (uint64_t first = 0; first < b->n_reads; first += per_launch) {
-        const uint32_t end = (uint32_t)std::min<uint64_t>(b->n_reads, first + per_launch);
+    for (uint64_t first = 0; first < n_reads; first += per_launch) {
+        const uint32_t end = (uint32_t)std::min<uint64_t>(n_reads, first + per_launch);
         covariate_count_kernel<<<grid, KBBQ_HIST_THREADS, smem, ctx->stream>>>(b->view(), ctx->counts(), d_err, d_mod,
                                                                                (uint32_t)first, end, S);
         if (int rc = check_launch(ctx, "covariate_count_kernel")) return rc;
@@ -1205,23 +1205,28 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
             b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, b->d_err_bits, b->d_mod, ctx->d_work);
         if (int rc = check_launch(ctx, "pass3_errors_kernel")) return rc;
         mark_kernel(ctx, "covariate_count_kernel");
-        if (int rc = launch_count(ctx, b, b->d_err_bits, b->d_mod)) return rc;
+        if (int rc = launch_count(ctx, b, b->d_err_bits, b->d_mod, b->n_reads)) return rc;
     }
     pass_end(ctx);
     return fetch_bits(ctx, b, err_bits);
 }
 
 int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* err_bits) {
+    return kbbq_consume_errors_n(ctx, cb, err_bits, cb ? cb->n_reads : 0);
+}
+
+int kbbq_consume_errors_n(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* err_bits, uint32_t n_first) {
     if (int rc = use(ctx)) return rc;
     kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
     if (!b || !err_bits) return fail(KBBQ_EINVAL, "null argument");
+    if (n_first > b->n_reads) return fail(KBBQ_EINVAL, "n_first exceeds the batch");
     if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     if (b->n_words) CU(cudaMemcpyAsync(b->d_err_bits, err_bits, b->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
-    if (b->n_reads) {
+    if (n_first) {
         mark_kernel(ctx, "covariate_count_kernel");
-        if (int rc = launch_count(ctx, b, b->d_err_bits, nullptr)) return rc;
+        if (int rc = launch_count(ctx, b, b->d_err_bits, nullptr, n_first)) return rc;
     }
     pass_end(ctx);
     CU(cudaStreamSynchronize(ctx->stream));  // err_bits is the caller's buffer

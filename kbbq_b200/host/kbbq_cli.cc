@@ -196,8 +196,9 @@ int main(int argc, char* argv[]) {
                 const size_t first = session.batch_ranges()[b].first;
                 const size_t last = std::min(session.batch_ranges()[b].second, fx.n());
                 // character comparison like the reference's std::not_equal_to<char>; a read owns its words of `bits`, so
-                // ranges of reads go to threads.  (The reference stops consuming at the end of the shorter file and reads
-                // past a shorter fixed read; here reads without a partner, and bases past its end, count as error-free.)
+                // ranges of reads go to threads.  Like the reference's loop (kbbq.cc:370) only reads that have a partner in
+                // the fixed file are consumed.  (The reference reads past the end of a fixed read that is shorter than
+                // its partner; here the bases without a partner count as error-free.)
                 const unsigned nt = std::max(1u, std::min(16u, nthreads > 0 ? (unsigned)nthreads : std::thread::hardware_concurrency()));
                 std::vector<std::thread> th;
                 for (unsigned t = 0; t < nt; ++t)
@@ -211,7 +212,8 @@ int main(int argc, char* argv[]) {
                         }
                     });
                 for (auto& t : th) t.join();
-                if (kbbq_consume_errors(session.ctx(), session.batches()[b], bits.data()) != KBBQ_OK) kbbq::throw_last(-3);
+                const uint32_t n_first = (uint32_t)(last > first ? last - first : 0);
+                if (kbbq_consume_errors_n(session.ctx(), session.batches()[b], bits.data(), n_first) != KBBQ_OK) kbbq::throw_last(-3);
             }
             data = recalibrateutils::download_covariates(session, n_rg, (int)std::max<uint32_t>(1, store.max_len));
         }

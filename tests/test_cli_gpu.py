@@ -127,3 +127,28 @@ def test_cli_bam_against_live_reference_cli(tmp_path):
         assert r.returncode == 0
         got, _ = _run(["--seed", "2854027472"] + args, tmp_path)
         assert got == gzip.open(tmp_path / "ref.gz").read()
+
+
+def test_cli_fixed_mode_with_a_shorter_fixed_file(tmp_path):
+    """main()'s --fixed loop stops consuming where the shorter file ends (kbbq.cc:370); every read is still
+    recalibrated.  Checked against the live reference CLI."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/kbbq_ref not present")
+    import sys
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from kbbq_b200 import synth
+
+    rs = synth.make_reads(30000, 20, 100, seed=91, n_rg=2, n_frac=0.002)
+    fq, fx = str(tmp_path / "in.fq"), str(tmp_path / "fixed.fq")
+    synth.to_fastq(rs, fq)
+    clean = rs.subset(0, rs.n * 2 // 3)
+    clean.seq = np.ascontiguousarray(clean.clean_seq)
+    synth.to_fastq(clean, fx)
+    args = ["-k", "32", "-f", fx, fq]
+    with open(tmp_path / "ref.gz", "wb") as fo:
+        r = subprocess.run([ref] + args, stdout=fo, stderr=subprocess.PIPE)
+    assert r.returncode == 0
+    got, _ = _run(args, tmp_path)
+    assert got == gzip.open(tmp_path / "ref.gz").read()
