@@ -228,3 +228,27 @@ def test_device_warmup_fails_loudly_without_a_gpu():
         assert L.kbbq_device_warmup(0) == 0
     else:
         assert L.kbbq_device_warmup(0) == -3 and b"no CPU path" in L.kbbq_last_error()
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/kbbq_b200.h must compile as C99 on its own, and a C program must link against
+    the library and get the loud no-GPU failure (or a context) through it."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "kbbq_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "kbbq_b200.h"\n'
+                   'int main(void) { kbbq_ctx* c = 0; kbbq_bloom_geom g; int rc;\n'
+                   '  if (kbbq_bloom_geometry(7000000, 0.01, KBBQ_DEFAULT_BLOOM_SEED, &g)) return 2;\n'
+                   '  printf("%llu %u\\n", (unsigned long long)g.table_bits, g.n_salts);\n'
+                   '  rc = kbbq_ctx_create(0, 32, 1, 100, &c);\n'
+                   '  if (rc == KBBQ_OK) kbbq_ctx_destroy(c); else printf("%d %s\\n", rc, kbbq_last_error());\n'
+                   '  return 0; }\n')
+    exe = tmp_path / "t"
+    lib_dir = os.path.join(ROOT, "kbbq_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src), "-L", lib_dir,
+                           "-lkbbq_b200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == "67150848 7"   # SURVEY.md Appendix A: Bloom(7000000, 0.01)
+    if api.lib().kbbq_device_count() == 0:
+        assert out[1].startswith("-3 ") and "no CPU path" in out[1]
