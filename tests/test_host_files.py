@@ -150,3 +150,33 @@ def test_multi_line_and_crlf_fastq_fall_back_to_kseq_semantics(tool, tmp_path):
     (tmp_path / "short_qual.fq").write_bytes(b"@a\nACGT\n+\nIII\n")
     r = subprocess.run([tool, "dump", str(tmp_path / "short_qual.fq")], capture_output=True, text=True)
     assert r.returncode == 1 and "truncated quality" in r.stderr
+
+
+def test_cli_error_paths_without_a_gpu(tmp_path):
+    """The CLI's argument and input errors (kbbq.cc:98-190) surface before any GPU work; with a valid input and no GPU
+    it fails loudly instead of falling back to a CPU path."""
+    cli = os.path.join(ROOT, "kbbq_b200", "host", "kbbq")
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    (tmp_path / "tiny.fq").write_bytes(b"@ab\n" + b"ACGT" * 9 + b"\n+\n" + b"I" * 36 + b"\n")
+    (tmp_path / "empty.fq").write_bytes(b"")
+
+    def run(*args):
+        r = subprocess.run([cli] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=tmp_path)
+        return r.returncode, r.stderr.decode()
+
+    rc, err = run("-k", "40", "tiny.fq")
+    assert rc == 1 and "k must be <= 32" in err
+    rc, err = run("nonexistent.fq")
+    assert rc == 1 and "Error opening file nonexistent.fq" in err
+    rc, err = run("-g", "100", "empty.fq")
+    assert rc == 1 and "File format must be bam, cram, or fastq" in err
+    rc, err = run("--bogus", "tiny.fq")
+    assert rc == 1 and "Unknown argument" in err
+    from kbbq_b200 import api
+    rc, err = run("tiny.fq")
+    if api.lib().kbbq_device_count() == 0:  # the GPU context comes first: no device, no run
+        assert rc == 1 and "no CPU path" in err
+        rc, err = run("-g", "100", "-c", "5", "tiny.fq")
+        assert rc == 1 and "no CPU path" in err
+    else:
+        assert rc == 1 and "--genomelen must be specified" in err
