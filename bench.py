@@ -1,24 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- bases recalibrated per second on the reference's config 2 shape (BASELINE.json).
+"""bench.py -- bases recalibrated per second on the reference's config 3 shape (BASELINE.json configs[2]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--genome G --coverage C]
 
-A step is one whole recalibration (passes 1-4, host maths and, for N>1, the merges) of a synthetic read set with
-the shape of BASELINE.json configs[1]: 4.6 Mb genome, 50X, 150 bp reads, two read groups, paired flags.  For N>1
-every rank holds one such shard of an N x 4.6 Mb genome (weak scaling); the filters are sized for the whole genome
-and replicated, partial filters / count tables are merged after passes 1-3.
+A step is one whole recalibration (passes 1-4, host maths and, for N>1, the merges) of a synthetic read set with the
+shape of BASELINE.json configs[2] -- the largest configuration that fits one GPU: 64 Mb genome, 30X, 150 bp reads
+(12.8 M reads, 1.92 Gbases per GPU), two read groups, paired flags.  The reads are a pure function of (seed, read
+index) made on the device (kbbq_synth_batch; kbbq_synth_host gives the CPU reference the very same reads).  For N>1
+every rank holds one such shard of an N x 64 Mb genome (weak scaling); the filters are sized for the whole genome
+and replicated, partial filters / count tables are merged after passes 1-3, and every rank's merged state must
+digest to the same value or the run fails.
 
   value     whole-job bases/s with the packed reads resident in HBM (device time, max over ranks)
-  e2e       the same through the C ABI from pinned HOST buffers: H2D of the packed batch and D2H of the new
+  e2e       the same through the C ABI from pinned HOST buffers (already packed: kbbq_pack_reads / kbbq_quality_masks
+            are host-side preparation outside the timed region): H2D of the packed batch and D2H of the new
             qualities inside the timed region
   roofline  the slowest pass kernel: algorithmic bytes / its CUDA-event time vs measured HBM copy peak
-  cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host on a bounded sample, rank 0, N=1
+  cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host on a bounded sample, rank 0
 
---impl reference times the reference's own CPU implementation of the path on a bounded sample per step.
+--impl reference times the reference's own CPU implementation of the path on a bounded sample per step: the same
+filter geometry as the full workload (filters sized for the whole genome), reads of the same synthetic stream drawn
+from a sub-genome at the same coverage, so that per-read work and cache behaviour are the full workload's.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -31,16 +38,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GENOME, COVERAGE, READ_LEN, K, N_RG, SEED = 4_600_000, 50, 150, 32, 2, 2854027472
-SAMPLE_GENOME = 400_000  # bounded CPU sample: 133 k reads, 20 Mbases, ~8 s of single-thread reference time per step
+GENOME, COVERAGE, READ_LEN, K, N_RG, SEED = 64_000_000, 30, 150, 32, 2, 2854027472
+ERR_SCALE = 1.5
+SAMPLE_GENOME = 500_000  # bounded CPU sample: 100 k reads, 15 Mbases from a 0.5 Mb stretch, filters at full size
 METRIC = "bases recalibrated/sec"
 
 
+def workload_id(genome, coverage):
+    return {(1_000_000, 20): "c1", (4_600_000, 50): "c2", (64_000_000, 30): "c3"}.get((genome, coverage), f"g{genome}_c{coverage}")
+
+
 def workload_name(n, genome=GENOME, coverage=COVERAGE):
-    which = ("BASELINE.json configs[1] shape" if (genome, coverage) == (GENOME, COVERAGE) else
-             "BASELINE.json configs[2] shape" if (genome, coverage) == (64_000_000, 30) else "custom shape")
+    which = {"c2": "BASELINE.json configs[1] shape", "c3": "BASELINE.json configs[2] shape"}.get(workload_id(genome, coverage), "custom shape")
     return (f"synthetic {n}x{genome / 1e6:.1f} Mb genome, {coverage}X, 150 bp reads, 2 read groups ({which}; "
             f"packed 2-bit batches instead of BAM records), k=32")
+
+
+def config_dict(world, genome, coverage):
+    n_reads = genome * coverage // READ_LEN
+    return {"workload": workload_name(world, genome, coverage), "reads_per_gpu": n_reads, "bases_per_gpu": n_reads * READ_LEN,
+            "l2": "packed inputs per GPU (%d MB) exceed the 126 MB L2; both filters are rebuilt from zero every step" % (n_reads * 271 // 1_000_000)}
 
 
 # ---- clocks ---------------------------------------------------------------------------------------------------------
@@ -88,17 +105,31 @@ class ClockSampler:
 
 
 # ---- reference arm ------------------------------------------------------------------------------------------------------
-def reference_pipeline(rs, genomelen):
-    """The unmodified reference's four pass drivers + host maths, as main() chains them; returns seconds per stage."""
+def synth_params(genome_len, seed, genome_seed=999):
+    from kbbq_b200 import api
+
+    return api.SynthParams(seed=seed, genome_seed=genome_seed, genome_len=genome_len, read_len=READ_LEN, n_rg=N_RG, err_scale=ERR_SCALE)
+
+
+def sample_reads(coverage, seed=7):
+    """the bounded CPU sample: reads of the bench's synthetic stream over a SAMPLE_GENOME stretch at full coverage"""
+    from kbbq_b200 import api
+
+    return api.synth_host(synth_params(SAMPLE_GENOME, seed), 0, SAMPLE_GENOME * coverage // READ_LEN, n_threads=os.cpu_count() or 1)
+
+
+def reference_pipeline(rs, genomelen, coverage):
+    """The unmodified reference's four pass drivers + host maths, as main() chains them; returns seconds per stage.
+    `genomelen` sizes the filters (kbbq.cc:264-266) -- the FULL workload's genome, not the sample's."""
     from oracle import refharness as R
 
-    alpha_ld = np.longdouble(7.0) / np.longdouble(COVERAGE)
-    approx = int(np.longdouble(genomelen) * COVERAGE * alpha_ld)
+    alpha_ld = np.longdouble(7.0) / np.longdouble(coverage)
+    approx = int(np.longdouble(genomelen) * coverage * alpha_ld)
     t0 = time.perf_counter()
     p = R.RefPipeline(rs, K)
     sampled, trusted = R.RefBloom(approx, 0.01), R.RefBloom(approx, 0.0005)
     p.subsample(sampled, float(alpha_ld), SEED)
-    th = p.thresholds(sampled, 7.0, float(COVERAGE))
+    th = p.thresholds(sampled, 7.0, float(coverage))
     p.find_trusted(trusted, sampled, th)
     p.covariates(trusted)
     p.get_dqs()
@@ -106,28 +137,28 @@ def reference_pipeline(rs, genomelen):
     return time.perf_counter() - t0, dict(p.times)
 
 
-def port_pipeline(rs, genomelen):
+def port_pipeline(rs, genomelen, coverage):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import common
 
     t0 = time.perf_counter()
-    common.run_port(rs, K, genomelen, COVERAGE, SEED)
+    common.run_port(rs, K, genomelen, coverage, SEED)
     return time.perf_counter() - t0, {}
 
 
-def _one_copy(seed):
+def _one_copy(arg):
     """one independent copy of the reference pipeline on its own sample (a worker process of all_cores_throughput)"""
-    from kbbq_b200 import synth
+    seed, genomelen, coverage = arg
     from oracle import refharness as R
 
-    rs = synth.make_reads(SAMPLE_GENOME, COVERAGE, READ_LEN, seed=seed, n_rg=N_RG, keep_clean=False)
+    rs = sample_reads(coverage, seed)
     fn = reference_pipeline if R.available() else port_pipeline
     t0 = time.time()
-    fn(rs, SAMPLE_GENOME)
+    fn(rs, genomelen, coverage)
     return rs.total_bases, t0, time.time()
 
 
-def all_cores_throughput():
+def all_cores_throughput(genomelen, coverage):
     """The reference computes on ONE thread (kbbq.cc:159-168: --threads only sizes htslib's pool), so the most a host
     can get out of it is one independent run per core -- as many files at once as there are cores.  Aggregate bases/s of
     `cores` concurrent copies, each on its own sample: the CPU's best case, reported next to the single-run figure."""
@@ -135,58 +166,63 @@ def all_cores_throughput():
 
     cores = os.cpu_count() or 1
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_one_copy, [100 + i for i in range(cores)])
+        res = pool.map(_one_copy, [(100 + i, genomelen, coverage) for i in range(cores)])
     bases = sum(r[0] for r in res)
     span = max(r[2] for r in res) - min(r[1] for r in res)
     return {"value": bases / span, "unit": "bases/s", "cores": cores,
-            "how": f"{cores} independent single-thread copies of the reference pipeline at once, one {SAMPLE_GENOME / 1e6:.1f} Mb / "
-                   f"{COVERAGE}X sample each; total bases / wall time from first start to last finish"}
+            "how": f"{cores} independent single-thread copies of the reference pipeline at once, one sample each (see `sample`); "
+                   f"total bases / wall time from first start to last finish"}
 
 
-def cpu_baseline_run():
-    from kbbq_b200 import synth
+def sample_text(rs, genomelen, coverage):
+    return (f"{rs.n} reads x {READ_LEN} bp ({rs.total_bases / 1e6:.0f} Mbases) of the bench's synthetic stream over a "
+            f"{SAMPLE_GENOME / 1e6:.1f} Mb stretch at {coverage}X, filters sized for the full {genomelen / 1e6:.0f} Mb genome as in the "
+            f"GPU arm; all four passes + model fit through the reference's own pass drivers, in memory (no parsing, no gzip); the "
+            f"reference computes on one thread whatever --threads says (kbbq.cc:159-168 only sizes htslib's pool)")
+
+
+def cpu_baseline_run(genomelen, coverage, with_all_cores=True):
     from oracle import refharness as R
 
-    rs = synth.make_reads(SAMPLE_GENOME, COVERAGE, READ_LEN, seed=7, n_rg=N_RG)
+    rs = sample_reads(coverage)
     if R.available():
-        secs, stages = reference_pipeline(rs, SAMPLE_GENOME)
+        secs, stages = reference_pipeline(rs, genomelen, coverage)
         kind = "reference"
     else:
-        secs, stages = port_pipeline(rs, SAMPLE_GENOME)
+        secs, stages = port_pipeline(rs, genomelen, coverage)
         kind = "port"
-    return {"value": rs.total_bases / secs, "unit": "bases/s", "cores": 1, "kind": kind, "all_cores": all_cores_throughput(),
-            "sample": f"{rs.n} reads x {READ_LEN} bp ({rs.total_bases / 1e6:.0f} Mbases) from a {SAMPLE_GENOME / 1e6:.1f} Mb genome at "
-                      f"{COVERAGE}X, all four passes + model fit, in memory (no parsing, no gzip); the reference computes on one "
-                      f"thread whatever --threads says (kbbq.cc:159-168 only sizes htslib's pool)",
-            "seconds": secs, "stages_s": stages}
+    out = {"value": rs.total_bases / secs, "unit": "bases/s", "cores": 1, "kind": kind,
+           "sample": sample_text(rs, genomelen, coverage), "seconds": secs, "stages_s": stages}
+    if with_all_cores:
+        out["all_cores"] = all_cores_throughput(genomelen, coverage)
+    return out
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from kbbq_b200 import synth
     from oracle import refharness as R
 
-    rs = synth.make_reads(SAMPLE_GENOME, COVERAGE, READ_LEN, seed=7, n_rg=N_RG)
+    genomelen = args.genome * args.gpus
+    rs = sample_reads(args.coverage)
     fn = reference_pipeline if R.available() else port_pipeline
     kind = "reference" if R.available() else "port"
-    for _ in range(args.warmup):
-        fn(rs, SAMPLE_GENOME)
+    for _ in range(min(args.warmup, 1)):  # a CPU has no clocks to ramp: one untimed step warms the page cache and allocator
+        fn(rs, genomelen, args.coverage)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fn(rs, SAMPLE_GENOME)
+        fn(rs, genomelen, args.coverage)
     secs = (time.perf_counter() - t0) / max(args.steps, 1)
     value = rs.total_bases / secs
-    sample = (f"each step = {rs.n} reads x {READ_LEN} bp ({rs.total_bases / 1e6:.0f} Mbases, {SAMPLE_GENOME / 1e6:.1f} Mb genome, "
-              f"{COVERAGE}X) through the reference's own pass drivers in memory")
+    sample = "each step = " + sample_text(rs, genomelen, args.coverage)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64/u8 integer (long double model fit)", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": 1, "kind": kind, "sample": sample,
-                         "all_cores": all_cores_throughput()},
+        "dtype": "u64/u8 integer (long double model fit on host)", "data": "synthetic",
+        "config": config_dict(args.gpus, args.genome, args.coverage),
+        "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
@@ -194,18 +230,21 @@ def run_reference_arm(args):
 
 # ---- our arm ----------------------------------------------------------------------------------------------------------
 def algorithmic_bytes(n_reads, L, k, sampled_ins, trusted_ins):
-    """bytes each pass must move for a batch of n_reads fixed-length reads."""
+    """bytes each pass must move for a batch of n_reads fixed-length reads.  Per kernel, a pass's bytes
+    are split by what each of its kernels must touch."""
     P, M, nk = (L + 3) // 4, (L + 7) // 8, L - k + 1
+    S = 8 * ((nk + 63) // 64)
     return {
-        "pass1": n_reads * (P + M + 8 * ((nk + 63) // 64)) + sampled_ins * 128,
+        "pass1": n_reads * (P + M + S) + sampled_ins * 128,
         "pass2": n_reads * (P + M + L + nk * 64) + trusted_ins * 128,
         "pass3": n_reads * (P + M + L + nk * 64),
         "pass4": n_reads * (P + M + 2 * L),
-        # per kernel (pass 1 and pass 3 are two kernels each; DESIGN.md section 4)
-        "rng_sample_kernel": n_reads * 8 * ((nk + 63) // 64),
-        "pass1_insert_kernel": n_reads * (P + M + 8 * ((nk + 63) // 64)) + sampled_ins * 128,
+        "rng_sample_kernel": n_reads * S,
+        "pass1_insert_kernel": n_reads * (P + M + S) + sampled_ins * 128,
         "pass2_trusted_kernel": n_reads * (P + M + L + nk * 64) + trusted_ins * 128,
         "pass3_errors_kernel": n_reads * (P + M + L + nk * 64),
+        "pass3_scan_kernel": n_reads * (P + M + nk * 64),          # the mandatory scan: every k-mer's block once
+        "pass3_repair_kernel": n_reads * (P + M + M),              # repairs' probes are data dependent and not credited
         "covariate_count_kernel": n_reads * (P + M + L + M),
         "pass4_apply_kernel": n_reads * (P + M + 2 * L),
     }
@@ -214,12 +253,13 @@ def algorithmic_bytes(n_reads, L, k, sampled_ins, trusted_ins):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--genome", type=int, default=GENOME, help="per-GPU genome length (default: config 2)")
-    ap.add_argument("--coverage", type=int, default=COVERAGE, help="coverage (default: config 2's 50; config 3: --genome 64000000 --coverage 30)")
+    ap.add_argument("--genome", type=int, default=GENOME, help="per-GPU genome length (default: config 3's 64 Mb)")
+    ap.add_argument("--coverage", type=int, default=COVERAGE, help="coverage (default: config 3's 30; config 2: --genome 4600000 --coverage 50)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (human-scale shards: 20 GB of pinned memory per rank)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -227,7 +267,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from kbbq_b200 import api, synth
+    from kbbq_b200 import api
     from kbbq_b200.dist import GpuComm
     from kbbq_b200.pipeline import Recalibrator
 
@@ -245,16 +285,13 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         comm = GpuComm(rank, world, local)
 
-    # ---- synthetic shard of this rank: reads over the WHOLE (world x per-GPU) genome -- one genome shared by all ranks
-    #      (genome_seed), a distinct read stream per rank
+    # ---- synthetic shard of this rank: reads [rank*n, (rank+1)*n) of one stream over the WHOLE (world x per-GPU) genome
     genomelen = args.genome * world
     n_reads = args.genome * args.coverage // READ_LEN
-    rs = synth.make_reads(genomelen, args.coverage, READ_LEN, seed=1000 + rank, n_rg=N_RG, n_reads=n_reads, keep_clean=False,
-                          genome_seed=None if world == 1 else 999)
-    pb = api.PackedBatch(rs, pinned=True)
-    total_bases = rs.total_bases * world
-
+    total_bases = n_reads * READ_LEN * world
     rc = Recalibrator(K, N_RG, READ_LEN, genomelen, args.coverage, SEED, device=local, comm=comm)
+    sp = synth_params(genomelen, 1000)
+    db = rc.ctx.synth_batch(sp, rank * n_reads, n_reads)
     stream = torch.cuda.ExternalStream(rc.ctx.stream, device=f"cuda:{local}")
 
     def barrier():
@@ -278,7 +315,7 @@ def main():
         return ms, outs
 
     # ---- resident path: inputs already in HBM
-    rc.add_batch(pb)
+    rc.add_resident(db)
 
     def step_resident():
         rc.reset()
@@ -297,35 +334,63 @@ def main():
     ms_step = ms_res / args.steps
     value = total_bases / (ms_step * 1e-3)
 
+    # ---- the result checks itself: every rank's merged state must digest to the same value; the counters must add up
+    rgc, qc, cyc, dic = rc.ctx.covariates()
+    small = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in (rgc, qc, cyc, dic, stats[-1].thresholds))).hexdigest()[:16]
+    digest = {"sampled": "%016x%016x" % rc.ctx.bloom_digest(api.FILTER_SAMPLED), "trusted": "%016x%016x" % rc.ctx.bloom_digest(api.FILTER_TRUSTED),
+              "counts_thresholds_sha256": small, "sampled_inserted": sampled_ins, "trusted_inserted": trusted_ins}
+    my_newqual = "%016x%016x" % rc.ctx.newqual_digest(db)
+    checks = {"bases_counted": int(rgc[:, 1].sum()), "bases_expected": total_bases,
+              "errors_rg_q_cycle_agree": int(rgc[:, 0].sum()) == int(qc[..., 0].sum()) == int(cyc[..., 0].sum())}
+    ok = checks["bases_counted"] == total_bases and checks["errors_rg_q_cycle_agree"] and int(qc[..., 1].sum()) == total_bases
+    per_rank = [digest]
+    if comm is not None:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, digest)
+        ok = ok and all(d == per_rank[0] for d in per_rank)
+    checks["ranks_agree"] = all(d == per_rank[0] for d in per_rank)
+    if not ok:
+        print(f"[rank {rank}] SELF-CHECK FAILED: {checks} {per_rank}", file=sys.stderr, flush=True)
+        return 2
+
     # ---- end to end: host buffers in, host qualities out, every step
-    rc.clear_batches()
-    qual_out = np.zeros(max(pb.n_words, 1) * 32, dtype=np.uint8)
-    qual_out_t = torch.from_numpy(qual_out).pin_memory()
-    qual_out_np = qual_out_t.numpy()
-
-    def step_e2e():
-        rc.reset()
-        rc.add_batch(pb)                                            # H2D of the packed batch from pinned memory
-        st = rc.run(fetch_quals=True, qual_bufs=[qual_out_np])      # ... D2H of the recalibrated qualities
+    e2e = None
+    if not args.no_e2e:
+        pb = rc.ctx.download(db, pinned=True)  # the host copy of the shard: what a host feeder would have packed
         rc.clear_batches()
-        return st
+        qual_out_t = torch.zeros(max(pb.n_words, 1) * 32, dtype=torch.uint8).pin_memory()
+        qual_out_np = qual_out_t.numpy()
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
-    e2e_value = total_bases / (ms_e2e / args.steps * 1e-3)
+        def step_e2e():
+            rc.reset()
+            rc.add_batch(pb)                                            # H2D of the packed batch from pinned memory
+            st = rc.run(fetch_quals=True, qual_bufs=[qual_out_np])      # ... D2H of the recalibrated qualities
+            rc.clear_batches()
+            return st
+
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, _ = timed(step_e2e, args.steps)
+        e2e_ok = "%016x%016x" % api.digest_words(qual_out_np) == my_newqual  # the host copy IS what the resident run made
+        if not e2e_ok:
+            print(f"[rank {rank}] SELF-CHECK FAILED: end-to-end qualities differ from the resident run's", file=sys.stderr, flush=True)
+            return 2
+        e2e = {"value": total_bases / (ms_e2e / args.steps * 1e-3), "unit": "bases/s", "h2d_bytes_per_step": pb.h2d_bytes * world,
+               "d2h_bytes_per_step": int(pb.n_words) * 32 * world, "ms_per_step": ms_e2e / args.steps,
+               "note": "host buffers are already packed (kbbq_pack_reads / kbbq_quality_masks run before the timed region: host-side "
+                       "preparation, the C-ABI call as defined); qualities read back match the resident run's digest"}
 
     # ---- roofline of the slowest pass kernel (per launch: one launch per pass per step at one batch per rank)
     pass_ms = {p: float(np.mean([s.pass_ms[p] for s in stats])) for p in ("pass1", "pass2", "pass3", "pass4")}
     host_ms = {p: float(np.mean([s.host_ms[p] for s in stats])) for p in stats[0].host_ms}
     merge_ms = {p: float(np.mean([s.merge_ms[p] for s in stats])) for p in stats[0].merge_ms}
     # per-rank insert counts for the byte model: merged counters / world is the per-rank average
-    ab = algorithmic_bytes(rs.n, READ_LEN, K, sampled_ins // world, trusted_ins // world)
+    ab = algorithmic_bytes(n_reads, READ_LEN, K, sampled_ins // world, trusted_ins // world)
     kernel_ms = {kn: float(np.mean([s.kernel_ms[kn] for s in stats])) for kn in stats[0].kernel_ms}
     merge_kernel_ms = kernel_ms.pop("or_allreduce_p2p_kernel", None)  # two launches per step (N>1); reported with the merges
-    # bloom_insert_sorted_kernel (staged inserts of HBM-sized filters) applies what pass 1b / pass 2 staged: its time
-    # belongs to those kernels' algorithmic bytes, half of the 128 bytes per insert each way
-    sorted_ms = kernel_ms.pop("bloom_insert_sorted_kernel", None)
+    # helper kernels of the staged inserts (HBM-sized filters) apply what pass 1b / pass 2 staged: their time is in the
+    # pass totals; they have no algorithmic bytes of their own
+    helpers = {kn: kernel_ms.pop(kn) for kn in list(kernel_ms) if kn not in ab}
     dom = max(kernel_ms, key=kernel_ms.get)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -333,15 +398,16 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = ab[dom] / (kernel_ms[dom] * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")  # ncu DRAM bytes per launch, keyed by workload then kernel
+    if os.path.exists(tpath) and world == 1:
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            t = json.load(open(tpath)).get(workload_id(args.genome, args.coverage), {})
+            traffic, traffic_src = t.get(dom), t.get("_source")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "ms_per_launch": kernel_ms[dom],
                 "all_kernels": {kn: {"ms": kernel_ms[kn], "GBps": ab[kn] / (kernel_ms[kn] * 1e-3) / 1e9,
                                      "frac": ab[kn] / (kernel_ms[kn] * 1e-3) / 1e9 / peak} for kn in kernel_ms},
@@ -349,26 +415,24 @@ def main():
                                for p in pass_ms}}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_run()
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_run(genomelen, args.coverage, with_all_cores=(world == 1))
 
     if rank == 0:
+        cfg = config_dict(world, args.genome, args.coverage)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64/u8 integer (long double model fit on host)", "data": "synthetic",
-            "config": {"workload": workload_name(world, args.genome, args.coverage), "reads_per_gpu": rs.n, "bases_per_gpu": rs.total_bases,
-                       "l2": "packed inputs per GPU (%d MB) exceed the 126 MB L2; both filters are rebuilt from zero every step"
-                             % (pb.h2d_bytes // 1_000_000),
-                       "sampled_inserts": sampled_ins, "trusted_inserts": trusted_ins},
-            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": pb.h2d_bytes * world,
-                    "d2h_bytes_per_step": int(pb.n_words) * 32 * world, "ms_per_step": ms_e2e / args.steps},
+            "config": cfg,
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clock_info,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "breakdown_ms": {"passes": pass_ms, "kernels": kernel_ms, "host": host_ms, "merge": merge_ms,
-                             "merge_kernel_or_allreduce_p2p": merge_kernel_ms, "bloom_insert_sorted_kernel": sorted_ms},
+            "self_check": {"passed": True, **checks, "digest": digest},
+            "breakdown_ms": {"passes": pass_ms, "kernels": kernel_ms, "helper_kernels": helpers, "host": host_ms, "merge": merge_ms,
+                             "merge_kernel_or_allreduce_p2p": merge_kernel_ms},
         }))
     rc.close()
     if world > 1:

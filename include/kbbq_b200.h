@@ -146,6 +146,13 @@ void* kbbq_bloom_device_counter(kbbq_ctx* ctx, int which);
 /* words |= other (other: device pointer to an equally sized bit array, e.g. a peer GPU's mapped filter) */
 int kbbq_bloom_or_from(kbbq_ctx* ctx, int which, const void* other_device_words, uint64_t first_word, uint64_t n_words);
 
+/* Order-independent 128-bit digests {sum, xor of mix(word ^ mix(index))} of a filter's bit array, of the four count
+ * tables and of a batch's recalibrated qualities, computed on the device: equality checks across ranks, runs and
+ * against a CPU restatement (tests) without moving tens of GB to the host.  An all-zero array digests to {0, 0}. */
+int kbbq_bloom_digest(kbbq_ctx* ctx, int which, uint64_t out[2]);
+int kbbq_covariates_digest(kbbq_ctx* ctx, uint64_t out[2]);
+int kbbq_batch_newqual_digest(kbbq_ctx* ctx, const kbbq_dbatch* b, uint64_t out[2]);
+
 /* Save / restore a filter (parameters, insert counter, bit array laid out as the reference's bit_table_): checkpoint
  * between passes, fixtures across runs.  kbbq_bloom_load (re)creates filter `which` from the file's parameters.
  * The reference never serialises its filters. */
@@ -209,6 +216,28 @@ int kbbq_set_model(kbbq_ctx* ctx, const int32_t* meanq, const int32_t* rgdq, con
 int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* b, uint8_t* qual_out);
 /* device pointer to the batch's recalibrated qualities (valid after kbbq_pass4_recalibrate) */
 void* kbbq_batch_device_newqual(kbbq_dbatch* b);
+
+/* ---- synthetic batches: MEASUREMENT TOOLING, not part of the reference's interface ---------------------------------- */
+/* Reads of the shape SURVEY.md section 8(d) / Appendix C describes as a pure function of (seed, read index): uniform
+ * genome, uniform start and strand, fixed length, qualities from {2,11,25,37,40}, substitution errors at
+ * err_scale * 10^(-q/10), second = index & 1, read group = (index / 2) % n_rg.  kbbq_synth_batch fills a packed batch
+ * for reads [first_read, first_read + n_reads) directly in device memory; kbbq_synth_host writes the same reads as
+ * ASCII (seq[n*read_len], qual[n*read_len] phred, rg[n], second[n]) for a CPU reference; kbbq_batch_download copies a
+ * resident batch's arrays back into caller-allocated host buffers laid out like the arrays of a kbbq_batch; any pointer may be NULL. */
+typedef struct kbbq_synth_params {
+    uint64_t seed;        /* read stream */
+    uint64_t genome_seed; /* genome; shards of one run share it */
+    uint64_t genome_len;
+    uint32_t read_len;
+    uint32_t n_rg;
+    double err_scale;
+} kbbq_synth_params;
+int kbbq_synth_batch(kbbq_ctx* ctx, const kbbq_synth_params* p, uint64_t first_read, uint32_t n_reads, kbbq_dbatch** out);
+int kbbq_synth_host(const kbbq_synth_params* p, uint64_t first_read, uint64_t n_reads, char* seq, uint8_t* qual, int32_t* rg,
+                    uint8_t* second, int n_threads);
+int kbbq_batch_extent(const kbbq_dbatch* b, uint32_t* n_reads, uint64_t* n_words, uint32_t* max_len);
+int kbbq_batch_download(kbbq_ctx* ctx, const kbbq_dbatch* b, uint64_t* bases, uint32_t* nmask, uint8_t* qual, uint32_t* word_off,
+                        uint32_t* len, uint16_t* rg, uint8_t* second, uint32_t* qmask);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,12 @@ class _Batch(C.Structure):
     ]
 
 
+class SynthParams(C.Structure):
+    """kbbq_synth_params: synthetic reads as a pure function of (seed, read index) -- measurement tooling"""
+    _fields_ = [("seed", C.c_uint64), ("genome_seed", C.c_uint64), ("genome_len", C.c_uint64), ("read_len", C.c_uint32),
+                ("n_rg", C.c_uint32), ("err_scale", C.c_double)]
+
+
 _lib = None
 
 
@@ -121,6 +127,13 @@ def lib():
         L.kbbq_pass4_recalibrate.argtypes = [vp, vp, vp]
         L.kbbq_batch_device_newqual.restype = vp
         L.kbbq_batch_device_newqual.argtypes = [vp]
+        L.kbbq_bloom_digest.argtypes = [vp, i32, vp]
+        L.kbbq_covariates_digest.argtypes = [vp, vp]
+        L.kbbq_batch_newqual_digest.argtypes = [vp, vp, vp]
+        L.kbbq_synth_batch.argtypes = [vp, C.POINTER(SynthParams), u64, u32, C.POINTER(vp)]
+        L.kbbq_synth_host.argtypes = [C.POINTER(SynthParams), u64, u64, vp, vp, vp, vp, i32]
+        L.kbbq_batch_extent.argtypes = [vp, C.POINTER(u32), C.POINTER(u64), C.POINTER(u32)]
+        L.kbbq_batch_download.argtypes = [vp, vp] + [vp] * 8
         _lib = L
     return _lib
 
@@ -175,17 +188,49 @@ def fit_model_host(rgc, qc, cyc, dic):
     return meanq, rgdq, qdq, cydq, didq
 
 
+def digest_words(words: np.ndarray) -> tuple:
+    """host restatement of the library's digest kernel (numpy): {sum, xor} of mix(word ^ mix(index)) over non-zero words"""
+    w = np.ascontiguousarray(words).view(np.uint64).reshape(-1)
+
+    def mix(x):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+    s, x = np.uint64(0), np.uint64(0)
+    with np.errstate(over="ignore"):
+        for lo in range(0, w.size, 1 << 24):
+            v = w[lo : lo + (1 << 24)]
+            nz = np.flatnonzero(v)
+            if nz.size == 0:
+                continue
+            h = mix(v[nz] ^ mix((nz + lo).astype(np.uint64)))
+            s = s + h.sum(dtype=np.uint64)
+            x = x ^ np.bitwise_xor.reduce(h)
+    return int(s), int(x)
+
+
+def synth_host(params: SynthParams, first_read: int, n_reads: int, n_threads: int = 8):
+    """the reads kbbq_synth_batch makes, as a synth.ReadSet (ASCII arrays for the oracle)"""
+    from . import synth
+
+    L = int(params.read_len)
+    seq = np.zeros(n_reads * L, dtype=np.uint8)
+    qual = np.zeros(n_reads * L, dtype=np.uint8)
+    rg = np.zeros(max(n_reads, 1), dtype=np.int32)
+    second = np.zeros(max(n_reads, 1), dtype=np.uint8)
+    _check(lib().kbbq_synth_host(C.byref(params), first_read, n_reads, _p(seq), _p(qual), _p(rg), _p(second), n_threads))
+    off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(L)).astype(np.uint64)
+    return synth.ReadSet(seq=seq, off=off, qual=qual, rg=rg[:n_reads], second=second[:n_reads], n_rg=int(params.n_rg))
+
+
 class PackedBatch:
     """Host-side packed read batch (the kbbq_batch layout)."""
 
-    def __init__(self, rs, n_threads: int = 8, pinned: bool = False, qmask: bool = True):
-        n = rs.n
-        nw = C.c_uint64(0)
-        ml = C.c_uint32(0)
-        off = np.ascontiguousarray(rs.off, dtype=np.uint64)
-        _check(lib().kbbq_pack_size(n, _p(off), C.byref(nw), C.byref(ml)))
-        self.n_reads, self.n_words, self.max_len = n, int(nw.value), int(ml.value)
+    def _alloc_arrays(self, pinned: bool, qmask: bool):
         self._keep = []  # pinned torch tensors backing the numpy views
+        n = self.n_reads
 
         def alloc(count, dt):
             if not pinned:
@@ -196,6 +241,7 @@ class PackedBatch:
             self._keep.append(t)
             return t.numpy().view(dt)
 
+        self._alloc = alloc
         self.bases = alloc(max(self.n_words, 1), np.uint64)
         self.nmask = alloc(max(self.n_words, 1), np.uint32)
         self.qual = alloc(max(self.n_words, 1) * 32, np.uint8)
@@ -204,6 +250,25 @@ class PackedBatch:
         self.len = alloc(max(n, 1), np.uint32)
         self.rg = alloc(max(n, 1), np.uint16)
         self.second = alloc(max(n, 1), np.uint8)
+        self.qmask = alloc(max(self.n_words, 1) * 2, np.uint32) if qmask else None
+
+    @classmethod
+    def empty(cls, n_reads: int, n_words: int, max_len: int, pinned: bool = False, qmask: bool = True) -> "PackedBatch":
+        """zeroed arrays of the given extent (the destination of Context.download)"""
+        self = cls.__new__(cls)
+        self.n_reads, self.n_words, self.max_len = n_reads, n_words, max_len
+        self._alloc_arrays(pinned, qmask)
+        return self
+
+    def __init__(self, rs, n_threads: int = 8, pinned: bool = False, qmask: bool = True):
+        n = rs.n
+        nw = C.c_uint64(0)
+        ml = C.c_uint32(0)
+        off = np.ascontiguousarray(rs.off, dtype=np.uint64)
+        _check(lib().kbbq_pack_size(n, _p(off), C.byref(nw), C.byref(ml)))
+        self.n_reads, self.n_words, self.max_len = n, int(nw.value), int(ml.value)
+        self._alloc_arrays(pinned, False)
+        alloc = self._alloc
         if n:
             self.rg[:] = rs.rg
             self.second[:] = rs.second
@@ -371,6 +436,21 @@ class Context:
     def bloom_or_from(self, which: int, other_ptr: int, first_word: int, n_words: int):
         _check(self.L.kbbq_bloom_or_from(self.h, which, C.c_void_p(other_ptr), first_word, n_words))
 
+    def bloom_digest(self, which: int) -> tuple:
+        d = np.zeros(2, dtype=np.uint64)
+        _check(self.L.kbbq_bloom_digest(self.h, which, _p(d)))
+        return int(d[0]), int(d[1])
+
+    def covariates_digest(self) -> tuple:
+        d = np.zeros(2, dtype=np.uint64)
+        _check(self.L.kbbq_covariates_digest(self.h, _p(d)))
+        return int(d[0]), int(d[1])
+
+    def newqual_digest(self, db: "DeviceBatch") -> tuple:
+        d = np.zeros(2, dtype=np.uint64)
+        _check(self.L.kbbq_batch_newqual_digest(self.h, db.h, _p(d)))
+        return int(d[0]), int(d[1])
+
     def bloom_save(self, which: int, path: str):
         _check(self.L.kbbq_bloom_save(self.h, which, os.fsencode(path)))
 
@@ -396,6 +476,22 @@ class Context:
         h = C.c_void_p()
         _check(self.L.kbbq_batch_upload_async(self.h, C.byref(s), C.byref(h)))
         return DeviceBatch(self, h, pb)
+
+    def synth_batch(self, params: SynthParams, first_read: int, n_reads: int) -> "DeviceBatch":
+        """reads [first_read, first_read + n_reads) of the synthetic stream, made on the device (measurement tooling)"""
+        h = C.c_void_p()
+        _check(self.L.kbbq_synth_batch(self.h, C.byref(params), first_read, n_reads, C.byref(h)))
+        nr, nw, ml = C.c_uint32(0), C.c_uint64(0), C.c_uint32(0)
+        _check(self.L.kbbq_batch_extent(h, C.byref(nr), C.byref(nw), C.byref(ml)))
+        return DeviceBatch(self, h, BatchExtent(int(nr.value), int(nw.value), int(ml.value)))
+
+    def download(self, db: "DeviceBatch", pinned: bool = False) -> PackedBatch:
+        """a resident batch's arrays as a host PackedBatch (e.g. the host copy of a synthetic batch)"""
+        e = db.pb
+        pb = PackedBatch.empty(e.n_reads, e.n_words, e.max_len, pinned=pinned, qmask=True)
+        _check(self.L.kbbq_batch_download(self.h, db.h, _p(pb.bases), _p(pb.nmask), _p(pb.qual), _p(pb.word_off), _p(pb.len),
+                                          _p(pb.rg), _p(pb.second), _p(pb.qmask)))
+        return pb
 
     # passes
     def sampler_seed(self, seed: int, alpha: float):
@@ -467,6 +563,13 @@ class Context:
             out = np.zeros(max(db.pb.n_words, 1) * 32, dtype=np.uint8)
         _check(self.L.kbbq_pass4_recalibrate(self.h, db.h, _p(out) if fetch else None))
         return out
+
+
+class BatchExtent:
+    """what the passes need to know of a batch that has no host copy"""
+
+    def __init__(self, n_reads: int, n_words: int, max_len: int):
+        self.n_reads, self.n_words, self.max_len = n_reads, n_words, max_len
 
 
 class DeviceBatch:

@@ -7,6 +7,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 
 #include "kbbq_host.h"
 #include "kbbq_kernels.cuh"
+#include "kbbq_synth.cuh"
 
 using namespace kbbq;
 
@@ -110,6 +112,10 @@ struct kbbq_ctx {
     int8_t* d_cy = nullptr;
     int8_t* d_di = nullptr;
     unsigned int* d_work = nullptr;
+    // set by qual_range_kernel when an uploaded batch holds a quality above 93 (kbbq_batch is a public struct: callers may
+    // fill it without kbbq_pack_reads); mapped pinned memory, reported by the next synchronising call
+    int* h_badq = nullptr;
+    int* d_badq = nullptr;
     bool count_attr_set = false;
     // both filters' pattern tables (2 x 4 MiB) in ONE allocation: every probe and insert reads one pattern, pass 2
     // reads both tables; measured on the config-3 shape, pass 2 runs in 59.4 ms with the tables adjacent against 70.2 ms
@@ -174,6 +180,13 @@ namespace {
 int use(kbbq_ctx* ctx) {
     if (!ctx) return fail(KBBQ_EINVAL, "null context");
     CU(cudaSetDevice(ctx->device));
+    return KBBQ_OK;
+}
+
+// after a synchronising call: did any uploaded batch bring a quality the tables cannot index?
+int check_quals(kbbq_ctx* ctx) {
+    if (ctx->h_badq && *(volatile int*)ctx->h_badq)
+        return fail(KBBQ_ERANGE, "quality above 93 in an uploaded batch: outside the model's table range (bases holding one were skipped)");
     return KBBQ_OK;
 }
 
@@ -339,6 +352,67 @@ void geom_from_c(const kbbq_bloom_geom* o, host::BloomGeom& g) {
 
 }  // namespace
 
+// ---- synthetic batches (measurement tooling, kbbq_synth.cuh): one thread per 32-base word ---------------------------
+namespace kbbq {
+__global__ void __launch_bounds__(256) synth_reads_kernel(SynthSpec s, unsigned long long first_read, uint32_t n_reads, uint32_t wpr,
+                                                          unsigned long long* __restrict__ bases, uint32_t* __restrict__ nmask,
+                                                          uint8_t* __restrict__ qual, uint2* __restrict__ qmask,
+                                                          uint32_t* __restrict__ word_off, uint32_t* __restrict__ len,
+                                                          uint16_t* __restrict__ rg, uint8_t* __restrict__ second) {
+    const unsigned long long gw = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gw >= (unsigned long long)n_reads * wpr) return;
+    const uint32_t r = (uint32_t)(gw / wpr), w = (uint32_t)(gw % wpr);
+    const unsigned long long gr = first_read + r;
+    const SynthRead rd = synth_read(s, gr);
+    unsigned long long bw = 0;
+    uint32_t q4[8] = {0, 0, 0, 0, 0, 0, 0, 0}, m2 = 0, m6 = 0;
+    const uint32_t cnt = s.read_len - 32 * w < 32 ? s.read_len - 32 * w : 32;
+#pragma unroll
+    for (uint32_t i = 0; i < 32; ++i) {
+        if (i >= cnt) break;
+        int code, q;
+        synth_base(s, rd, 32 * w + i, code, q);
+        bw |= (unsigned long long)code << (2 * i);
+        q4[i >> 2] |= (uint32_t)q << (8 * (i & 3));
+        m2 |= (uint32_t)(q <= 2) << i;
+        m6 |= (uint32_t)(q <= 6) << i;
+    }
+    bases[gw] = bw;
+    nmask[gw] = 0;
+    uint4* qo = reinterpret_cast<uint4*>(qual + gw * 32);
+    qo[0] = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+    qo[1] = make_uint4(q4[4], q4[5], q4[6], q4[7]);
+    qmask[gw] = make_uint2(m2, m6);
+    if (w == 0) {
+        word_off[r] = r * wpr;
+        len[r] = s.read_len;
+        rg[r] = (uint16_t)((gr >> 1) % s.n_rg);
+        second[r] = (uint8_t)(gr & 1);
+        if (r == n_reads - 1) word_off[n_reads] = n_reads * wpr;
+    }
+}
+}  // namespace kbbq
+
+namespace {
+int synth_spec(const kbbq_synth_params* p, SynthSpec& s) {
+    if (!p) return fail(KBBQ_EINVAL, "null synth parameters");
+    if (p->read_len < 1 || p->read_len > KBBQ_MAX_READ_LEN || p->genome_len < p->read_len || p->n_rg < 1 || p->n_rg > 65535 ||
+        !(p->err_scale >= 0))
+        return fail(KBBQ_EINVAL, "bad synth parameters");
+    s.seed = p->seed; s.genome_seed = p->genome_seed; s.genome_len = p->genome_len; s.read_len = p->read_len; s.n_rg = p->n_rg;
+    const double pq[5] = {0.01, 0.04, 0.10, 0.35, 0.50};
+    const int qv[5] = {2, 11, 25, 37, 40};
+    double cum = 0;
+    for (int i = 0; i < 5; ++i) {
+        cum += pq[i];
+        s.q_cum[i] = cum >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(cum * 4294967296.0);
+        const double pe = std::min(1.0, p->err_scale * std::pow(10.0, -qv[i] / 10.0));
+        s.err_thr[i] = pe >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(pe * 4294967296.0);
+    }
+    return KBBQ_OK;
+}
+}  // namespace
+
 extern "C" {
 
 const char* kbbq_last_error(void) { return g_err.c_str(); }
@@ -443,8 +517,9 @@ int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint
     word_off[n] = (uint32_t)words;
     unsigned char code[256];
     for (int c = 0; c < 256; ++c) code[c] = (unsigned char)host::nt4((unsigned char)c);
-    bool bad_q = false;
+    std::atomic<bool> bad_q{false};
     auto work = [&](uint64_t lo, uint64_t hi) {
+        bool bad = false;
         for (uint64_t r = lo; r < hi; ++r) {
             const char* s = seq + off[r];
             const uint8_t* q = qual + off[r];
@@ -458,7 +533,7 @@ int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint
                     if (c < 4) bw |= (uint64_t)c << (2 * i);
                     else nw |= 1u << i;
                     const uint8_t qq = q[w * 32 + i];
-                    if (qq > KBBQ_MAXQ) bad_q = true;
+                    if (qq > KBBQ_MAXQ) bad = true;
                     qual_out[(size_t)(wo + w) * 32 + i] = qq;
                 }
                 for (uint32_t i = cnt; i < 32; ++i) qual_out[(size_t)(wo + w) * 32 + i] = 0;
@@ -466,6 +541,7 @@ int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint
                 nmask[wo + w] = nw;
             }
         }
+        if (bad) bad_q.store(true, std::memory_order_relaxed);
     };
     if (n_threads <= 1 || n < 4096) {
         work(0, n);
@@ -478,7 +554,7 @@ int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint
         }
         for (auto& t : th) t.join();
     }
-    if (bad_q) return fail(KBBQ_ERANGE, "quality above 93: outside the model's table range");
+    if (bad_q.load()) return fail(KBBQ_ERANGE, "quality above 93: outside the model's table range");
     return KBBQ_OK;
 }
 
@@ -555,6 +631,9 @@ int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) 
     CU(cudaMalloc(&c->d_cy, (size_t)n_rg * KBBQ_NQ * 2 * max_cycle));
     CU(cudaMalloc(&c->d_di, (size_t)n_rg * KBBQ_NQ * 16));
     CU(cudaMalloc(&c->d_work, sizeof(unsigned int)));
+    CU(cudaHostAlloc(&c->h_badq, sizeof(int), cudaHostAllocMapped));
+    *c->h_badq = 0;
+    CU(cudaHostGetDevicePointer(&c->d_badq, c->h_badq, 0));
     CU(cudaMalloc(&c->d_pattern_pool, (size_t)2 * KBBQ_NUM_PATTERNS * 64));
     *out = c;
     return KBBQ_OK;
@@ -577,6 +656,7 @@ void kbbq_ctx_destroy(kbbq_ctx* c) {
     cudaFree(c->d_cy);
     cudaFree(c->d_di);
     cudaFree(c->d_work);
+    cudaFreeHost(c->h_badq);
     cudaFree(c->d_pattern_pool);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -592,7 +672,7 @@ int kbbq_sync(kbbq_ctx* ctx) {
     if (int rc = use(ctx)) return rc;
     CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return KBBQ_OK;
+    return check_quals(ctx);
 }
 
 void* kbbq_stream(kbbq_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -734,6 +814,41 @@ int kbbq_bloom_fprate(kbbq_ctx* ctx, int which, double* fpr) {
     const host::BloomGeom& g = ctx->filt[which].geom;
     *fpr = host::effective_fpp(g.table_bits, ins, g.n_salts);
     return KBBQ_OK;
+}
+
+static int digest_words(kbbq_ctx* ctx, const unsigned long long* d_words, uint64_t n, uint64_t out[2]) {
+    unsigned long long* d_out = nullptr;
+    CU(cudaMallocAsync(&d_out, 16, ctx->stream));
+    CU(cudaMemsetAsync(d_out, 0, 16, ctx->stream));
+    if (n) {
+        const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+        digest_kernel<<<grid, 256, 0, ctx->stream>>>(d_words, n, d_out);
+        if (int rc = check_launch(ctx, "digest_kernel")) return rc;
+    }
+    CU(cudaMemcpyAsync(out, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaFreeAsync(d_out, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_digest(kbbq_ctx* ctx, int which, uint64_t out[2]) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    if (!out) return fail(KBBQ_EINVAL, "null output");
+    return digest_words(ctx, ctx->filt[which].d_words, ctx->filt[which].geom.table_bits / 64, out);
+}
+
+int kbbq_covariates_digest(kbbq_ctx* ctx, uint64_t out[2]) {
+    if (int rc = use(ctx)) return rc;
+    if (!out) return fail(KBBQ_EINVAL, "null output");
+    return digest_words(ctx, ctx->d_counts, ctx->n_counts(), out);
+}
+
+int kbbq_batch_newqual_digest(kbbq_ctx* ctx, const kbbq_dbatch* b, uint64_t out[2]) {
+    if (int rc = use(ctx)) return rc;
+    if (!b || !out) return fail(KBBQ_EINVAL, "null argument");
+    if (!b->d_newqual) return fail(KBBQ_ESTATE, "pass 4 has not run on this batch");
+    return digest_words(ctx, reinterpret_cast<const unsigned long long*>(b->d_newqual), b->n_words * 4, out);
 }
 
 void* kbbq_bloom_device_words(kbbq_ctx* ctx, int which) {
@@ -963,6 +1078,13 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
         if (e2 == cudaSuccess && !h->n_words) e2 = cudaMemsetAsync(b->d_qual, 0, qbytes, ctx->copy_stream);
         if (e2 == cudaSuccess && h->n_words)
             e2 = cudaMemcpyAsync(b->d_qual, h->qual, (size_t)h->n_words * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e2 == cudaSuccess && h->n_words) {  // the count and apply kernels index tables by quality: flag anything above 93
+            const unsigned long long n16 = (unsigned long long)h->n_words * 2;
+            qual_range_kernel<<<(unsigned)std::min<unsigned long long>((n16 + 255) / 256, (unsigned long long)ctx->sm_count * 8), 256, 0,
+                                ctx->copy_stream>>>(reinterpret_cast<const uint4*>(b->d_qual), n16, ctx->d_badq);
+            e2 = cudaGetLastError();
+            ++ctx->launches;
+        }
         if (e2 == cudaSuccess && !h->qmask && h->n_words) {  // no masks from the host: derive them where the qualities land
             qual_masks_kernel<<<(unsigned)((h->n_words * 32 + 255) / 256), 256, 0, ctx->copy_stream>>>(b->d_qual, h->n_words, b->d_qmask);
             e2 = cudaGetLastError();
@@ -1134,7 +1256,7 @@ static int fetch_bits(kbbq_ctx* ctx, kbbq_dbatch* b, uint32_t* host_bits) {
     if (!host_bits || !b->n_words) return KBBQ_OK;
     CU(cudaMemcpyAsync(host_bits, b->d_err_bits, b->n_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return KBBQ_OK;
+    return check_quals(ctx);
 }
 
 int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bits) {
@@ -1334,7 +1456,7 @@ int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_o
         pass_end(ctx);
         if (parts > 1) {
             CU(cudaStreamSynchronize(ctx->copy_stream));
-            return KBBQ_OK;
+            return check_quals(ctx);
         }
     } else {
         pass_end(ctx);
@@ -1342,7 +1464,111 @@ int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_o
     if (fetch) {
         CU(cudaMemcpyAsync(qual_out, b->d_newqual, (size_t)b->n_words * 32, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        return check_quals(ctx);
     }
+    return KBBQ_OK;
+}
+
+// ---- synthetic batches (measurement tooling) -------------------------------------------------------------------------
+int kbbq_synth_host(const kbbq_synth_params* p, uint64_t first_read, uint64_t n_reads, char* seq, uint8_t* qual, int32_t* rg,
+                    uint8_t* second, int n_threads) {
+    SynthSpec s;
+    if (int rc = synth_spec(p, s)) return rc;
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t r = lo; r < hi; ++r) {
+            const SynthRead rd = synth_read(s, first_read + r);
+            for (uint32_t i = 0; i < s.read_len; ++i) {
+                int code, q;
+                synth_base(s, rd, i, code, q);
+                seq[r * s.read_len + i] = "ACGT"[code];
+                qual[r * s.read_len + i] = (uint8_t)q;
+            }
+            if (rg) rg[r] = (int32_t)(((first_read + r) >> 1) % s.n_rg);
+            if (second) second[r] = (uint8_t)((first_read + r) & 1);
+        }
+    };
+    if (n_threads <= 1 || n_reads < 4096) {
+        work(0, n_reads);
+    } else {
+        std::vector<std::thread> th;
+        const uint64_t per = (n_reads + n_threads - 1) / n_threads;
+        for (int t = 0; t < n_threads; ++t) {
+            const uint64_t lo = std::min<uint64_t>(n_reads, (uint64_t)t * per), hi = std::min<uint64_t>(n_reads, lo + per);
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto& t : th) t.join();
+    }
+    return KBBQ_OK;
+}
+
+int kbbq_synth_batch(kbbq_ctx* ctx, const kbbq_synth_params* p, uint64_t first_read, uint32_t n_reads, kbbq_dbatch** out) {
+    if (int rc = use(ctx)) return rc;
+    if (!out) return fail(KBBQ_EINVAL, "null output");
+    SynthSpec s;
+    if (int rc = synth_spec(p, s)) return rc;
+    if ((int)s.read_len > ctx->max_cycle) return fail(KBBQ_ERANGE, "read longer than the context's max_cycle");
+    if ((int)s.n_rg > ctx->n_rg) return fail(KBBQ_ERANGE, "read group id >= n_rg");
+    const uint32_t wpr = (s.read_len + 31) / 32;
+    const uint64_t n_words = (uint64_t)n_reads * wpr;
+    if (n_words > 0xFFFFFFFFull) return fail(KBBQ_ERANGE, "batch too large: split it");
+    kbbq_dbatch* b = new (std::nothrow) kbbq_dbatch();
+    if (!b) return fail(KBBQ_ENOMEM, "out of host memory");
+    b->n_reads = n_reads; b->max_len = s.read_len; b->n_words = n_words; b->k = ctx->k;
+    for (int i = 0; i <= 4; ++i) {
+        b->part_read[i] = (uint32_t)((uint64_t)n_reads * i / 4);
+        b->part_word[i] = (uint64_t)b->part_read[i] * wpr;
+    }
+    const size_t nw = std::max<uint64_t>(n_words, 1);
+    void** ptrs[] = {(void**)&b->d_bases, (void**)&b->d_nmask, (void**)&b->d_qual, (void**)&b->d_qmask, (void**)&b->d_word_off,
+                     (void**)&b->d_len, (void**)&b->d_rg, (void**)&b->d_second, (void**)&b->d_slot_off};
+    const size_t bytes[] = {(nw + 1) * 8, (nw + 1) * 4, nw * 32, nw * 8, ((size_t)n_reads + 1) * 4, std::max<size_t>(n_reads, 4) * 4,
+                            std::max<size_t>(n_reads, 8) * 2, std::max<size_t>(n_reads, 16), ((size_t)n_reads + 1) * 8};
+    for (int i = 0; i < 9; ++i) {
+        cudaError_t e = cudaMallocAsync(ptrs[i], bytes[i], ctx->stream);
+        if (e == cudaSuccess && i < 2) e = cudaMemsetAsync((char*)*ptrs[i] + (bytes[i] - (i ? 4 : 8)), 0, i ? 4 : 8, ctx->stream);  // the padding word
+        if (e != cudaSuccess) {
+            kbbq_batch_free(ctx, b);
+            return fail(e == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA, std::string("synth batch: ") + cudaGetErrorString(e));
+        }
+    }
+    if (n_reads) {
+        synth_reads_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, ctx->stream>>>(s, first_read, n_reads, wpr, b->d_bases, b->d_nmask, b->d_qual,
+                                                                                      b->d_qmask, b->d_word_off, b->d_len, b->d_rg, b->d_second);
+        if (int rc = check_launch(ctx, "synth_reads_kernel")) { kbbq_batch_free(ctx, b); return rc; }
+        if (int rc = slot_prefix(ctx, b->d_len, n_reads, b->d_slot_off)) { kbbq_batch_free(ctx, b); return rc; }
+    } else {
+        CU(cudaMemsetAsync(b->d_word_off, 0, 4, ctx->stream));
+        CU(cudaMemsetAsync(b->d_slot_off, 0, 8, ctx->stream));
+    }
+    b->n_slots = (int)s.read_len >= ctx->k ? (uint64_t)n_reads * (s.read_len - ctx->k + 1) : 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = b;
+    return KBBQ_OK;
+}
+
+int kbbq_batch_extent(const kbbq_dbatch* b, uint32_t* n_reads, uint64_t* n_words, uint32_t* max_len) {
+    if (!b) return fail(KBBQ_EINVAL, "null batch");
+    if (n_reads) *n_reads = b->n_reads;
+    if (n_words) *n_words = b->n_words;
+    if (max_len) *max_len = b->max_len;
+    return KBBQ_OK;
+}
+
+int kbbq_batch_download(kbbq_ctx* ctx, const kbbq_dbatch* b, uint64_t* bases, uint32_t* nmask, uint8_t* qual, uint32_t* word_off,
+                        uint32_t* len, uint16_t* rg, uint8_t* second, uint32_t* qmask) {
+    if (int rc = use(ctx)) return rc;
+    if (!b) return fail(KBBQ_EINVAL, "null batch");
+    if (int rc = need_quals(ctx, const_cast<kbbq_dbatch*>(b))) return rc;
+    const size_t nw = b->n_words, n = b->n_reads;
+    if (bases && nw) CU(cudaMemcpyAsync(bases, b->d_bases, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nmask && nw) CU(cudaMemcpyAsync(nmask, b->d_nmask, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (qual && nw) CU(cudaMemcpyAsync(qual, b->d_qual, nw * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (qmask && nw) CU(cudaMemcpyAsync(qmask, b->d_qmask, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (word_off) CU(cudaMemcpyAsync(word_off, b->d_word_off, (n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (len && n) CU(cudaMemcpyAsync(len, b->d_len, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rg && n) CU(cudaMemcpyAsync(rg, b->d_rg, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (second && n) CU(cudaMemcpyAsync(second, b->d_second, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return KBBQ_OK;
 }
 

@@ -266,6 +266,18 @@ __global__ void qual_masks_kernel(const uint8_t* __restrict__ qual, unsigned lon
     if ((threadIdx.x & 31) == 0) out[w] = make_uint2(m2, m6);
 }
 
+// ---- batch set-up: any quality above KBBQ_MAXQ?  (the count and apply kernels skip such bases; the host is told)
+__global__ void __launch_bounds__(256) qual_range_kernel(const uint4* __restrict__ q, unsigned long long n16, int* __restrict__ flag) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = __ldg(q + i);
+        const uint32_t lim = 0x01010101u * KBBQ_MAXQ;
+        bad = bad || __vmaxu4(v.x, lim) != lim || __vmaxu4(v.y, lim) != lim || __vmaxu4(v.z, lim) != lim || __vmaxu4(v.w, lim) != lim;
+    }
+    if (__any_sync(KBBQ_FULL, bad) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+
 // ---- batch set-up: k-mer slots per read (max(0, len-k+1)) and a trailing 0, scanned in place into slot_off ---------
 __global__ void slot_counts_kernel(const uint32_t* __restrict__ len, uint32_t n, int k, unsigned long long* __restrict__ out) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -570,10 +582,11 @@ covariate_count_kernel(BatchView b, CountView cv, const uint32_t* __restrict__ e
             if (lane < 4 * nwg) qq = __ldg(reinterpret_cast<const uint2*>(b.qual + (size_t)(wo + w0) * 32) + lane);
             for (int c = 0; c < nwg; ++c) {
                 const int i = (w0 + c) * 32 + lane;
-                const bool in = i < len;
+                const bool inl = i < len;
                 const int src = 4 * c + (lane >> 3);
                 const uint32_t qlo = __shfl_sync(KBBQ_FULL, qq.x, src), qhi = __shfl_sync(KBBQ_FULL, qq.y, src);
-                const int qi = in ? (int)((((lane & 4) ? qhi : qlo) >> (8 * (lane & 3))) & 255u) : 255;
+                const int qi = inl ? (int)((((lane & 4) ? qhi : qlo) >> (8 * (lane & 3))) & 255u) : 255;
+                const bool in = inl && qi <= KBBQ_MAXQ;  // a quality the tables cannot index is skipped (and reported: qual_range_kernel)
                 const unsigned long long Ac = __shfl_sync(KBBQ_FULL, A, c);
                 const uint32_t nmc = __shfl_sync(KBBQ_FULL, nm, c), emask = __shfl_sync(KBBQ_FULL, e, c);
                 const uint32_t cxc = __shfl_sync(KBBQ_FULL, cx, c);
@@ -790,7 +803,7 @@ __device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Head& h, c
     for (int j = 0; j < 8; ++j) {
         const int i = i0 + j;
         const int qi = (int)((res[j >> 2] >> (8 * (j & 3))) & 255u);
-        if (i < h.len && qi >= 6) {  // minqual: lower qualities pass through unchanged
+        if (i < h.len && qi >= 6 && qi <= KBBQ_MAXQ) {  // minqual: lower qualities pass through unchanged (so does anything the tables cannot index)
             const size_t row = h.rgrow + qi;
             int v = mv.base[row] + mv.cy[(row * 2 + h.sec) * (size_t)mv.max_cycle + i];
             if (((d.nflags >> j) & 3u) == 0) {  // this base and the one before it are ACGT (and i > 0)
@@ -851,6 +864,36 @@ __global__ void bloom_query_keys_kernel(BloomView f, const unsigned long long* _
                                         uint8_t* __restrict__ hits) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) hits[i] = bloom_contains_dev(f, keys[i]) ? 1 : 0;
+}
+
+// ---- order-independent digest of a word array: {sum, xor} of mix(word ^ mix(index)) -- equality checks across ranks/runs
+__device__ __forceinline__ unsigned long long digest_mix(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) digest_kernel(const unsigned long long* __restrict__ w, unsigned long long n,
+                                                     unsigned long long* __restrict__ out) {
+    unsigned long long s = 0, x = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long v = __ldg(w + i);
+        if (v) {  // zero words contribute nothing: an empty table digests to {0, 0} whatever its size
+            const unsigned long long h = digest_mix(v ^ digest_mix(i));
+            s += h;
+            x ^= h;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        s += __shfl_xor_sync(KBBQ_FULL, s, d);
+        x ^= __shfl_xor_sync(KBBQ_FULL, x, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, s);
+        atomicXor(out + 1, x);
+    }
 }
 
 // ---- dst |= src over 128-bit words: the local half of the multi-GPU filter merge -------------------------------------

@@ -57,6 +57,11 @@ class Recalibrator:
         self.batches.append(db)
         return db
 
+    def add_resident(self, db: api.DeviceBatch) -> api.DeviceBatch:
+        """adopt a batch that is already in device memory (Context.synth_batch)"""
+        self.batches.append(db)
+        return db
+
     def clear_batches(self):
         for b in self.batches:
             b.free()
