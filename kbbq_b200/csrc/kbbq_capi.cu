@@ -117,6 +117,7 @@ struct kbbq_ctx {
     int* h_badq = nullptr;
     int* d_badq = nullptr;
     bool count_attr_set = false;
+    bool p4_attr_set = false;
     // both filters' pattern tables (2 x 4 MiB) in ONE allocation: every probe and insert reads one pattern, pass 2
     // reads both tables; measured on the config-3 shape, pass 2 runs in 59.4 ms with the tables adjacent against 70.2 ms
     // with two separate cudaMallocs (marking them persisting in L2 on top of that changed nothing)
@@ -152,6 +153,8 @@ struct kbbq_dbatch {
     unsigned long long* d_slot_off = nullptr;
     uint32_t* d_sample_bits = nullptr;
     uint32_t* d_err_bits = nullptr;
+    uint32_t* d_tflags = nullptr;  // pass 3: trusted flag of every k-mer (word layout), scan -> repair
+    uint32_t* d_repair = nullptr;  // pass 3: indices of the reads the scan could not finish
     uint32_t* d_mod = nullptr;  // per read: the base get_errors left modified, or 0xFFFFFFFF (see covariate_count_kernel)
     uint8_t* d_newqual = nullptr;
     // pass 4 hands its output to the host in KBBQ_P4_PARTS pieces, each copied while the next is computed
@@ -630,7 +633,7 @@ int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) 
     CU(cudaMalloc(&c->d_base, sizeof(int16_t) * (size_t)n_rg * KBBQ_NQ));
     CU(cudaMalloc(&c->d_cy, (size_t)n_rg * KBBQ_NQ * 2 * max_cycle));
     CU(cudaMalloc(&c->d_di, (size_t)n_rg * KBBQ_NQ * 16));
-    CU(cudaMalloc(&c->d_work, sizeof(unsigned int)));
+    CU(cudaMalloc(&c->d_work, 2 * sizeof(unsigned int)));
     CU(cudaHostAlloc(&c->h_badq, sizeof(int), cudaHostAllocMapped));
     *c->h_badq = 0;
     CU(cudaHostGetDevicePointer(&c->d_badq, c->h_badq, 0));
@@ -1004,7 +1007,7 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaStream_t st = ctx ? ctx->stream : nullptr;
     void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_qmask, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
-                    b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual};
+                    b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual, b->d_tflags, b->d_repair};
     if (b->qual_ready) {
         if (ctx && !b->qual_waited) cudaStreamWaitEvent(st, b->qual_ready, 0);  // d_qual is freed in `st`'s order
         cudaEventDestroy(b->qual_ready);
@@ -1321,11 +1324,18 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
     if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {
-        CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
-        mark_kernel(ctx, "pass3_errors_kernel");
-        pass3_errors_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), ctx->filt[KBBQ_FILTER_TRUSTED].view(), ctx->k, b->d_err_bits, b->d_mod, ctx->d_work);
-        if (int rc = check_launch(ctx, "pass3_errors_kernel")) return rc;
+        if (!b->d_tflags) CU(cudaMallocAsync(&b->d_tflags, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+        if (!b->d_repair) CU(cudaMallocAsync(&b->d_repair, (size_t)b->n_reads * 4, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned int), ctx->stream));  // [0] repair-list length, [1] work counter
+        const BloomView tv = ctx->filt[KBBQ_FILTER_TRUSTED].view();
+        mark_kernel(ctx, "pass3_scan_kernel");
+        pass3_scan_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+            b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work);
+        if (int rc = check_launch(ctx, "pass3_scan_kernel")) return rc;
+        mark_kernel(ctx, "pass3_repair_kernel");
+        pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+            b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1);
+        if (int rc = check_launch(ctx, "pass3_repair_kernel")) return rc;
         mark_kernel(ctx, "covariate_count_kernel");
         if (int rc = launch_count(ctx, b, b->d_err_bits, b->d_mod, b->n_reads)) return rc;
     }
@@ -1436,13 +1446,29 @@ int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_o
     if (b->n_reads) {
         mark_kernel(ctx, "pass4_apply_kernel");
         ModelView mv{ctx->d_base, ctx->d_cy, ctx->d_di, ctx->max_cycle};
+        // lookup tables in shared memory when they leave room for three blocks per SM (two read groups of 150-base reads:
+        // 63 KB); larger models keep the global-memory lookups
+        size_t p4_smem = p4_smem_bytes(ctx->n_rg, ctx->max_cycle);
+        if (p4_smem > 72 * 1024 || getenv("KBBQ_P4_GLOBAL")) p4_smem = 0;
+        if (p4_smem && !ctx->p4_attr_set) {
+            CU(cudaFuncSetAttribute(pass4_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+            ctx->p4_attr_set = true;
+        }
+        const int blocks_per_sm = p4_smem ? (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (p4_smem + 1024))) : 8;
+        auto p4_grid = [&](uint32_t n_reads) {
+            const long long need = ((long long)n_reads + KBBQ_WARPS_PER_BLOCK - 1) / KBBQ_WARPS_PER_BLOCK;
+            return (int)std::max(1ll, std::min(need, (long long)ctx->sm_count * blocks_per_sm));
+        };
         // with a host destination the batch goes in four pieces: piece i travels on the copy stream while piece i+1 is
         // looked up (the D2H copy is 5x the kernel, so this hides the kernel, not the copy)
         const int parts = fetch && b->n_reads >= (1u << 16) ? 4 : 1;
         for (int i = 0; i < parts; ++i) {
             const uint32_t r0 = parts == 1 ? 0 : b->part_read[i], r1 = parts == 1 ? b->n_reads : b->part_read[i + 1];
             if (r1 > r0) {
-                pass4_apply_kernel<<<read_grid(ctx, r1 - r0), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), mv, b->d_newqual, r0, r1);
+                if (p4_smem)
+                    pass4_apply_kernel<true><<<p4_grid(r1 - r0), KBBQ_WARPS_PER_BLOCK * 32, p4_smem, ctx->stream>>>(b->view(), mv, ctx->n_rg, b->d_newqual, r0, r1);
+                else
+                    pass4_apply_kernel<false><<<read_grid(ctx, r1 - r0), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), mv, ctx->n_rg, b->d_newqual, r0, r1);
                 if (int rc = check_launch(ctx, "pass4_apply_kernel")) return rc;
             }
             if (parts > 1) {

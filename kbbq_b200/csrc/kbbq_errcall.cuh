@@ -391,7 +391,8 @@ struct ErrCaller {
 
     // One invocation of get_errors on `cur` (length cur.len), whose base 0 is base `base` of the top-level read.
     // Error flags live in sc.E at offset `base`.  Returns bad_prefix / bad_suffix for the caller's recursion test.
-    KBBQ_HD void call(const SeqRef& cur, int base, bool top, int& bad_prefix, int& bad_suffix, ErrResult& res) {
+    // `prescanned`: sc.T_orig already holds the trusted flag of every k-mer of `cur` (the scan kernel made them).
+    KBBQ_HD void call(const SeqRef& cur, int base, bool top, int& bad_prefix, int& bad_suffix, ErrResult& res, bool prescanned = false) {
         const int len = cur.len;
         bad_prefix = 0;
         bad_suffix = KBBQ_NPOS;
@@ -401,7 +402,7 @@ struct ErrCaller {
         for (int w = 0; w <= nw; ++w) sc.O_nm[w] = cur.nm[w];
         bool multiple = false;
         memo_reset();
-        scan(cur, sc.T_orig);
+        if (!prescanned) scan(cur, sc.T_orig);
         T = sc.T_orig;
         T_mirrored = false;
         int a0, a1;
@@ -440,7 +441,7 @@ struct ErrCaller {
                 T_mirrored = true;
                 anchor = len - a0 - 1;
             }
-            const SeqRef& s = side ? rc : cur;
+            const SeqRef s = side ? rc : cur;  // by value: a reference to one of two structs would pin both in local memory
             if (anchor_len - k + 1 >= k) {  // at least k trusted k-mers: the anchor's tail may be false positives
                 bool cm;
                 anchor = adjust_right_anchor(anchor, s, cm);  // ref quirk: ACGT order on both sides (readutils.cc:374)
@@ -558,7 +559,9 @@ struct ErrCaller {
     // Top level: get_errors(first_call=true) including the one-level recursion on a long bad prefix / suffix
     // (readutils.cc:547-563).  sc.P_* must hold the read, sc.QL its low-quality flags, sc.E must be zero.
     // On return sc.E holds read.errors.
-    KBBQ_HD ErrResult run(int len) {
+    // `prescanned`: see call(); applies to the whole read (job 0) only -- the sub-reads of the recursion are cut from
+    // the partly corrected read and scanned here.
+    KBBQ_HD ErrResult run(int len, bool prescanned = false) {
         ErrResult res;
         res.mod_idx = -1;
         res.mod_base = -1;
@@ -589,9 +592,12 @@ struct ErrCaller {
                 A.nm[nw] = 0;
             }
             int bp, bs;
-            ErrResult sub;
-            call(job ? A : P, from, job == 0, bp, bs, job ? sub : res);
-            if (job == 0) { top_prefix = bp; top_suffix = bs; }
+            ErrResult one;  // by value, like the sequence: references picked at run time would pin their targets in local memory
+            one.mod_idx = -1;
+            one.mod_base = -1;
+            const SeqRef cur = job ? A : P;
+            call(cur, from, job == 0, bp, bs, one, prescanned && job == 0);
+            if (job == 0) { top_prefix = bp; top_suffix = bs; res = one; }
         }
         return res;
     }

@@ -676,6 +676,55 @@ covariate_count_kernel(BatchView b, CountView cv, const uint32_t* __restrict__ e
 }
 
 // ---- pass 3: get_errors + consume_read (recalibrateutils.cc:42-89) ------------------------------------------------
+// Pass 3 runs as two kernels.
+//
+// pass3_scan_kernel -- the mandatory part of get_errors (bloom::find_longest_trusted_seq's walk, bloom.cc:96-128): the
+// trusted flag of EVERY k-mer of every read, with the warp-cooperative probe pass 2 uses (four lanes per 64-byte block,
+// all loads of a 32-k-mer query in flight together).  One lane per probe -- what the error caller uses for its sparse,
+// dependent questions -- touches 32 lines per warp load and reaches half the probe rate of the cooperative form once
+// the filter lives in HBM (tools/probe_ceiling.cu: 21.8 vs 42.6 G probes/s from a 1 GB table), and these 119 probes per
+// read are 2/3 of all of pass 3's.  A read whose k-mers are all trusted (readutils.cc:263-265) is finished here: its
+// flags are zero.  Every other read gets its k-mer flags written (tflags, one word per 32 k-mers in the batch's word
+// layout) and its index appended to the repair list.
+//
+// pass3_repair_kernel -- the rest of get_errors for the listed reads, one warp per read pulled from the list: anchors,
+// repairs, overcorrection check, the one-level recursion; it starts from the scan's flags instead of re-scanning.
+#ifndef KBBQ_P3_MIN_BLOCKS
+#define KBBQ_P3_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
+pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
+                  uint32_t* __restrict__ mod_out, uint32_t* __restrict__ repair_list, unsigned int* __restrict__ repair_count) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
+        const int len = (int)b.len[r];
+        const int nk = len - k + 1;
+        const uint32_t wo = b.word_off[r];
+        const int nw = (len + 31) >> 5;
+        bool all_trusted = true;
+        if (nk > 0) {
+            const CSeqRef s{b.bases + wo, b.nmask + wo, len};
+            for (int j0 = 0; j0 < nk; j0 += 32) {
+                const int j = j0 + lane;
+                uint64_t key = 0;
+                const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+                const uint32_t m = warp_bloom_query<true>(trusted, valid, key);
+                const int cnt = nk - j0 < 32 ? nk - j0 : 32;
+                all_trusted = all_trusted && m == (cnt < 32 ? (1u << cnt) - 1u : ~0u);
+                if (lane == 0) tflags[wo + (j0 >> 5)] = m;
+            }
+        }
+        // fewer than k bases (out of contract in the reference, bloom.cc:30): untouched, like a clean read
+        if (all_trusted || nk <= 0) {
+            if (lane < nw) err_out[wo + lane] = 0u;
+            if (lane == 0) mod_out[r] = 0xFFFFFFFFu;
+        } else if (lane == 0) {
+            repair_list[atomicAdd(repair_count, 1u)] = r;
+        }
+    }
+}
+
 // one copy of hash + 4 loads + compare for every question the error caller asks (it asks from five places)
 __device__ __noinline__ uint32_t probe_ballot(const BloomView* f, bool valid, uint64_t key) {
     return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(*f, key));
@@ -705,15 +754,15 @@ struct DevQuery {
     }
 };
 
-// 4 blocks/SM = 64 registers, 32 warps/SM: measured 21.2 ms vs 23.0 (unbounded, 80 regs) and 23.8 (5 blocks, spills)
-#ifndef KBBQ_P3_MIN_BLOCKS
-#define KBBQ_P3_MIN_BLOCKS 4
-#endif
 // Writes read.errors (err_out, kbbq_batch word layout) and, per read, the base get_errors left modified (mod_out, see
-// covariate_count_kernel); the counting itself is covariate_count_kernel's.
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
-pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ err_out, uint32_t* __restrict__ mod_out,
-                    unsigned int* __restrict__ work_counter) {
+// covariate_count_kernel) for the reads of the repair list; the counting itself is covariate_count_kernel's.
+#ifndef KBBQ_P3R_MIN_BLOCKS
+#define KBBQ_P3R_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3R_MIN_BLOCKS)
+pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
+                    uint32_t* __restrict__ mod_out, const uint32_t* __restrict__ repair_list,
+                    const unsigned int* __restrict__ repair_count, unsigned int* __restrict__ work_counter) {
     __shared__ ErrScratch scratch[KBBQ_WARPS_PER_BLOCK];
     __shared__ BloomView filter;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -721,12 +770,14 @@ pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict_
     if (threadIdx.x == 0) filter = trusted;
     __syncthreads();
     DevQuery q{&filter};
+    const uint32_t n_list = *repair_count;
     for (;;) {
-        // reads differ a lot in cost (most need only the mandatory scan, a few need ~1000 probes): pull, don't stride
-        uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(work_counter, 1u);
-        r = __shfl_sync(KBBQ_FULL, r, 0);
-        if (r >= b.n_reads) break;
+        // reads differ a lot in cost (a single repair to ~1000 probes): pull, don't stride
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(work_counter, 1u);
+        idx = __shfl_sync(KBBQ_FULL, idx, 0);
+        if (idx >= n_list) break;
+        const uint32_t r = repair_list[idx];
         const int len = (int)b.len[r];
         const uint32_t wo = b.word_off[r];
         const int nw = (len + 31) >> 5;
@@ -735,6 +786,7 @@ pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict_
             sc.P_w[lane] = lane < nw ? b.bases[wo + lane] : 0ull;
             sc.P_nm[lane] = lane < nw ? b.nmask[wo + lane] : 0u;
             sc.E[lane] = 0;
+            sc.T_orig[lane] = 32 * lane < len - k + 1 ? tflags[wo + lane] : 0u;  // the scan wrote one word per 32 k-mers
             // low-quality flags for the overcorrection half weight (bits past the read's end cleared)
             const int left = len - 32 * lane;
             sc.QL[lane] = lane < nw ? b.qmask[wo + lane].y & (left >= 32 ? ~0u : ((1u << left) - 1u)) : 0u;
@@ -742,7 +794,7 @@ pass3_errors_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict_
         __syncwarp();
         const bool has_n = __any_sync(KBBQ_FULL, lane < nw && sc.P_nm[lane] != 0u);
         ErrCaller<DevQuery> ec(q, k, qual, sc, has_n);
-        const ErrResult res = ec.run(len);
+        const ErrResult res = ec.run(len, true);
         __syncwarp();
         if (lane < nw) err_out[wo + lane] = sc.E[lane];
         if (lane == 0) mod_out[r] = res.mod_idx >= 0 ? (uint32_t)(4 * res.mod_idx + res.mod_base) : 0xFFFFFFFFu;
@@ -796,7 +848,16 @@ __device__ __forceinline__ P4Data p4_data(const BatchView& b, const P4Head& h, i
     }
     return d;
 }
-__device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Head& h, const P4Data& d, int i0, uint8_t* __restrict__ out) {
+// SMEM: the lookup tables live in shared memory (the launch checks that they fit): cy as it is, and `dib` = base + di
+// folded into one int16 table of 17 entries per row (entry 16 = no dinucleotide term), so a base costs two shared
+// loads instead of three dependent global ones (round 1: issue-bound at 76 %, 660 GB/s).
+struct P4Tables {
+    const int8_t* cy;
+    const int16_t* dib;
+};
+template <bool SMEM>
+__device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Tables& st, const P4Head& h, const P4Data& d, int i0,
+                                         uint8_t* __restrict__ out) {
     if (i0 >= h.len) return;
     uint32_t res[2] = {d.qq.x, d.qq.y};
 #pragma unroll
@@ -805,10 +866,15 @@ __device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Head& h, c
         const int qi = (int)((res[j >> 2] >> (8 * (j & 3))) & 255u);
         if (i < h.len && qi >= 6 && qi <= KBBQ_MAXQ) {  // minqual: lower qualities pass through unchanged (so does anything the tables cannot index)
             const size_t row = h.rgrow + qi;
-            int v = mv.base[row] + mv.cy[(row * 2 + h.sec) * (size_t)mv.max_cycle + i];
-            if (((d.nflags >> j) & 3u) == 0) {  // this base and the one before it are ACGT (and i > 0)
-                const uint32_t x = (d.codes >> (2 * j)) & 15u;  // previous base in the low pair
-                v += mv.di[row * 16 + (((x & 3u) << 2) | (x >> 2))];
+            const bool has_di = ((d.nflags >> j) & 3u) == 0;  // this base and the one before it are ACGT (and i > 0)
+            const uint32_t x = (d.codes >> (2 * j)) & 15u;    // previous base in the low pair
+            const uint32_t dn = ((x & 3u) << 2) | (x >> 2);
+            int v;
+            if (SMEM) {
+                v = st.cy[(row * 2 + h.sec) * (size_t)mv.max_cycle + i] + st.dib[row * 17 + (has_di ? dn : 16u)];
+            } else {
+                v = mv.base[row] + mv.cy[(row * 2 + h.sec) * (size_t)mv.max_cycle + i];
+                if (has_di) v += mv.di[row * 16 + dn];
             }
             v = v < 0 ? 0 : (v > KBBQ_MAXQ ? KBBQ_MAXQ : v);
             res[j >> 2] = (res[j >> 2] & ~(255u << (8 * (j & 3)))) | ((uint32_t)v << (8 * (j & 3)));
@@ -816,8 +882,29 @@ __device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Head& h, c
     }
     *reinterpret_cast<uint2*>(out + (size_t)h.wo * 32 + i0) = make_uint2(res[0], res[1]);
 }
+// bytes of shared memory the SMEM variant needs for n_rg read groups (0 when n_rg is unknown to the caller)
+__host__ __device__ inline size_t p4_smem_bytes(int n_rg, int max_cycle) {
+    const size_t cy = ((size_t)n_rg * KBBQ_NQ * 2 * max_cycle + 15) & ~(size_t)15;
+    return cy + (size_t)n_rg * KBBQ_NQ * 17 * 2;
+}
+template <bool SMEM>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32)
-pass4_apply_kernel(BatchView b, ModelView mv, uint8_t* __restrict__ out, uint32_t first_read, uint32_t end_read) {
+pass4_apply_kernel(BatchView b, ModelView mv, int n_rg, uint8_t* __restrict__ out, uint32_t first_read, uint32_t end_read) {
+    extern __shared__ __align__(16) unsigned char p4_smem[];
+    P4Tables st{nullptr, nullptr};
+    if (SMEM) {
+        const size_t n_cy = (size_t)n_rg * KBBQ_NQ * 2 * mv.max_cycle, cy_bytes = (n_cy + 15) & ~(size_t)15;
+        int8_t* cy = reinterpret_cast<int8_t*>(p4_smem);
+        int16_t* dib = reinterpret_cast<int16_t*>(p4_smem + cy_bytes);
+        for (size_t i = threadIdx.x; i < n_cy; i += blockDim.x) cy[i] = mv.cy[i];
+        for (int i = threadIdx.x; i < n_rg * KBBQ_NQ * 17; i += blockDim.x) {
+            const int row = i / 17, dd = i - row * 17;
+            dib[i] = (int16_t)(mv.base[row] + (dd < 16 ? mv.di[row * 16 + dd] : 0));
+        }
+        __syncthreads();
+        st.cy = cy;
+        st.dib = dib;
+    }
     const int lane = threadIdx.x & 31;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp = first_read + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -829,8 +916,8 @@ pass4_apply_kernel(BatchView b, ModelView mv, uint8_t* __restrict__ out, uint32_
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
         const P4Head h2 = p4_head(b, r + 2 * nwarps);  // header two reads ahead
         const P4Data d1 = p4_data(b, h1, 8 * lane);    // words one read ahead
-        p4_apply(mv, h0, d0, 8 * lane, out);
-        for (int i0 = 256 + 8 * lane; i0 < h0.len; i0 += 256) p4_apply(mv, h0, p4_data(b, h0, i0), i0, out);  // reads > 256 bases
+        p4_apply<SMEM>(mv, st, h0, d0, 8 * lane, out);
+        for (int i0 = 256 + 8 * lane; i0 < h0.len; i0 += 256) p4_apply<SMEM>(mv, st, h0, p4_data(b, h0, i0), i0, out);  // reads > 256 bases
         h0 = h1; h1 = h2; d0 = d1;
     }
 }
