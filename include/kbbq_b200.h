@@ -202,8 +202,23 @@ int kbbq_consume_errors(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* err
 /* the same for the first n_first reads of the batch only: main()'s loop stops consuming where the shorter of the two
  * files ends (kbbq.cc:370) */
 int kbbq_consume_errors_n(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* err_bits, uint32_t n_first);
+/* --fixed mode with both files resident (kbbq.cc:367-378): flags base i of read r of `b` when it differs from base i
+ * of read r of `fixed` (std::not_equal_to<char> over read.seq; bases beyond the shorter of the two reads are error-free,
+ * where the reference reads past the end), then CCovariateData::consume_read for the first n_first reads.  Packed
+ * batches compare letters up to case and up to WHICH non-ACGT letter a base is: a host that must tell 'a' from 'A' or
+ * 'N' from 'R' compares characters itself and calls kbbq_consume_errors_n.  err_bits (host, may be NULL) as above. */
+int kbbq_fixed_errors(kbbq_ctx* ctx, const kbbq_dbatch* b, const kbbq_dbatch* fixed, uint32_t n_first, uint32_t* err_bits);
+/* the coverage-estimation pass (kbbq.cc:229-236): total sequence length of a resident batch */
+int kbbq_batch_total_bases(kbbq_ctx* ctx, const kbbq_dbatch* b, uint64_t* total);
 int kbbq_covariates_reset(kbbq_ctx* ctx);
 int kbbq_covariates_download(kbbq_ctx* ctx, uint64_t* rgc, uint64_t* qc, uint64_t* cyc, uint64_t* dic);
+/* GATK-style text report of the four count tables ("#:GATKReport.v1.1:3": RecalTable0 per read group, RecalTable1 per
+ * read group x quality, RecalTable2 cycle and dinucleotide-context rows; observed rows only) -- what the reference's
+ * unused include/kbbq/gatkreport.hh:1-295 was written for.  rg_names[n_rg] may be NULL (rg<id>).  The _host form
+ * formats dense tables laid out as above and needs no GPU. */
+int kbbq_covariates_report(kbbq_ctx* ctx, const char* path, const char* const* rg_names);
+int kbbq_report_tables_host(const char* path, int n_rg, int max_cycle, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc,
+                            const uint64_t* dic, const char* const* rg_names);
 /* device pointer + size in uint64 words of the four count tables laid out back to back (for a sum all-reduce) */
 void* kbbq_covariates_device(kbbq_ctx* ctx, uint64_t* n_words);
 /* CCovariateData::get_dqs (covariateutils.cc:204-230) on the context's tables; installs the lookup tables.

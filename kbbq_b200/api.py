@@ -127,6 +127,10 @@ def lib():
         L.kbbq_pass4_recalibrate.argtypes = [vp, vp, vp]
         L.kbbq_batch_device_newqual.restype = vp
         L.kbbq_batch_device_newqual.argtypes = [vp]
+        L.kbbq_covariates_report.argtypes = [vp, C.c_char_p, vp]
+        L.kbbq_report_tables_host.argtypes = [C.c_char_p, i32, i32, vp, vp, vp, vp, vp]
+        L.kbbq_fixed_errors.argtypes = [vp, vp, vp, u32, vp]
+        L.kbbq_batch_total_bases.argtypes = [vp, vp, C.POINTER(u64)]
         L.kbbq_bloom_digest.argtypes = [vp, i32, vp]
         L.kbbq_covariates_digest.argtypes = [vp, vp]
         L.kbbq_batch_newqual_digest.argtypes = [vp, vp, vp]
@@ -209,6 +213,16 @@ def digest_words(words: np.ndarray) -> tuple:
             s = s + h.sum(dtype=np.uint64)
             x = x ^ np.bitwise_xor.reduce(h)
     return int(s), int(x)
+
+
+def report_tables(path: str, rgc, qc, cyc, dic, rg_names=None) -> None:
+    """GATK-style report of dense count tables (host only)"""
+    R, ml = rgc.shape[0], cyc.shape[3]
+    arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (rgc, qc, cyc, dic)]
+    names = None
+    if rg_names is not None:
+        names = (C.c_char_p * R)(*[n.encode() for n in rg_names])
+    _check(lib().kbbq_report_tables_host(os.fsencode(path), R, ml, *[_p(a) for a in arrs], names))
 
 
 def synth_host(params: SynthParams, first_read: int, n_reads: int, n_threads: int = 8):
@@ -523,6 +537,24 @@ class Context:
 
     def consume_errors(self, db: "DeviceBatch", bits: np.ndarray):
         _check(self.L.kbbq_consume_errors(self.h, db.h, _p(np.ascontiguousarray(bits, dtype=np.uint32))))
+
+    def fixed_errors(self, db: "DeviceBatch", fixed: "DeviceBatch", n_first: int | None = None, want_errors: bool = False):
+        """--fixed mode on the device: flags = `db` differs from `fixed`, then consume the first n_first reads"""
+        n = min(db.pb.n_reads, fixed.pb.n_reads) if n_first is None else n_first
+        bits = np.zeros(max(db.pb.n_words, 1), dtype=np.uint32) if want_errors else None
+        _check(self.L.kbbq_fixed_errors(self.h, db.h, fixed.h, n, _p(bits)))
+        return bits
+
+    def total_bases(self, db: "DeviceBatch") -> int:
+        v = C.c_uint64(0)
+        _check(self.L.kbbq_batch_total_bases(self.h, db.h, C.byref(v)))
+        return int(v.value)
+
+    def covariates_report(self, path: str, rg_names=None):
+        names = None
+        if rg_names is not None:
+            names = (C.c_char_p * self.n_rg)(*[n.encode() for n in rg_names])
+        _check(self.L.kbbq_covariates_report(self.h, os.fsencode(path), names))
 
     def covariates_reset(self):
         _check(self.L.kbbq_covariates_reset(self.h))

@@ -1365,6 +1365,44 @@ int kbbq_consume_errors_n(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* 
     return KBBQ_OK;
 }
 
+int kbbq_fixed_errors(kbbq_ctx* ctx, const kbbq_dbatch* cb, const kbbq_dbatch* fixed, uint32_t n_first, uint32_t* err_bits) {
+    if (int rc = use(ctx)) return rc;
+    kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
+    if (!b || !fixed) return fail(KBBQ_EINVAL, "null argument");
+    if (n_first > b->n_reads || n_first > fixed->n_reads) return fail(KBBQ_EINVAL, "n_first exceeds a batch");
+    if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+    if (int rc = need_quals(ctx, b)) return rc;
+    pass_begin(ctx);
+    if (b->n_reads) {
+        mark_kernel(ctx, "fixed_diff_kernel");
+        fixed_diff_kernel<<<read_grid(ctx, b->n_reads), 256, 0, ctx->stream>>>(b->view(), fixed->view(), n_first, b->d_err_bits);
+        if (int rc = check_launch(ctx, "fixed_diff_kernel")) return rc;
+    }
+    if (n_first) {
+        mark_kernel(ctx, "covariate_count_kernel");
+        if (int rc = launch_count(ctx, b, b->d_err_bits, nullptr, n_first)) return rc;
+    }
+    pass_end(ctx);
+    return fetch_bits(ctx, b, err_bits);
+}
+
+int kbbq_batch_total_bases(kbbq_ctx* ctx, const kbbq_dbatch* b, uint64_t* total) {
+    if (int rc = use(ctx)) return rc;
+    if (!b || !total) return fail(KBBQ_EINVAL, "null argument");
+    unsigned long long* d = nullptr;
+    CU(cudaMallocAsync(&d, 8, ctx->stream));
+    CU(cudaMemsetAsync(d, 0, 8, ctx->stream));
+    if (b->n_reads) {
+        const int grid = (int)std::min<uint64_t>(((uint64_t)b->n_reads + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        total_bases_kernel<<<grid, 256, 0, ctx->stream>>>(b->d_len, b->n_reads, d);
+        if (int rc = check_launch(ctx, "total_bases_kernel")) return rc;
+    }
+    CU(cudaMemcpyAsync(total, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaFreeAsync(d, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
 int kbbq_covariates_reset(kbbq_ctx* ctx) {
     if (int rc = use(ctx)) return rc;
     CU(cudaMemsetAsync(ctx->d_counts, 0, ctx->n_counts() * 8, ctx->stream));
@@ -1380,6 +1418,23 @@ int kbbq_covariates_download(kbbq_ctx* ctx, uint64_t* rgc, uint64_t* qc, uint64_
     if (dic) CU(cudaMemcpyAsync(dic, c.dic, ctx->n_dic * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return KBBQ_OK;
+}
+
+int kbbq_report_tables_host(const char* path, int n_rg, int max_cycle, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc,
+                            const uint64_t* dic, const char* const* rg_names) {
+    if (!path || !rgc || !qc || !cyc || !dic || n_rg < 1 || max_cycle < 1) return fail(KBBQ_EINVAL, "bad argument");
+    if (!host::write_gatk_report(path, n_rg, max_cycle, rgc, qc, cyc, dic, rg_names)) return fail(KBBQ_EINVAL, std::string("cannot write ") + path);
+    return KBBQ_OK;
+}
+
+int kbbq_covariates_report(kbbq_ctx* ctx, const char* path, const char* const* rg_names) {
+    if (int rc = use(ctx)) return rc;
+    std::vector<uint64_t> counts(ctx->n_counts());
+    CU(cudaMemcpyAsync(counts.data(), ctx->d_counts, counts.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const uint64_t* rgc = counts.data();
+    return kbbq_report_tables_host(path, ctx->n_rg, ctx->max_cycle, rgc, rgc + ctx->n_rgc, rgc + ctx->n_rgc + ctx->n_qc,
+                                   rgc + ctx->n_rgc + ctx->n_qc + ctx->n_cyc, rg_names);
 }
 
 void* kbbq_covariates_device(kbbq_ctx* ctx, uint64_t* n_words) {

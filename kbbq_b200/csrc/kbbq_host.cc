@@ -1,6 +1,9 @@
 // kbbq_host.cc -- see kbbq_host.h.  Compiled with -ffp-contract=off: results must not depend on FMA availability.
 #include "kbbq_host.h"
 
+#include <cstdio>
+#include <string>
+
 #include <algorithm>
 #include <cerrno>
 #include <cmath>
@@ -358,6 +361,92 @@ void fit_model(int R, int L, const uint64_t* rgc, const uint64_t* qc, const uint
         }
         for (auto& t : th) t.join();
     }
+}
+
+// ---- GATK-style report -------------------------------------------------------------------------------------------------
+namespace {
+struct ReportRow {
+    std::vector<std::string> cell;
+};
+void write_table(FILE* fh, const char* name, const char* fmt_line, const std::vector<std::string>& head, const std::vector<ReportRow>& rows) {
+    std::vector<size_t> w(head.size());
+    for (size_t c = 0; c < head.size(); ++c) w[c] = head[c].size();
+    for (const ReportRow& r : rows)
+        for (size_t c = 0; c < head.size(); ++c) w[c] = std::max(w[c], r.cell[c].size());
+    fprintf(fh, "#:GATKTable:%zu:%zu:%s:;\n#:GATKTable:%s:\n", head.size(), rows.size(), fmt_line, name);
+    for (size_t c = 0; c < head.size(); ++c) fprintf(fh, "%-*s%s", (int)w[c], head[c].c_str(), c + 1 < head.size() ? "  " : "\n");
+    for (const ReportRow& r : rows)
+        for (size_t c = 0; c < head.size(); ++c) {
+            // strings left aligned, numbers right aligned, like GATK's reports
+            const bool text = c < 2 || head[c] == "CovariateValue" || head[c] == "CovariateName" || head[c] == "EventType";
+            fprintf(fh, text ? "%-*s%s" : "%*s%s", (int)w[c], r.cell[c].c_str(), c + 1 < head.size() ? "  " : "\n");
+        }
+    fputc('\n', fh);
+}
+std::string fixed(double v, int digits) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.*f", digits, v);
+    return buf;
+}
+// GATK's empirical quality: -10 log10((errors + 1) / (observations + 2)), capped at 93
+double empirical_q(uint64_t errors, uint64_t obs) {
+    const double q = -10.0 * std::log10(((double)errors + 1.0) / ((double)obs + 2.0));
+    return q > 93.0 ? 93.0 : q;
+}
+}  // namespace
+
+bool write_gatk_report(const char* path, int R, int C, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc, const uint64_t* dic,
+                       const char* const* rg_names) {
+    FILE* fh = fopen(path, "w");
+    if (!fh) return false;
+    auto rgname = [&](int r) { return rg_names && rg_names[r] ? std::string(rg_names[r]) : "rg" + std::to_string(r); };
+    fprintf(fh, "#:GATKReport.v1.1:3\n");
+    {
+        std::vector<ReportRow> rows;
+        for (int r = 0; r < R; ++r) {
+            const uint64_t err = rgc[2 * r], obs = rgc[2 * r + 1];
+            if (!obs) continue;
+            long double expected = 0;  // errors the reported qualities predict: sum over q of n_q * 10^(-q/10)
+            for (int q = 0; q < 94; ++q) expected += (long double)qc[((size_t)r * 94 + q) * 2 + 1] * std::pow(10.0l, -(long double)q / 10.0l);
+            const double est = expected > 0 ? (double)(-10.0l * std::log10(expected / (long double)obs)) : 93.0;
+            rows.push_back({{rgname(r), "M", fixed(empirical_q(err, obs), 4), fixed(est, 4), std::to_string(obs), fixed((double)err, 2)}});
+        }
+        write_table(fh, "RecalTable0", "%s:%s:%.4f:%.4f:%d:%.2f",
+                    {"ReadGroup", "EventType", "EmpiricalQuality", "EstimatedQReported", "Observations", "Errors"}, rows);
+    }
+    {
+        std::vector<ReportRow> rows;
+        for (int r = 0; r < R; ++r)
+            for (int q = 0; q < 94; ++q) {
+                const uint64_t err = qc[((size_t)r * 94 + q) * 2], obs = qc[((size_t)r * 94 + q) * 2 + 1];
+                if (!obs) continue;
+                rows.push_back({{rgname(r), std::to_string(q), "M", fixed(empirical_q(err, obs), 4), std::to_string(obs), fixed((double)err, 2)}});
+            }
+        write_table(fh, "RecalTable1", "%s:%s:%s:%.4f:%d:%.2f",
+                    {"ReadGroup", "QualityScore", "EventType", "EmpiricalQuality", "Observations", "Errors"}, rows);
+    }
+    {
+        std::vector<ReportRow> rows;
+        for (int r = 0; r < R; ++r)
+            for (int q = 0; q < 94; ++q) {
+                for (int d = 0; d < 16; ++d) {  // dinucleotide context: previous base, this base
+                    const uint64_t* c = dic + (((size_t)r * 94 + q) * 16 + d) * 2;
+                    if (!c[1]) continue;
+                    const std::string ctx{"ACGT"[d >> 2], "ACGT"[d & 3]};
+                    rows.push_back({{rgname(r), std::to_string(q), ctx, "Context", "M", fixed(empirical_q(c[0], c[1]), 4), std::to_string(c[1]), fixed((double)c[0], 2)}});
+                }
+                for (int sec = 0; sec < 2; ++sec)  // cycle: 1-based, negative for the second read of a pair (GATK's convention)
+                    for (int i = 0; i < C; ++i) {
+                        const uint64_t* c = cyc + ((((size_t)r * 94 + q) * 2 + sec) * C + i) * 2;
+                        if (!c[1]) continue;
+                        rows.push_back({{rgname(r), std::to_string(q), std::to_string(sec ? -(i + 1) : i + 1), "Cycle", "M", fixed(empirical_q(c[0], c[1]), 4),
+                                         std::to_string(c[1]), fixed((double)c[0], 2)}});
+                    }
+            }
+        write_table(fh, "RecalTable2", "%s:%s:%s:%s:%s:%.4f:%d:%.2f",
+                    {"ReadGroup", "QualityScore", "CovariateValue", "CovariateName", "EventType", "EmpiricalQuality", "Observations", "Errors"}, rows);
+    }
+    return fclose(fh) == 0;
 }
 
 }  // namespace host

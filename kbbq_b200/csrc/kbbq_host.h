@@ -61,6 +61,13 @@ void rng_advance(uint64_t state[4], uint64_t steps);  // O(popcount(steps)) matr
 void fit_model(int R, int max_cycle, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc, const uint64_t* dic,
                int32_t* meanq, int32_t* rgdq, int32_t* qdq, int32_t* cydq, int32_t* didq, int n_threads);
 
+// ---- GATK-style recalibration report of the count tables (the intent of the reference's unused gatkreport.hh) ----
+// Writes "#:GATKReport.v1.1:3": RecalTable0 (per read group), RecalTable1 (per read group x quality), RecalTable2
+// (cycle and dinucleotide context rows) with Observations / Errors / EmpiricalQuality columns; only rows that were
+// observed.  rg_names may be null (rg<id> is used).  Returns false when the file cannot be written.
+bool write_gatk_report(const char* path, int R, int max_cycle, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc,
+                       const uint64_t* dic, const char* const* rg_names);
+
 // ---- packing ASCII reads into 2-bit words (the host feeder's inner loop) ----
 // seq_nt16_int[seq_nt16_table[ch]] (bloom.hh:351): 0..3 for ACGTacgt0123, 4 otherwise
 int nt4(unsigned char ch);

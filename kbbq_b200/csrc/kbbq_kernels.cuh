@@ -953,6 +953,51 @@ __global__ void bloom_query_keys_kernel(BloomView f, const unsigned long long* _
     if (i < n) hits[i] = bloom_contains_dev(f, keys[i]) ? 1 : 0;
 }
 
+// ---- --fixed mode (kbbq.cc:367-378): a base is an error when it differs from the same base of the pre-corrected read ----
+// gather the even bits of a 64-bit word into 32 bits
+__device__ __forceinline__ uint32_t even_bits(unsigned long long x) {
+    x &= 0x5555555555555555ull;
+    x = (x | (x >> 1)) & 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+    return (uint32_t)x;
+}
+// One warp per read, one lane per 32-base word.  Read r of `a` is compared with read r of `f` over the bases both have
+// (the reference's std::transform runs over read.seq and reads past the end of a shorter fixed read: undefined there,
+// error-free here); packed form compares letters up to case and up to which non-ACGT letter a base is.
+__global__ void __launch_bounds__(256) fixed_diff_kernel(BatchView a, BatchView f, uint32_t n_first, uint32_t* __restrict__ err_out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < a.n_reads; r += nwarps) {
+        const int la = (int)a.len[r];
+        const uint32_t wa = a.word_off[r];
+        const int lf = r < n_first && r < f.n_reads ? (int)f.len[r] : 0;
+        const uint32_t wf = lf ? f.word_off[r] : 0u;
+        const int both = la < lf ? la : lf;
+        for (int w = lane; 32 * w < la; w += 32) {
+            uint32_t m = 0;
+            const int left = both - 32 * w;
+            if (left > 0) {
+                const unsigned long long x = a.bases[wa + w] ^ f.bases[wf + w];
+                const uint32_t na = a.nmask[wa + w], nf = f.nmask[wf + w];
+                m = ((even_bits(x | (x >> 1)) & ~na & ~nf) | (na ^ nf)) & (left >= 32 ? ~0u : (1u << left) - 1u);
+            }
+            err_out[wa + w] = m;
+        }
+    }
+}
+
+// ---- coverage estimation (kbbq.cc:229-236): total sequence length of a batch ----------------------------------------
+__global__ void __launch_bounds__(256) total_bases_kernel(const uint32_t* __restrict__ len, uint32_t n, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += len[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(KBBQ_FULL, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
 // ---- order-independent digest of a word array: {sum, xor} of mix(word ^ mix(index)) -- equality checks across ranks/runs
 __device__ __forceinline__ unsigned long long digest_mix(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;

@@ -373,3 +373,29 @@ def test_filter_save_and_load_round_trip(tmp_path):
         b.bloom_load(api.FILTER_SAMPLED, path)
     db.free()
     b.close()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_fixed_mode_on_the_device_matches_port(ragged):
+    """kbbq_fixed_errors: the --fixed comparison (kbbq.cc:367-378) as a kernel over two resident batches -- flags and
+    tables against the oracle fed with the character comparison; the fixed file may end early (n_first)."""
+    kw = dict(ragged=True, min_len=40) if ragged else {}
+    rs = synth.make_reads(50000, 20, 100, seed=6, n_rg=2, n_frac=0.003, **kw)
+    fx = synth.ReadSet(seq=rs.clean_seq, off=rs.off, qual=rs.qual, rg=rs.rg, second=rs.second, n_rg=rs.n_rg)
+    n_first = rs.n - 37
+    errors = (rs.seq != rs.clean_seq).astype(np.uint8)
+    first = rs.subset(0, n_first)
+    want = P.PortPipeline(first, 32).consume(errors[: first.total_bases], maxlen=rs.max_len)
+    ctx = api.Context(32, rs.n_rg, rs.max_len)
+    pb, pf = api.PackedBatch(rs), api.PackedBatch(fx)
+    db, df = ctx.upload(pb), ctx.upload(pf)
+    bits = ctx.fixed_errors(db, df, n_first, want_errors=True)
+    flags = pb.unpack_bits(bits, rs.total_bases)
+    assert np.array_equal(flags[: first.total_bases], errors[: first.total_bases])
+    assert not flags[first.total_bases :].any()  # reads without a partner carry no flags
+    for a, b in zip(ctx.covariates(), want):
+        assert np.array_equal(a, b)
+    assert ctx.total_bases(db) == rs.total_bases and ctx.total_bases(df) == rs.total_bases
+    db.free()
+    df.free()
+    ctx.close()
