@@ -153,6 +153,8 @@ struct kbbq_dbatch {
     unsigned long long* d_slot_off = nullptr;
     uint32_t* d_sample_bits = nullptr;
     uint32_t* d_err_bits = nullptr;
+    uint32_t* d_word_read = nullptr;  // read index of every word (flat traversal), made on demand for non-uniform batches
+    uint32_t uniform_wpr = 0;         // words per read when every read occupies the same number of words, else 0
     uint32_t* d_tflags = nullptr;  // pass 3: trusted flag of every k-mer (word layout), scan -> repair
     uint32_t* d_repair = nullptr;  // pass 3: indices of the reads the scan could not finish
     uint32_t* d_mod = nullptr;  // per read: the base get_errors left modified, or 0xFFFFFFFF (see covariate_count_kernel)
@@ -230,10 +232,24 @@ int check_launch(kbbq_ctx* ctx, const char* what) {
     return KBBQ_OK;
 }
 
+// the read of every word, for the flat traversal of batches whose reads differ in word count (made once per batch)
+int flat_map(kbbq_ctx* ctx, kbbq_dbatch* b, FlatMap& fm) {
+    fm.word_read = nullptr;
+    fm.wpr = b->uniform_wpr ? b->uniform_wpr : 1;
+    if (b->uniform_wpr || !b->n_reads) return KBBQ_OK;
+    if (!b->d_word_read) {
+        CU(cudaMallocAsync(&b->d_word_read, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
+        word_read_kernel<<<(b->n_reads + 255) / 256, 256, 0, ctx->stream>>>(b->d_word_off, b->n_reads, b->d_word_read);
+        if (int rc = check_launch(ctx, "word_read_kernel")) return rc;
+    }
+    fm.word_read = b->d_word_read;
+    return KBBQ_OK;
+}
+
 // covariate_count_kernel: rows of the block-private table that fit beside a second resident block, and the launch(es)
-int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, const uint32_t* d_mod, uint32_t n_reads) {
-    const int row_cells = KBBQ_HIST_FIXED + 4 * ctx->max_cycle;
-    const long long fixed_words = KBBQ_HIST_DIRECT_RG * KBBQ_NQ + 2 + 2 * KBBQ_HIST_RG;
+int launch_count(kbbq_ctx* ctx, kbbq_dbatch* b, const uint32_t* d_err, const uint32_t* d_mod, uint32_t n_first) {
+    const int row_cells = 4 * ctx->max_cycle + 32;
+    const long long fixed_words = KBBQ_HIST_DIRECT_RG * KBBQ_NQ + 2;
     const long long budget_words = (108 * 1024) / 4 - fixed_words;  // 2 blocks/SM inside the 227 KB of an SM
     int S = (int)std::max(0ll, std::min(64ll, budget_words / (row_cells + 1)));
     if (const char* e = getenv("KBBQ_HIST_S")) S = std::min(S, atoi(e));  // measurement override
@@ -242,15 +258,17 @@ int launch_count(kbbq_ctx* ctx, const kbbq_dbatch* b, const uint32_t* d_err, con
         CU(cudaFuncSetAttribute(covariate_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         ctx->count_attr_set = true;
     }
-    const int warps_per_block = KBBQ_HIST_THREADS / 32;
-    const long long need = ((long long)n_reads + warps_per_block - 1) / warps_per_block;
+    FlatMap fm;
+    if (int rc = flat_map(ctx, b, fm)) return rc;
+    const unsigned long long n_half = (unsigned long long)b->n_words * 2;
+    const long long need = (long long)((n_half + KBBQ_HIST_THREADS - 1) / KBBQ_HIST_THREADS);
     const int grid = (int)std::max(1ll, std::min(need, (long long)ctx->sm_count * 2));
-    // a block's 32-bit cells must not overflow: at most 2^22 reads (of <= 512 bases) per block and launch
-    const uint64_t per_launch = (uint64_t)grid << 22;
-    for (uint64_t first = 0; first < n_reads; first += per_launch) {
-        const uint32_t end = (uint32_t)std::min<uint64_t>(n_reads, first + per_launch);
-        covariate_count_kernel<<<grid, KBBQ_HIST_THREADS, smem, ctx->stream>>>(b->view(), ctx->counts(), d_err, d_mod,
-                                                                               (uint32_t)first, end, S);
+    // a block's 32-bit cells must not overflow: a half word adds at most 16 to a cell, so at most 2^26 half words per
+    // block and launch
+    const unsigned long long per_launch = (unsigned long long)grid << 26;
+    for (unsigned long long first = 0; first < n_half; first += per_launch) {
+        const unsigned long long end = std::min(n_half, first + per_launch);
+        covariate_count_kernel<<<grid, KBBQ_HIST_THREADS, smem, ctx->stream>>>(b->view(), fm, ctx->counts(), d_err, d_mod, first, end, n_first, S);
         if (int rc = check_launch(ctx, "covariate_count_kernel")) return rc;
     }
     return KBBQ_OK;
@@ -1007,7 +1025,7 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaStream_t st = ctx ? ctx->stream : nullptr;
     void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_qmask, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
-                    b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual, b->d_tflags, b->d_repair};
+                    b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual, b->d_tflags, b->d_repair, b->d_word_read};
     if (b->qual_ready) {
         if (ctx && !b->qual_waited) cudaStreamWaitEvent(st, b->qual_ready, 0);  // d_qual is freed in `st`'s order
         cudaEventDestroy(b->qual_ready);
@@ -1109,11 +1127,15 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
         unsigned long long slots = 0;
         uint32_t longest = 0, biggest_rg = 0;
         const uint32_t km1 = (uint32_t)ctx->k - 1;
+        bool uniform = n > 0;
+        const uint32_t wpr0 = n ? (h->len[0] + 31) / 32 : 0;
         for (uint32_t r = 0; r < n; ++r) {
             const uint32_t l = h->len[r];
             longest = std::max(longest, l);
             slots += l > km1 ? l - km1 : 0;
+            uniform = uniform && (l + 31) / 32 == wpr0 && h->word_off[r] == r * wpr0;
         }
+        b->uniform_wpr = uniform && wpr0 ? wpr0 : 0;
         if (h->rg)
             for (uint32_t r = 0; r < n; ++r) biggest_rg = std::max<uint32_t>(biggest_rg, h->rg[r]);
         b->n_slots = slots;
@@ -1509,25 +1531,26 @@ int kbbq_pass4_recalibrate(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint8_t* qual_o
             CU(cudaFuncSetAttribute(pass4_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
             ctx->p4_attr_set = true;
         }
+        FlatMap fm;
+        if (int rc = flat_map(ctx, b, fm)) return rc;
         const int blocks_per_sm = p4_smem ? (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (p4_smem + 1024))) : 8;
-        auto p4_grid = [&](uint32_t n_reads) {
-            const long long need = ((long long)n_reads + KBBQ_WARPS_PER_BLOCK - 1) / KBBQ_WARPS_PER_BLOCK;
+        auto p4_grid = [&](unsigned long long n_half) {
+            const long long need = (long long)((n_half + 255) / 256);
             return (int)std::max(1ll, std::min(need, (long long)ctx->sm_count * blocks_per_sm));
         };
         // with a host destination the batch goes in four pieces: piece i travels on the copy stream while piece i+1 is
-        // looked up (the D2H copy is 5x the kernel, so this hides the kernel, not the copy)
+        // looked up (the D2H copy is several times the kernel, so this hides the kernel, not the copy)
         const int parts = fetch && b->n_reads >= (1u << 16) ? 4 : 1;
         for (int i = 0; i < parts; ++i) {
-            const uint32_t r0 = parts == 1 ? 0 : b->part_read[i], r1 = parts == 1 ? b->n_reads : b->part_read[i + 1];
-            if (r1 > r0) {
+            const uint64_t w0 = parts == 1 ? 0 : b->part_word[i], w1 = parts == 1 ? b->n_words : b->part_word[i + 1];
+            if (w1 > w0) {
                 if (p4_smem)
-                    pass4_apply_kernel<true><<<p4_grid(r1 - r0), KBBQ_WARPS_PER_BLOCK * 32, p4_smem, ctx->stream>>>(b->view(), mv, ctx->n_rg, b->d_newqual, r0, r1);
+                    pass4_apply_kernel<true><<<p4_grid(2 * (w1 - w0)), 256, p4_smem, ctx->stream>>>(b->view(), fm, mv, ctx->n_rg, b->d_newqual, 2 * w0, 2 * w1);
                 else
-                    pass4_apply_kernel<false><<<read_grid(ctx, r1 - r0), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), mv, ctx->n_rg, b->d_newqual, r0, r1);
+                    pass4_apply_kernel<false><<<p4_grid(2 * (w1 - w0)), 256, 0, ctx->stream>>>(b->view(), fm, mv, ctx->n_rg, b->d_newqual, 2 * w0, 2 * w1);
                 if (int rc = check_launch(ctx, "pass4_apply_kernel")) return rc;
             }
             if (parts > 1) {
-                const uint64_t w0 = b->part_word[i], w1 = b->part_word[i + 1];
                 CU(cudaEventRecord(ctx->evp[i], ctx->stream));
                 CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->evp[i], 0));
                 if (w1 > w0)
@@ -1622,6 +1645,7 @@ int kbbq_synth_batch(kbbq_ctx* ctx, const kbbq_synth_params* p, uint64_t first_r
         CU(cudaMemsetAsync(b->d_slot_off, 0, 8, ctx->stream));
     }
     b->n_slots = (int)s.read_len >= ctx->k ? (uint64_t)n_reads * (s.read_len - ctx->k + 1) : 0;
+    b->uniform_wpr = n_reads ? wpr : 0;
     CU(cudaStreamSynchronize(ctx->stream));
     *out = b;
     return KBBQ_OK;

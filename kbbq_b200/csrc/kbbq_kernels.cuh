@@ -492,185 +492,198 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
     if (lane == 0 && inserted) atomicAdd(trusted.inserted, inserted);
 }
 
-// ---- covariate counting: CCovariateData::consume_read (covariateutils.cc:30-42,65-76,102-116,147-164,193-202) -------
-// Every base adds to three tables ({errors,total} of its read group x quality, of that row's cycle cell, of that
-// row's dinucleotide cell) and the tables are small and hot: binned qualities put half of all bases on one row.  Sent
-// to global memory that is ~700 M RED operations per 230 Mbases, serialised per address in L2 (measured: 10 ms of a
-// 20 ms pass).  Here each block keeps an associative set of S rows in shared memory -- one row = everything keyed by
-// (read group, quality): its q pair, 16 dinucleotide pairs and 2 x C cycle pairs -- counts there with 32-bit shared
-// atomics, and flushes the rows it used with 64-bit global atomics when it retires.  A row that finds no free slot
-// (or belongs to a read group beyond the direct table) falls through to global atomics, so any input stays exact.  The launch bounds the reads per block so that no 32-bit
-// cell can overflow.
-#define KBBQ_HIST_THREADS 512
-#define KBBQ_HIST_RG 64            // read groups whose {errors,total} pair is privatised too
-#define KBBQ_HIST_EMPTY 0xFFFFFFFFu
-#define KBBQ_HIST_FIXED 34         // cells of a row before the cycle cells: q pair, 16 dinuc errors, 16 dinuc totals
+// ---- the flat traversal shared by covariate counting and pass 4 -----------------------------------------------------
+// Both kernels are streaming passes over every base with a little per-read context.  One THREAD takes one half word --
+// 16 consecutive bases of one read: a 16-byte load of qualities, the word's 2-bit bases and N flags, the read's group
+// and pair flag -- so a warp instruction covers 512 bases whatever the read length (one warp per read left 13 of 32
+// lanes idle on 150-base reads and a third of the issue slots in shuffles).  The read a word belongs to is word / wpr
+// for batches whose reads all occupy the same number of words (the launch checks), else looked up in word_read.
+struct FlatMap {
+    const uint32_t* word_read;  // [n_words] read index of every word, or nullptr: uniform batch
+    uint32_t wpr;               // words per read of a uniform batch
+};
+struct HalfWord {
+    uint32_t r, wo, gw;
+    int i0, len, sec, o;        // first base of the half word in the read, read length, pair flag, offset in the word (0/16)
+    uint32_t rgrow;             // rg * 94
+    unsigned long long codes;   // 17 bases: the one before the half word, then its 16 (2 bits each from bit 0)
+    uint32_t nflags;            // 17 N flags likewise; bit 0 also set when there is no base before (i0 == 0)
+    uint4 q;                    // 16 quality bytes
+};
+__device__ __forceinline__ bool load_half_word(const BatchView& b, const FlatMap& fm, unsigned long long h, unsigned long long n_half,
+                                               HalfWord& hw) {
+    if (h >= n_half) return false;
+    hw.gw = (uint32_t)(h >> 1);
+    hw.o = (int)(h & 1) * 16;
+    hw.r = fm.word_read ? __ldg(fm.word_read + hw.gw) : hw.gw / fm.wpr;
+    hw.wo = b.word_off[hw.r];
+    hw.len = (int)b.len[hw.r];
+    hw.i0 = (int)(hw.gw - hw.wo) * 32 + hw.o;
+    if (hw.i0 >= hw.len) return false;
+    hw.rgrow = (uint32_t)b.rg[hw.r] * KBBQ_NQ;
+    hw.sec = b.second[hw.r] ? 1 : 0;
+    hw.q = __ldg(reinterpret_cast<const uint4*>(b.qual + (size_t)hw.gw * 32 + hw.o));
+    const unsigned long long bw = b.bases[hw.gw];
+    const uint32_t nw = b.nmask[hw.gw];
+    if (hw.o) {
+        hw.codes = (bw >> 30) & 0x3FFFFFFFFull;
+        hw.nflags = (nw >> 15) & 0x1FFFFu;
+    } else {
+        const unsigned long long pw = hw.i0 ? b.bases[hw.gw - 1] : 0ull;
+        const uint32_t pn = hw.i0 ? b.nmask[hw.gw - 1] : 1u << 31;  // no base before the first: no dinucleotide
+        hw.codes = ((bw << 2) | (pw >> 62)) & 0x3FFFFFFFFull;
+        hw.nflags = ((nw << 1) | (pn >> 31)) & 0x1FFFFu;
+    }
+    return true;
+}
+__device__ __forceinline__ int half_word_qual(const HalfWord& hw, int j) {
+    const uint32_t w = j < 4 ? hw.q.x : j < 8 ? hw.q.y : j < 12 ? hw.q.z : hw.q.w;
+    return (int)((w >> (8 * (j & 3))) & 255u);
+}
+__global__ void __launch_bounds__(256) word_read_kernel(const uint32_t* __restrict__ word_off, uint32_t n_reads, uint32_t* __restrict__ word_read) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    for (uint32_t w = word_off[r]; w < word_off[r + 1]; ++w) word_read[w] = r;
+}
 
-// Row -> slot through a direct table (one shared load per lookup): slot_of[key] for the first KBBQ_HIST_DIRECT_RG read
-// groups; a row takes the next free slot the first time any warp of the block meets it, and NOSLOT for good once the
-// S slots are gone.  Two lanes of one warp never race for a key (a leader is unique per quality), so the short spin
-// on CLAIMING only ever waits for another warp.
+// ---- covariate counting: CCovariateData::consume_read (covariateutils.cc:30-42,65-76,102-116,147-164,193-202) -------
+// Every base adds to its (read group, quality) row's cycle cell and dinucleotide cell; the row's {errors,total} pair
+// and the read group's are sums of the cycle cells (skips are never set, covariateutils.cc:194-197: all three tables
+// count every base) and are formed when a block flushes.  The tables are small and hot -- binned qualities put half of
+// all bases on one row -- so as global RED operations they serialise per address in the L2 (tools/probe_lab.cu: 3.6 G/s
+// on 20 hot cells).  Each block keeps an associative set of S rows in shared memory and counts there with shared-memory
+// atomics, which the SM retires at ~16 per clock even on a handful of hot addresses (probe_lab: 2.3 T/s chip-wide,
+// the same as conflict-free ones): two per base.  (Round 1 elected one leader per distinct key with __match_any_sync to
+// save atomics: the match alone costs three times the atomics it saved.)  A row takes the next free slot the first
+// time any thread of the block meets it; a row that finds none -- or belongs to a read group beyond the direct table --
+// falls through to global atomics, so any input stays exact.  The launch bounds the words per block so that no
+// 32-bit cell can overflow.
+#define KBBQ_HIST_THREADS 512
+#define KBBQ_HIST_EMPTY 0xFFFFFFFFu
 #define KBBQ_HIST_DIRECT_RG 16
 #define KBBQ_HIST_UNASSIGNED 0xFFFFFFFFu
 #define KBBQ_HIST_CLAIMING 0xFFFFFFFEu
 #define KBBQ_HIST_NOSLOT 0xFFFFFFFDu
+// row layout: [0,2C) cycle totals (second*C + i), [2C,4C) cycle errors, [4C,4C+16) dinucleotide totals, then 16 errors
 __device__ __forceinline__ int hist_slot(uint32_t* slot_of, uint32_t* tags, uint32_t* n_used, int S, uint32_t key) {
     if (key >= KBBQ_HIST_DIRECT_RG * KBBQ_NQ) return -1;
     volatile uint32_t* cell = slot_of + key;
     uint32_t v = *cell;
-    if (v == KBBQ_HIST_UNASSIGNED) {
-        if (atomicCAS(slot_of + key, KBBQ_HIST_UNASSIGNED, KBBQ_HIST_CLAIMING) == KBBQ_HIST_UNASSIGNED) {
-            const uint32_t n = atomicAdd(n_used, 1u);
-            v = n < (uint32_t)S ? n : KBBQ_HIST_NOSLOT;
-            if (n < (uint32_t)S) tags[n] = key;
-            __threadfence_block();
-            *cell = v;
-        } else {
-            v = KBBQ_HIST_CLAIMING;
-        }
+    if (v < (uint32_t)S) return (int)v;
+    if (v == KBBQ_HIST_UNASSIGNED && atomicCAS(slot_of + key, KBBQ_HIST_UNASSIGNED, KBBQ_HIST_CLAIMING) == KBBQ_HIST_UNASSIGNED) {
+        const uint32_t n = atomicAdd(n_used, 1u);
+        v = n < (uint32_t)S ? n : KBBQ_HIST_NOSLOT;
+        if (n < (uint32_t)S) tags[n] = key;
+        __threadfence_block();
+        *cell = v;
+    } else {
+        // another thread is claiming the row (independent thread scheduling lets it finish even from this warp)
+        while ((v = *cell) == KBBQ_HIST_CLAIMING || v == KBBQ_HIST_UNASSIGNED) __nanosleep(20);
     }
-    while (v == KBBQ_HIST_CLAIMING) v = *cell;
     return v < (uint32_t)S ? (int)v : -1;
 }
 
 // err_bits: read.errors as bit masks (kbbq_batch word layout).  mod: per read, 4*index+base of the one base that
 // get_errors left modified in seq (ref quirk, readutils.cc:263-265 vs 568), or 0xFFFFFFFF; nullptr = none.
+// Counts half words [first_half, end_half); reads at or past n_first are not counted (--fixed mode, kbbq.cc:370).
 __global__ void __launch_bounds__(KBBQ_HIST_THREADS, 2)
-covariate_count_kernel(BatchView b, CountView cv, const uint32_t* __restrict__ err_bits, const uint32_t* __restrict__ mod,
-                       uint32_t first_read, uint32_t end_read, int S) {
+covariate_count_kernel(BatchView b, FlatMap fm, CountView cv, const uint32_t* __restrict__ err_bits, const uint32_t* __restrict__ mod,
+                       unsigned long long first_half, unsigned long long end_half, uint32_t n_first, int S) {
     extern __shared__ uint32_t hist_smem[];
-    const int C = cv.max_cycle, row_cells = KBBQ_HIST_FIXED + 4 * C;
+    const int C = cv.max_cycle, row_cells = 4 * C + 32;
     uint32_t* slot_of = hist_smem;                                    // [KBBQ_HIST_DIRECT_RG * 94]
     uint32_t* tags = slot_of + KBBQ_HIST_DIRECT_RG * KBBQ_NQ;         // [S] key of each slot in use (for the flush)
     uint32_t* n_used = tags + S;                                      // [1] (+1 pad)
-    uint32_t* rgh = n_used + 2;
-    uint32_t* rows = rgh + 2 * KBBQ_HIST_RG;
+    uint32_t* rows = n_used + 2;
     for (int i = threadIdx.x; i < KBBQ_HIST_DIRECT_RG * KBBQ_NQ; i += blockDim.x) slot_of[i] = KBBQ_HIST_UNASSIGNED;
     for (int i = threadIdx.x; i < S; i += blockDim.x) tags[i] = KBBQ_HIST_EMPTY;
-    for (int i = threadIdx.x; i < 2 + 2 * KBBQ_HIST_RG + S * row_cells; i += blockDim.x) n_used[i] = 0;
+    for (int i = threadIdx.x; i < 2 + S * row_cells; i += blockDim.x) n_used[i] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = first_read + warp; r < end_read; r += nwarps) {
-        const int len = (int)b.len[r];
-        const uint32_t wo = b.word_off[r];
-        const int rg = (int)b.rg[r], sec = b.second[r] ? 1 : 0;
-        const uint32_t md = mod ? mod[r] : 0xFFFFFFFFu;
-        const int nw = (len + 31) >> 5;
-        const uint32_t rowkey0 = (uint32_t)rg * KBBQ_NQ;
-        int nerr = 0;
-        for (int w0 = 0; w0 < nw; w0 += 8) {  // 256 bases at a time: one round of loads, then up to 8 steps of 32 bases
-            const int nwg = nw - w0 < 8 ? nw - w0 : 8;
-            unsigned long long A = 0;
-            uint32_t nm = 0, e = 0, cx = 0;
-            const int wi = w0 + lane;
-            if (lane < nwg) {
-                A = b.bases[wo + wi];
-                nm = b.nmask[wo + wi];
-                e = err_bits[wo + wi];
-                if (wi > 0) cx = (uint32_t)(b.bases[wo + wi - 1] >> 62) | ((b.nmask[wo + wi - 1] >> 31) << 2);
-                if (md != 0xFFFFFFFFu) {
-                    const int mi = (int)(md >> 2), mb = (int)(md & 3u);
-                    if ((mi >> 5) == wi) {
-                        A = (A & ~(3ull << (2 * (mi & 31)))) | ((unsigned long long)mb << (2 * (mi & 31)));
-                        nm &= ~(1u << (mi & 31));
-                    }
-                    if (mi == 32 * wi - 1) cx = (uint32_t)mb;
-                }
-            }
-            uint2 qq = make_uint2(0, 0);
-            if (lane < 4 * nwg) qq = __ldg(reinterpret_cast<const uint2*>(b.qual + (size_t)(wo + w0) * 32) + lane);
-            for (int c = 0; c < nwg; ++c) {
-                const int i = (w0 + c) * 32 + lane;
-                const bool inl = i < len;
-                const int src = 4 * c + (lane >> 3);
-                const uint32_t qlo = __shfl_sync(KBBQ_FULL, qq.x, src), qhi = __shfl_sync(KBBQ_FULL, qq.y, src);
-                const int qi = inl ? (int)((((lane & 4) ? qhi : qlo) >> (8 * (lane & 3))) & 255u) : 255;
-                const bool in = inl && qi <= KBBQ_MAXQ;  // a quality the tables cannot index is skipped (and reported: qual_range_kernel)
-                const unsigned long long Ac = __shfl_sync(KBBQ_FULL, A, c);
-                const uint32_t nmc = __shfl_sync(KBBQ_FULL, nm, c), emask = __shfl_sync(KBBQ_FULL, e, c);
-                const uint32_t cxc = __shfl_sync(KBBQ_FULL, cx, c);
-                nerr += __popc(emask);
-                const bool er = (emask >> lane) & 1u;
-                // lanes with the same quality share a row: the leader finds (or claims) its slot
-                const uint32_t same_q = __match_any_sync(KBBQ_FULL, qi);
-                const int leader = __ffs(same_q) - 1;
-                const uint32_t key = rowkey0 + (uint32_t)qi;
-                int slot = -1;
-                if (in && lane == leader) slot = hist_slot(slot_of, tags, n_used, S, key);
-                slot = __shfl_sync(KBBQ_FULL, slot, leader);
-                uint32_t* row = rows + (size_t)(slot < 0 ? 0 : slot) * row_cells;
-                if (in && lane == leader) {  // CQCovariate
-                    const int cnt = __popc(same_q), ne = __popc(same_q & emask);
-                    if (slot >= 0) {
-                        atomicAdd(row + 1, (uint32_t)cnt);
-                        if (ne) atomicAdd(row, (uint32_t)ne);
-                    } else {
-                        atomicAdd(cv.qc + (size_t)key * 2 + 1, (unsigned long long)cnt);
-                        if (ne) atomicAdd(cv.qc + (size_t)key * 2, (unsigned long long)ne);
-                    }
-                }
-                if (in) {  // CCycleCovariate: cycle = index in read orientation, split by `second`
-                    if (slot >= 0) {
-                        atomicAdd(row + KBBQ_HIST_FIXED + sec * C + i, 1u);
-                        if (er) atomicAdd(row + KBBQ_HIST_FIXED + 2 * C + sec * C + i, 1u);
-                    } else {
-                        unsigned long long* cc = cv.cyc + (((size_t)key * 2 + sec) * (size_t)C + i) * 2;
-                        atomicAdd(cc + 1, 1ull);
-                        if (er) atomicAdd(cc, 1ull);
-                    }
-                }
-                // CDinucCovariate: i >= 1, both bases ACGT, qual >= 6
-                int dkey = -1;
-                if (in && i >= 1 && qi >= 6) {
-                    const bool n1 = (nmc >> lane) & 1u, n0 = lane ? (nmc >> (lane - 1)) & 1u : (cxc >> 2) & 1u;
-                    if (!n1 && !n0) {
-                        const int c1 = (int)((Ac >> (2 * lane)) & 3), c0 = lane ? (int)((Ac >> (2 * lane - 2)) & 3) : (int)(cxc & 3u);
-                        dkey = qi * 16 + ((c0 << 2) | c1);
-                    }
-                }
-                const uint32_t same_d = __match_any_sync(KBBQ_FULL, dkey);
-                if (dkey >= 0 && lane == __ffs(same_d) - 1) {
-                    const int cnt = __popc(same_d), ne = __popc(same_d & emask), d = dkey & 15;
-                    if (slot >= 0) {
-                        atomicAdd(row + 18 + d, (uint32_t)cnt);
-                        if (ne) atomicAdd(row + 2 + d, (uint32_t)ne);
-                    } else {
-                        unsigned long long* dd = cv.dic + ((size_t)key * 16 + d) * 2;
-                        atomicAdd(dd + 1, (unsigned long long)cnt);
-                        if (ne) atomicAdd(dd, (unsigned long long)ne);
-                    }
-                }
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long h = first_half + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; h < end_half; h += stride) {
+        HalfWord hw;
+        if (!load_half_word(b, fm, h, end_half, hw) || hw.r >= n_first) continue;
+        const uint32_t e16 = (err_bits[hw.gw] >> hw.o) & 0xFFFFu;
+        if (mod) {  // the base get_errors left modified takes part in the dinucleotide keys
+            const uint32_t md = mod[hw.r];
+            const int j = (int)(md >> 2) - (hw.i0 - 1);  // position among the 17 bases this thread looks at
+            if (md != 0xFFFFFFFFu && j >= 0 && j <= 16) {
+                hw.codes = (hw.codes & ~(3ull << (2 * j))) | ((unsigned long long)(md & 3u) << (2 * j));
+                hw.nflags &= ~(1u << j);
             }
         }
-        if (lane == 0) {  // CRGCovariate: {#errors, #bases}; skips are never set (covariateutils.cc:194-197)
-            if (rg < KBBQ_HIST_RG) {
-                if (nerr) atomicAdd(rgh + 2 * rg, (uint32_t)nerr);
-                atomicAdd(rgh + 2 * rg + 1, (uint32_t)len);
-            } else {
-                if (nerr) atomicAdd(cv.rgc + 2 * rg, (unsigned long long)nerr);
-                atomicAdd(cv.rgc + 2 * rg + 1, (unsigned long long)len);
+        uint32_t last_key = 0xFFFFFFFFu;
+        uint32_t* row = rows;
+        bool have_row = false;
+        const int n = hw.len - hw.i0 < 16 ? hw.len - hw.i0 : 16;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const int qi = half_word_qual(hw, j);
+            if (qi > KBBQ_MAXQ) continue;  // a quality the tables cannot index is skipped (and reported: qual_range_kernel)
+            const uint32_t key = hw.rgrow + (uint32_t)qi;
+            if (key != last_key) {
+                const int slot = hist_slot(slot_of, tags, n_used, S, key);
+                have_row = slot >= 0;
+                row = rows + (size_t)(have_row ? slot : 0) * row_cells;
+                last_key = key;
+            }
+            const int i = hw.i0 + j;
+            const bool er = (e16 >> j) & 1u;
+            // CDinucCovariate: i >= 1, both bases ACGT, qual >= 6
+            const bool di = qi >= 6 && ((hw.nflags >> j) & 3u) == 0;
+            const uint32_t x = (uint32_t)(hw.codes >> (2 * j)) & 15u;  // previous base in the low pair
+            const uint32_t d = ((x & 3u) << 2) | (x >> 2);
+            if (have_row) {
+                atomicAdd(row + hw.sec * C + i, 1u);
+                if (er) atomicAdd(row + 2 * C + hw.sec * C + i, 1u);
+                if (di) {
+                    atomicAdd(row + 4 * C + d, 1u);
+                    if (er) atomicAdd(row + 4 * C + 16 + d, 1u);
+                }
+            } else {  // no private row: straight to the tables, all four of them
+                unsigned long long* cc = cv.cyc + (((size_t)key * 2 + hw.sec) * (size_t)C + i) * 2;
+                atomicAdd(cc + 1, 1ull);
+                atomicAdd(cv.qc + (size_t)key * 2 + 1, 1ull);
+                atomicAdd(cv.rgc + 2 * (hw.rgrow / KBBQ_NQ) + 1, 1ull);
+                if (er) {
+                    atomicAdd(cc, 1ull);
+                    atomicAdd(cv.qc + (size_t)key * 2, 1ull);
+                    atomicAdd(cv.rgc + 2 * (hw.rgrow / KBBQ_NQ), 1ull);
+                }
+                if (di) {
+                    unsigned long long* dd = cv.dic + ((size_t)key * 16 + d) * 2;
+                    atomicAdd(dd + 1, 1ull);
+                    if (er) atomicAdd(dd, 1ull);
+                }
             }
         }
     }
     __syncthreads();
-    // flush what this block counted
-    for (int i = threadIdx.x; i < 2 * KBBQ_HIST_RG; i += blockDim.x)
-        if (rgh[i]) atomicAdd(cv.rgc + i, (unsigned long long)rgh[i]);
-    for (int s = 0; s < S; ++s) {
+    // flush what this block counted: one warp per row; the row's q pair and its read group's pair are sums of its cycle cells
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    for (int s = wib; s < S; s += nwb) {
         const uint32_t key = tags[s];
         if (key == KBBQ_HIST_EMPTY) continue;
         const uint32_t* row = rows + (size_t)s * row_cells;
-        for (int j = threadIdx.x; j < row_cells; j += blockDim.x) {
+        unsigned long long tot = 0, err = 0;
+        for (int j = lane; j < row_cells; j += 32) {
             const uint32_t v = row[j];
             if (!v) continue;
             unsigned long long* dst;
-            if (j < 2) dst = cv.qc + (size_t)key * 2 + j;
-            else if (j < 18) dst = cv.dic + ((size_t)key * 16 + (j - 2)) * 2;
-            else if (j < KBBQ_HIST_FIXED) dst = cv.dic + ((size_t)key * 16 + (j - 18)) * 2 + 1;
-            else if (j < KBBQ_HIST_FIXED + 2 * C) dst = cv.cyc + ((size_t)key * 2 * C + (j - KBBQ_HIST_FIXED)) * 2 + 1;
-            else dst = cv.cyc + ((size_t)key * 2 * C + (j - KBBQ_HIST_FIXED - 2 * C)) * 2;
+            if (j < 2 * C) { dst = cv.cyc + ((size_t)key * 2 * C + j) * 2 + 1; tot += v; }
+            else if (j < 4 * C) { dst = cv.cyc + ((size_t)key * 2 * C + (j - 2 * C)) * 2; err += v; }
+            else if (j < 4 * C + 16) dst = cv.dic + ((size_t)key * 16 + (j - 4 * C)) * 2 + 1;
+            else dst = cv.dic + ((size_t)key * 16 + (j - 4 * C - 16)) * 2;
             atomicAdd(dst, (unsigned long long)v);
+        }
+#pragma unroll
+        for (int dlt = 16; dlt; dlt >>= 1) {
+            tot += __shfl_xor_sync(KBBQ_FULL, tot, dlt);
+            err += __shfl_xor_sync(KBBQ_FULL, err, dlt);
+        }
+        if (lane == 0) {
+            if (tot) { atomicAdd(cv.qc + (size_t)key * 2 + 1, tot); atomicAdd(cv.rgc + 2 * (key / KBBQ_NQ) + 1, tot); }
+            if (err) { atomicAdd(cv.qc + (size_t)key * 2, err); atomicAdd(cv.rgc + 2 * (key / KBBQ_NQ), err); }
         }
     }
 }
@@ -803,93 +816,23 @@ pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __res
 }
 
 // ---- pass 4: CReadData::recalibrate (readutils.cc:572-595) as a fused table lookup ---------------------------------
-// One warp per read, one lane per 8 consecutive bases: the qualities move as one 8-byte load and one 8-byte store per
-// lane (a 150-base read is a single warp instruction each way), the 24 table lookups of a lane are independent.
-// The loop is software pipelined two deep -- read r+2's header and read r+1's words are in flight while read r is
-// looked up -- because a warp's own chain (header -> words -> tables -> store) is three memory round trips long.
-struct P4Head {
-    int len, sec;
-    uint32_t wo;
-    size_t rgrow;
-};
-struct P4Data {
-    uint2 qq;
-    uint32_t codes, nflags;  // the lane's 8 bases and the one before them, 2 bits each from bit 0; N flags likewise
-};
-__device__ __forceinline__ P4Head p4_head(const BatchView& b, uint32_t r) {
-    P4Head h;
-    h.len = 0; h.sec = 0; h.wo = 0; h.rgrow = 0;
-    if (r < b.n_reads) {
-        h.len = (int)b.len[r];
-        h.wo = b.word_off[r];
-        h.rgrow = (size_t)b.rg[r] * KBBQ_NQ;
-        h.sec = b.second[r] ? 1 : 0;
-    }
-    return h;
-}
-__device__ __forceinline__ P4Data p4_data(const BatchView& b, const P4Head& h, int i0) {
-    P4Data d;
-    d.qq = make_uint2(0, 0); d.codes = 0; d.nflags = 0;
-    if (i0 < h.len) {
-        const uint32_t w = h.wo + (uint32_t)(i0 >> 5);
-        const int o = i0 & 31;  // 0, 8, 16, 24
-        d.qq = __ldg(reinterpret_cast<const uint2*>(b.qual + (size_t)h.wo * 32 + i0));
-        const unsigned long long bw = b.bases[w];
-        const uint32_t nw = b.nmask[w];
-        if (o) {
-            d.codes = (uint32_t)(bw >> (2 * o - 2)) & 0x3FFFFu;
-            d.nflags = (nw >> (o - 1)) & 0x1FFu;
-        } else {
-            const unsigned long long pw = i0 ? b.bases[w - 1] : 0ull;
-            const uint32_t pn = i0 ? b.nmask[w - 1] : 1u << 31;  // no base before the first: no dinucleotide
-            d.codes = ((uint32_t)bw << 2 | (uint32_t)(pw >> 62)) & 0x3FFFFu;
-            d.nflags = (nw << 1 | pn >> 31) & 0x1FFu;
-        }
-    }
-    return d;
-}
-// SMEM: the lookup tables live in shared memory (the launch checks that they fit): cy as it is, and `dib` = base + di
-// folded into one int16 table of 17 entries per row (entry 16 = no dinucleotide term), so a base costs two shared
-// loads instead of three dependent global ones (round 1: issue-bound at 76 %, 660 GB/s).
+// The flat traversal (above): one thread per 16 bases, one 16-byte load and one 16-byte store of qualities each, two
+// table lookups per base.  SMEM: the lookup tables live in shared memory (the launch checks that they fit): cy as it is,
+// and `dib` = base + di folded into one int16 table of 17 entries per row (entry 16 = no dinucleotide term); larger
+// models read the three global tables through the L1.
 struct P4Tables {
     const int8_t* cy;
     const int16_t* dib;
 };
-template <bool SMEM>
-__device__ __forceinline__ void p4_apply(const ModelView& mv, const P4Tables& st, const P4Head& h, const P4Data& d, int i0,
-                                         uint8_t* __restrict__ out) {
-    if (i0 >= h.len) return;
-    uint32_t res[2] = {d.qq.x, d.qq.y};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int i = i0 + j;
-        const int qi = (int)((res[j >> 2] >> (8 * (j & 3))) & 255u);
-        if (i < h.len && qi >= 6 && qi <= KBBQ_MAXQ) {  // minqual: lower qualities pass through unchanged (so does anything the tables cannot index)
-            const size_t row = h.rgrow + qi;
-            const bool has_di = ((d.nflags >> j) & 3u) == 0;  // this base and the one before it are ACGT (and i > 0)
-            const uint32_t x = (d.codes >> (2 * j)) & 15u;    // previous base in the low pair
-            const uint32_t dn = ((x & 3u) << 2) | (x >> 2);
-            int v;
-            if (SMEM) {
-                v = st.cy[(row * 2 + h.sec) * (size_t)mv.max_cycle + i] + st.dib[row * 17 + (has_di ? dn : 16u)];
-            } else {
-                v = mv.base[row] + mv.cy[(row * 2 + h.sec) * (size_t)mv.max_cycle + i];
-                if (has_di) v += mv.di[row * 16 + dn];
-            }
-            v = v < 0 ? 0 : (v > KBBQ_MAXQ ? KBBQ_MAXQ : v);
-            res[j >> 2] = (res[j >> 2] & ~(255u << (8 * (j & 3)))) | ((uint32_t)v << (8 * (j & 3)));
-        }
-    }
-    *reinterpret_cast<uint2*>(out + (size_t)h.wo * 32 + i0) = make_uint2(res[0], res[1]);
-}
-// bytes of shared memory the SMEM variant needs for n_rg read groups (0 when n_rg is unknown to the caller)
+// bytes of shared memory the SMEM variant needs
 __host__ __device__ inline size_t p4_smem_bytes(int n_rg, int max_cycle) {
     const size_t cy = ((size_t)n_rg * KBBQ_NQ * 2 * max_cycle + 15) & ~(size_t)15;
     return cy + (size_t)n_rg * KBBQ_NQ * 17 * 2;
 }
 template <bool SMEM>
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32)
-pass4_apply_kernel(BatchView b, ModelView mv, int n_rg, uint8_t* __restrict__ out, uint32_t first_read, uint32_t end_read) {
+__global__ void __launch_bounds__(256)
+pass4_apply_kernel(BatchView b, FlatMap fm, ModelView mv, int n_rg, uint8_t* __restrict__ out, unsigned long long first_half,
+                   unsigned long long end_half) {
     extern __shared__ __align__(16) unsigned char p4_smem[];
     P4Tables st{nullptr, nullptr};
     if (SMEM) {
@@ -905,20 +848,34 @@ pass4_apply_kernel(BatchView b, ModelView mv, int n_rg, uint8_t* __restrict__ ou
         st.cy = cy;
         st.dib = dib;
     }
-    const int lane = threadIdx.x & 31;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t warp = first_read + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    b.n_reads = end_read;  // the launch covers reads [first_read, end_read): p4_head yields empty reads past the end
-    if (warp >= b.n_reads) return;
-    P4Head h0 = p4_head(b, warp);
-    P4Head h1 = p4_head(b, warp + nwarps);
-    P4Data d0 = p4_data(b, h0, 8 * lane);
-    for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
-        const P4Head h2 = p4_head(b, r + 2 * nwarps);  // header two reads ahead
-        const P4Data d1 = p4_data(b, h1, 8 * lane);    // words one read ahead
-        p4_apply<SMEM>(mv, st, h0, d0, 8 * lane, out);
-        for (int i0 = 256 + 8 * lane; i0 < h0.len; i0 += 256) p4_apply<SMEM>(mv, st, h0, p4_data(b, h0, i0), i0, out);  // reads > 256 bases
-        h0 = h1; h1 = h2; d0 = d1;
+    const int C = mv.max_cycle;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long h = first_half + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; h < end_half; h += stride) {
+        HalfWord hw;
+        if (!load_half_word(b, fm, h, end_half, hw)) continue;  // past the read's end: the output stays zero like the input
+        uint32_t res[4] = {hw.q.x, hw.q.y, hw.q.z, hw.q.w};
+        const int n = hw.len - hw.i0 < 16 ? hw.len - hw.i0 : 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int qi = (int)((res[j >> 2] >> (8 * (j & 3))) & 255u);
+            if (j < n && qi >= 6 && qi <= KBBQ_MAXQ) {  // minqual: lower qualities pass through unchanged (so does anything the tables cannot index)
+                const size_t row = hw.rgrow + qi;
+                const int i = hw.i0 + j;
+                const bool has_di = ((hw.nflags >> j) & 3u) == 0;  // this base and the one before it are ACGT (and i > 0)
+                const uint32_t x = (uint32_t)(hw.codes >> (2 * j)) & 15u;  // previous base in the low pair
+                const uint32_t dn = ((x & 3u) << 2) | (x >> 2);
+                int v;
+                if (SMEM) {
+                    v = st.cy[(row * 2 + hw.sec) * (size_t)C + i] + st.dib[row * 17 + (has_di ? dn : 16u)];
+                } else {
+                    v = mv.base[row] + mv.cy[(row * 2 + hw.sec) * (size_t)C + i];
+                    if (has_di) v += mv.di[row * 16 + dn];
+                }
+                v = v < 0 ? 0 : (v > KBBQ_MAXQ ? KBBQ_MAXQ : v);
+                res[j >> 2] = (res[j >> 2] & ~(255u << (8 * (j & 3)))) | ((uint32_t)v << (8 * (j & 3)));
+            }
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)hw.gw * 32 + hw.o) = make_uint4(res[0], res[1], res[2], res[3]);
     }
 }
 
