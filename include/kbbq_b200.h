@@ -83,6 +83,13 @@ int kbbq_device_count(void);
  * kbbq_ctx_create does it implicitly; a host may call this from a side thread while it parses its input. */
 int kbbq_device_warmup(int device);
 
+/* page-locked host memory (what kbbq_batch_upload_async / _stream and kbbq_pass4_recalibrate need for their copies to
+ * be asynchronous), usable from every device of the process; and a device's free / total memory, for a host that
+ * decides how many batches may stay resident */
+int kbbq_host_alloc(size_t bytes, void** out);
+void kbbq_host_free(void* p);
+int kbbq_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes);
+
 /* ---- host-only helpers (no GPU needed) ------------------------------------------------------------------------ */
 /* bloom::Bloom ctor geometry; KBBQ_EINVAL where the reference throws (bloom.cc:18-21) */
 int kbbq_bloom_geometry(uint64_t projected, double fpr, uint64_t seed, kbbq_bloom_geom* out);
@@ -170,12 +177,28 @@ int kbbq_bloom_load(kbbq_ctx* ctx, int which, const char* path);
 int kbbq_bloom_ipc_handle(kbbq_ctx* ctx, int which, void* handle64);
 int kbbq_bloom_or_allreduce_p2p(kbbq_ctx* ctx, int which, int rank, int world, const void* handles);
 
+/* The same merge for several contexts of ONE process (a host that drives several GPUs itself): peer access instead of
+ * IPC handles, every rank's kernel launched from this one call, the insert counters summed; synchronises every
+ * context's stream before and after.  KBBQ_ECUDA when two of the devices cannot map each other's memory. */
+int kbbq_bloom_or_allreduce_local(kbbq_ctx* const* ctxs, int n, int which);
+/* replace the context's count tables by the caller's (dense layout as above): the host-side SUM of per-GPU partial
+ * tables goes back to every GPU this way (they are a few hundred KB) */
+int kbbq_covariates_upload(kbbq_ctx* ctx, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc, const uint64_t* dic);
+
 /* ---- batches -------------------------------------------------------------------------------------------------------- */
 int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
 /* Same, but the quality array (3/4 of the bytes) is copied on a side stream and may still be in flight on return:
  * pass 1 does not read it and overlaps the copy; passes 2-4 wait for it on the device.  host->qual must stay valid and
  * unmodified until kbbq_sync() has returned (with pinned memory the copy is truly asynchronous). */
 int kbbq_batch_upload_async(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
+/* Same, but EVERY array travels on the side stream and nothing is waited for: the call returns as soon as the copies
+ * are queued, the passes wait for them on the device, and the upload of the next batch overlaps the passes of this one
+ * -- double buffering for inputs larger than device memory, which are streamed through the device once per pass as the
+ * reference re-reads its file once per pass (kbbq.cc:232,258,336,365,456).  Every host array must be pinned and stay
+ * valid and unmodified until kbbq_batch_wait (or kbbq_sync) has returned. */
+int kbbq_batch_upload_stream(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
+/* blocks until every host array of a kbbq_batch_upload_async / _stream call has been read */
+int kbbq_batch_wait(kbbq_ctx* ctx, const kbbq_dbatch* b);
 void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b);
 /* number of k-mer slots of the batch = sum over reads of max(0, len-k+1): the draws pass 1 consumes */
 uint64_t kbbq_batch_slots(const kbbq_dbatch* b);

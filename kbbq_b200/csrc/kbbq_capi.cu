@@ -164,6 +164,7 @@ struct kbbq_dbatch {
     uint64_t part_word[5] = {0, 0, 0, 0, 0};   // ... and their word offsets (from the host's word_off at upload)
     cudaEvent_t qual_ready = nullptr;  // recorded on the copy stream after d_qual's upload
     bool qual_waited = true;           // false until `stream` has been made to wait for qual_ready
+    bool all_on_copy = false;          // kbbq_batch_upload_stream: every array is ready with qual_ready, not before
     BatchView view() const {
         BatchView v;
         v.bases = d_bases;
@@ -276,15 +277,16 @@ int launch_count(kbbq_ctx* ctx, kbbq_dbatch* b, const uint32_t* d_err, const uin
 
 // d_slot_off[0..n] = exclusive prefix sum of max(0, len[r]-k+1) (the k-mer slots of the reads before r):
 // slot_counts_kernel writes the n counts and a trailing 0, cub scans the n+1 items in place
-int slot_prefix(kbbq_ctx* ctx, const uint32_t* d_len, uint32_t n, unsigned long long* d_slot_off) {
-    slot_counts_kernel<<<(unsigned)(((size_t)n + 1 + 255) / 256), 256, 0, ctx->stream>>>(d_len, n, ctx->k, d_slot_off);
+int slot_prefix(kbbq_ctx* ctx, const uint32_t* d_len, uint32_t n, unsigned long long* d_slot_off, cudaStream_t st = nullptr) {
+    if (!st) st = ctx->stream;
+    slot_counts_kernel<<<(unsigned)(((size_t)n + 1 + 255) / 256), 256, 0, st>>>(d_len, n, ctx->k, d_slot_off);
     if (int rc = check_launch(ctx, "slot_counts_kernel")) return rc;
     size_t tmp_bytes = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_slot_off, d_slot_off, (size_t)n + 1, ctx->stream));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_slot_off, d_slot_off, (size_t)n + 1, st));
     void* tmp = nullptr;
-    CU(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), ctx->stream));
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_slot_off, d_slot_off, (size_t)n + 1, ctx->stream);
-    cudaFreeAsync(tmp, ctx->stream);
+    CU(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), st));
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_slot_off, d_slot_off, (size_t)n + 1, st);
+    cudaFreeAsync(tmp, st);
     if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("slot prefix: ") + cudaGetErrorString(e));
     return KBBQ_OK;
 }
@@ -449,6 +451,24 @@ int kbbq_device_warmup(int device) {
     // while the caller parses its input
     if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess)
         return fail(KBBQ_ECUDA, std::string("no usable CUDA device ") + std::to_string(device) + " (this library has no CPU path)");
+    return KBBQ_OK;
+}
+
+int kbbq_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(KBBQ_EINVAL, "null output");
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 16), cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(KBBQ_ENOMEM, std::string("pinned host allocation: ") + cudaGetErrorString(e));
+    return KBBQ_OK;
+}
+void kbbq_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+int kbbq_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return fail(KBBQ_ECUDA, "no such device");
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
     return KBBQ_OK;
 }
 
@@ -1019,6 +1039,80 @@ int kbbq_bloom_or_allreduce_p2p(kbbq_ctx* ctx, int which, int rank, int world, c
     return KBBQ_OK;
 }
 
+// The same merge for several contexts of ONE process (one host thread driving several GPUs, or one thread per GPU that
+// meets here): peer access instead of IPC handles, the kernel of every rank launched from this call, counters summed
+// on the host.  Synchronises every context's stream before and after.
+int kbbq_bloom_or_allreduce_local(kbbq_ctx* const* ctxs, int n, int which) {
+    if (!ctxs || n < 1 || n > KBBQ_MAX_PEERS) return fail(KBBQ_EINVAL, "bad context list (at most 16 peers)");
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i]) return fail(KBBQ_EINVAL, "null context");
+        if (int rc = filter_ok(ctxs[i], which)) return rc;
+        if (ctxs[i]->filt[which].geom.table_bits != ctxs[0]->filt[which].geom.table_bits) return fail(KBBQ_EINVAL, "filters differ in size");
+        for (int j = 0; j < i; ++j)
+            if (ctxs[j]->device == ctxs[i]->device) return fail(KBBQ_EINVAL, "two contexts on one device");
+    }
+    if (n == 1) return KBBQ_OK;
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(ctxs[i]->device));
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, ctxs[i]->device, ctxs[j]->device));
+            if (!can) return fail(KBBQ_ECUDA, "no peer access between devices " + std::to_string(ctxs[i]->device) + " and " + std::to_string(ctxs[j]->device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        }
+        CU(cudaStreamSynchronize(ctxs[i]->stream));  // this rank's inserts are in memory
+    }
+    const unsigned long long n2 = ctxs[0]->filt[which].geom.table_bits / 128;
+    const unsigned long long per = (n2 + n - 1) / n;
+    for (int r = 0; r < n; ++r) {
+        kbbq_ctx* ctx = ctxs[r];
+        CU(cudaSetDevice(ctx->device));
+        PeerPtrs pp;
+        std::memset(&pp, 0, sizeof pp);
+        for (int s2 = 0; s2 < n; ++s2) pp.p[s2] = reinterpret_cast<ulonglong2*>(ctxs[(r + s2) % n]->filt[which].d_words);
+        const int grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((per + 255) / 256, (unsigned long long)ctx->sm_count * 8));
+        pass_begin(ctx);
+        mark_kernel(ctx, "or_allreduce_p2p_kernel");
+        switch (n) {
+        case 2: or_allreduce_p2p_kernel<2><<<grid, 256, 0, ctx->stream>>>(pp, r, n, n2); break;
+        case 4: or_allreduce_p2p_kernel<4><<<grid, 256, 0, ctx->stream>>>(pp, r, n, n2); break;
+        case 8: or_allreduce_p2p_kernel<8><<<grid, 256, 0, ctx->stream>>>(pp, r, n, n2); break;
+        default: or_allreduce_p2p_kernel<0><<<grid, 256, 0, ctx->stream>>>(pp, r, n, n2); break;
+        }
+        if (int rc = check_launch(ctx, "or_allreduce_p2p_kernel")) return rc;
+        pass_end(ctx);
+    }
+    unsigned long long total = 0;
+    for (int r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaStreamSynchronize(ctxs[r]->stream));  // every slice is written everywhere
+        unsigned long long c = 0;
+        CU(cudaMemcpy(&c, ctxs[r]->filt[which].d_inserted, 8, cudaMemcpyDeviceToHost));
+        total += c;
+    }
+    for (int r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaMemcpy(ctxs[r]->filt[which].d_inserted, &total, 8, cudaMemcpyHostToDevice));
+    }
+    return KBBQ_OK;
+}
+
+// count tables += the caller's (dense layout): the SUM merge of per-GPU partial tables when the host does it
+int kbbq_covariates_upload(kbbq_ctx* ctx, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc, const uint64_t* dic) {
+    if (int rc = use(ctx)) return rc;
+    if (!rgc || !qc || !cyc || !dic) return fail(KBBQ_EINVAL, "null table");
+    const CountView c = ctx->counts();
+    CU(cudaMemcpyAsync(c.rgc, rgc, ctx->n_rgc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(c.qc, qc, ctx->n_qc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(c.cyc, cyc, ctx->n_cyc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(c.dic, dic, ctx->n_dic * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KBBQ_OK;
+}
+
 // ---- batches -------------------------------------------------------------------------------------------------------
 void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (!b) return;
@@ -1035,12 +1129,23 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     delete b;
 }
 
-static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, bool async_qual);
+// mode 0: everything has landed on return; 1: the quality array may still be in flight on the copy stream (pass 1/2 do
+// not read it); 2: every array travels on the copy stream and nothing is waited for -- the upload of the next batch
+// overlaps the passes of this one (double buffering for inputs that are streamed through the device pass by pass)
+static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, int mode);
 
-int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) { return batch_upload(ctx, h, out, false); }
-int kbbq_batch_upload_async(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) { return batch_upload(ctx, h, out, true); }
+int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) { return batch_upload(ctx, h, out, 0); }
+int kbbq_batch_upload_async(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) { return batch_upload(ctx, h, out, 1); }
+int kbbq_batch_upload_stream(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out) { return batch_upload(ctx, h, out, 2); }
 
-static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, bool async_qual) {
+int kbbq_batch_wait(kbbq_ctx* ctx, const kbbq_dbatch* b) {
+    if (int rc = use(ctx)) return rc;
+    if (!b) return fail(KBBQ_EINVAL, "null batch");
+    if (b->qual_ready) CU(cudaEventSynchronize(b->qual_ready));
+    return KBBQ_OK;
+}
+
+static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, int mode) {
     if (int rc = use(ctx)) return rc;
     if (!h || !out) return fail(KBBQ_EINVAL, "null argument");
     if (h->max_len > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
@@ -1054,49 +1159,61 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
         b->part_word[i] = n ? h->word_off[b->part_read[i]] : 0;
     }
     const size_t nw = std::max<uint64_t>(h->n_words, 1);
-#define UP(dst, src, bytes)                                                                   \
-    do {                                                                                      \
-        cudaError_t e1 = cudaMallocAsync(&(dst), std::max<size_t>((bytes), 16), ctx->stream); \
-        if (e1 == cudaSuccess && (src) && (bytes))                                            \
-            e1 = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream); \
-        else if (e1 == cudaSuccess)                                                           \
-            e1 = cudaMemsetAsync((dst), 0, std::max<size_t>((bytes), 16), ctx->stream);       \
-        if (e1 != cudaSuccess) {                                                              \
-            kbbq_batch_free(ctx, b);                                                          \
-            return fail(e1 == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA,           \
-                        std::string("batch upload: ") + cudaGetErrorString(e1));              \
-        }                                                                                     \
+    cudaError_t e1 = cudaSuccess;
+    auto bail = [&](cudaError_t e) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        kbbq_batch_free(ctx, b);
+        return fail(e == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA, std::string("batch upload: ") + cudaGetErrorString(e));
+    };
+    // all device arrays come from the stream-ordered pool in `stream`'s order ...
+    struct Arr { void** dst; size_t bytes; };
+    const Arr arrs[] = {{(void**)&b->d_bases, (nw + 1) * 8}, {(void**)&b->d_nmask, (nw + 1) * 4}, {(void**)&b->d_qmask, nw * 8},
+                        {(void**)&b->d_word_off, ((size_t)n + 1) * 4}, {(void**)&b->d_len, std::max<size_t>(n, 4) * 4},
+                        {(void**)&b->d_rg, std::max<size_t>(n, 8) * 2}, {(void**)&b->d_second, std::max<size_t>(n, 16)},
+                        {(void**)&b->d_slot_off, ((size_t)n + 1) * 8}, {(void**)&b->d_qual, nw * 32}};
+    for (const Arr& a : arrs)
+        if (e1 == cudaSuccess) e1 = cudaMallocAsync(a.dst, a.bytes, ctx->stream);
+    if (e1 != cudaSuccess) return bail(e1);
+    // ... and are filled in the copy stream's (mode 2: all of them; otherwise the quality array only)
+    cudaEvent_t alloc_done = nullptr;
+    e1 = cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
+    if (e1 == cudaSuccess) e1 = cudaEventRecord(alloc_done, ctx->stream);
+    if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);
+    if (alloc_done) cudaEventDestroy(alloc_done);
+    if (e1 != cudaSuccess) return bail(e1);
+    cudaStream_t cs = mode == 2 ? ctx->copy_stream : ctx->stream;
+#define PUT(dst, src, bytes)                                                                                   \
+    do {                                                                                                       \
+        if (e1 == cudaSuccess && (bytes)) {                                                                    \
+            if (src) e1 = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, cs);                  \
+            else e1 = cudaMemsetAsync((dst), 0, (bytes), cs);                                                  \
+        }                                                                                                      \
     } while (0)
     // one padding word after the last read keeps two-word k-mer extraction in bounds
-    UP(b->d_bases, (const void*)nullptr, (nw + 1) * 8);
-    UP(b->d_nmask, (const void*)nullptr, (nw + 1) * 4);
-    if (h->n_words) {
-        CU(cudaMemcpyAsync(b->d_bases, h->bases, h->n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(b->d_nmask, h->nmask, h->n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if (h->qmask) UP(b->d_qmask, h->qmask, (size_t)h->n_words * 8);  // early: all pass 2 needs of the qualities
-    else UP(b->d_qmask, (const void*)nullptr, (size_t)h->n_words * 8);
-    UP(b->d_word_off, h->word_off, ((size_t)n + 1) * 4);
-    UP(b->d_len, h->len, (size_t)n * 4);
-    UP(b->d_rg, h->rg, (size_t)n * 2);
-    UP(b->d_second, h->second, (size_t)n);
-    UP(b->d_slot_off, (const void*)nullptr, ((size_t)n + 1) * 8);
-#undef UP
+    PUT(b->d_bases + h->n_words, (const void*)nullptr, 8);
+    PUT(b->d_nmask + h->n_words, (const void*)nullptr, 4);
+    PUT(b->d_bases, h->bases, h->n_words * 8);
+    PUT(b->d_nmask, h->nmask, h->n_words * 4);
+    if (h->qmask) PUT(b->d_qmask, h->qmask, (size_t)h->n_words * 8);  // early: all pass 2 needs of the qualities
+    PUT(b->d_word_off, h->word_off, ((size_t)n + 1) * 4);
+    PUT(b->d_len, h->len, (size_t)n * 4);
+    PUT(b->d_rg, h->rg, (size_t)n * 2);
+    PUT(b->d_second, h->second, (size_t)n);
+#undef PUT
+    if (e1 != cudaSuccess) return bail(e1);
     if (n) {  // slot_off = exclusive prefix of max(0, len-k+1), n+1 entries
-        if (int rc = slot_prefix(ctx, b->d_len, n, b->d_slot_off)) {
+        if (int rc = slot_prefix(ctx, b->d_len, n, b->d_slot_off, cs)) {
             kbbq_batch_free(ctx, b);
             return rc;
         }
+    } else {
+        e1 = cudaMemsetAsync(b->d_slot_off, 0, 8, cs);
     }
-    {   // the qualities (3/4 of the bytes) go last and on the copy stream: pass 1 does not read them and starts
+    {   // the qualities (3/5 of the bytes) go last and on the copy stream: pass 1 does not read them and starts
         // as soon as everything above has landed
-        const size_t qbytes = std::max<size_t>((size_t)h->n_words * 32, 16);
-        cudaError_t e2 = cudaMallocAsync(&b->d_qual, qbytes, ctx->stream);  // allocated in `stream` order ...
-        cudaEvent_t alloc_done = nullptr;
-        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
-        if (e2 == cudaSuccess) e2 = cudaEventRecord(alloc_done, ctx->stream);
-        if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);  // ... filled in the copy stream's
-        if (e2 == cudaSuccess && !h->n_words) e2 = cudaMemsetAsync(b->d_qual, 0, qbytes, ctx->copy_stream);
+        cudaError_t e2 = e1;
+        if (e2 == cudaSuccess && !h->n_words) e2 = cudaMemsetAsync(b->d_qual, 0, 32, ctx->copy_stream);
         if (e2 == cudaSuccess && h->n_words)
             e2 = cudaMemcpyAsync(b->d_qual, h->qual, (size_t)h->n_words * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
         if (e2 == cudaSuccess && h->n_words) {  // the count and apply kernels index tables by quality: flag anything above 93
@@ -1114,12 +1231,9 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
         }
         if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&b->qual_ready, cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaEventRecord(b->qual_ready, ctx->copy_stream);
-        if (alloc_done) cudaEventDestroy(alloc_done);
-        if (e2 != cudaSuccess) {
-            kbbq_batch_free(ctx, b);
-            return fail(e2 == cudaErrorMemoryAllocation ? KBBQ_ENOMEM : KBBQ_ECUDA, std::string("batch upload: ") + cudaGetErrorString(e2));
-        }
+        if (e2 != cudaSuccess) return bail(e2);
         b->qual_waited = false;
+        b->all_on_copy = mode == 2;
     }
     // validation and the slot total in tight host loops, while the copies above are in flight (the per-read prefix,
     // slot_off, is made on the device)
@@ -1148,8 +1262,8 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, b
             return fail(KBBQ_ERANGE, bad);
         }
     }
-    CU(cudaStreamSynchronize(ctx->stream));  // the caller may reuse everything but h->qual
-    if (!async_qual) CU(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse h->qual
+    if (mode != 2) CU(cudaStreamSynchronize(ctx->stream));     // the caller may reuse everything but h->qual
+    if (mode == 0) CU(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse h->qual
     *out = b;
     return KBBQ_OK;
 }
@@ -1219,6 +1333,8 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
     if (int rc = filter_ok(ctx, KBBQ_FILTER_SAMPLED)) return rc;
     kbbq_dbatch* b = const_cast<kbbq_dbatch*>(cb);
     if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
+    if (b->all_on_copy)
+        if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_slots) {
         const uint64_t chunks = (b->n_slots + 1023) / 1024;
@@ -1295,7 +1411,7 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     }
     if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
-    if (b->qmask_needs_quals)  // pass 2 reads the quality MASKS only; they are already there when the host brought them
+    if (b->qmask_needs_quals || b->all_on_copy)  // pass 2 reads the quality MASKS only; they are already there when the host brought them
         if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {

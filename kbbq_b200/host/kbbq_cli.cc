@@ -8,6 +8,7 @@
 #include <getopt.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <ctime>
@@ -46,7 +47,26 @@ static struct option long_options[] = {
     {"ksize", required_argument, 0, 'k'},   {"use-oq", no_argument, 0, 'u'},        {"set-oq", no_argument, 0, 's'},
     {"genomelen", required_argument, 0, 'g'}, {"coverage", required_argument, 0, 'c'}, {"fixed", required_argument, 0, 'f'},
     {"alpha", required_argument, 0, 'a'},   {"threads", required_argument, 0, 't'}, {"seed", required_argument, 0, 'S'},
+    {"gpus", required_argument, 0, 'G'},    {"report", required_argument, 0, 'R'},
     {0, 0, 0, 0}};
+
+// true when every base of the store is one of "ACGTN": packed batches then compare exactly like the characters do
+static bool plain_alphabet(const kbbq::ReadStore& rs, unsigned nt) {
+    bool ok[256] = {false};
+    for (char c : std::string("ACGTN")) ok[(unsigned char)c] = true;
+    const size_t total = rs.seq.size();
+    std::atomic<bool> plain{true};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t] {
+            bool mine = true;
+            const char* p = rs.seq.data();
+            for (size_t i = total * t / nt; i < total * (t + 1) / nt; ++i) mine = mine && ok[(unsigned char)p[i]];
+            if (!mine) plain.store(false, std::memory_order_relaxed);
+        });
+    for (auto& t : th) t.join();
+    return plain.load();
+}
 
 int main(int argc, char* argv[]) {
     int k = 32;
@@ -54,11 +74,11 @@ int main(int argc, char* argv[]) {
     uint64_t genomelen = 0;
     unsigned int coverage = 0;
     uint32_t seed = 0;
-    int nthreads = 0;
-    std::string fixedinput = "";
+    int nthreads = 0, ngpus = 1;
+    std::string fixedinput = "", reportfn = "";
     bool use_oq = false, set_oq = false;
     int opt = 0, opt_idx = 0;
-    while ((opt = getopt_long(argc, argv, "k:usg:c:f:a:t:S:", long_options, &opt_idx)) != -1) {
+    while ((opt = getopt_long(argc, argv, "k:usg:c:f:a:t:S:G:R:", long_options, &opt_idx)) != -1) {
         switch (opt) {
         case 'k':
             k = std::stoi(std::string(optarg));
@@ -78,6 +98,14 @@ int main(int argc, char* argv[]) {
             if (nthreads < 0) std::cerr << put_now << " Error: threads must be >= 0." << std::endl;
             break;
         case 'S': seed = (uint32_t)std::stoul(std::string(optarg)); break;
+        case 'G':  // GPUs to shard the reads over (0 = every device of the box)
+            ngpus = std::stoi(std::string(optarg));
+            if (ngpus < 0) {
+                std::cerr << put_now << " Error: gpus must be >= 0." << std::endl;
+                return 1;
+            }
+            break;
+        case 'R': reportfn = std::string(optarg); break;  // GATK-style report of the covariate tables
         case '?':
         default:
             std::cerr << put_now << "  Unknown argument " << (char)opt << std::endl;
@@ -116,7 +144,17 @@ int main(int argc, char* argv[]) {
             return 1;
         }
         const int n_rg = (int)std::max<size_t>(1, readutils::CReadData::rg_to_int.size());
-        kbbq::Session session(k, n_rg, (int)std::max<uint32_t>(1, store.max_len));
+        std::vector<int> devices;
+        {
+            const int have = kbbq_device_count();
+            const int want = ngpus == 0 ? have : ngpus;
+            if (want > have && have > 0) {
+                std::cerr << put_now << " Error: " << want << " GPUs requested, " << have << " present." << std::endl;
+                return 1;
+            }
+            for (int d = 0; d < std::max(1, want); ++d) devices.push_back(d);
+        }
+        kbbq::Session session(k, n_rg, (int)std::max<uint32_t>(1, store.max_len), devices);
         covariateutils::CCovariateData data;
         timer.mark("GPU context");
 
@@ -141,7 +179,15 @@ int main(int argc, char* argv[]) {
                 std::cerr << put_now << " Estimating alpha." << std::endl;
                 if (coverage == 0) {
                     std::cerr << put_now << " Estimating coverage." << std::endl;
-                    uint64_t seqlen = store.off.back();  // sum of sequence lengths (kbbq.cc:234-236)
+                    // sum of sequence lengths (kbbq.cc:234-236): the coverage pass, over the batches the GPUs hold
+                    session.ensure_resident(store);
+                    std::atomic<uint64_t> seqlen_dev{0};
+                    session.for_each_batch([&](kbbq_ctx* c, kbbq_dbatch* d, kbbq::SessionBatch&) {
+                        uint64_t t = 0;
+                        if (kbbq_batch_total_bases(c, d, &t) != KBBQ_OK) kbbq::throw_last(-3);
+                        seqlen_dev += t;
+                    });
+                    uint64_t seqlen = seqlen_dev.load();
                     std::cerr << put_now << " Total Sequence length: " << seqlen << std::endl;
                     std::cerr << put_now << " Genome length: " << genomelen << std::endl;
                     coverage = seqlen / genomelen;
@@ -191,33 +237,55 @@ int main(int argc, char* argv[]) {
             readutils::CReadData::rg_to_pu = saved_pu;
             const kbbq::ReadStore& fx = fixedfile->store();
             session.ensure_resident(store);
-            for (size_t b = 0; b < session.batches().size(); ++b) {
-                std::vector<uint32_t> bits(std::max<uint64_t>(session.n_words(b), 1), 0);
-                const size_t first = session.batch_ranges()[b].first;
-                const size_t last = std::min(session.batch_ranges()[b].second, fx.n());
-                // character comparison like the reference's std::not_equal_to<char>; a read owns its words of `bits`, so
-                // ranges of reads go to threads.  Like the reference's loop (kbbq.cc:370) only reads that have a partner in
-                // the fixed file are consumed.  (The reference reads past the end of a fixed read that is shorter than
-                // its partner; here the bases without a partner count as error-free.)
-                const unsigned nt = std::max(1u, std::min(16u, nthreads > 0 ? (unsigned)nthreads : std::thread::hardware_concurrency()));
+            const unsigned nt = std::max(1u, std::min(16u, nthreads > 0 ? (unsigned)nthreads : std::thread::hardware_concurrency()));
+            // Both files in upper-case ACGTN (the normal case): the comparison runs on the device over the packed batches
+            // (kbbq_fixed_errors).  Anything else -- soft-masked or IUPAC letters, which packing folds together -- is
+            // compared character by character here, like the reference's std::not_equal_to<char>.
+            const bool on_device = fx.max_len <= store.max_len && plain_alphabet(store, nt) && plain_alphabet(fx, nt) && !getenv("KBBQ_FIXED_ON_HOST");
+            for (kbbq_ctx* c : session.contexts())
+                if (kbbq_covariates_reset(c) != KBBQ_OK) kbbq::throw_last(-3);
+            session.for_each_batch([&](kbbq_ctx* c, kbbq_dbatch* d, kbbq::SessionBatch& sb) {
+                // like the reference's loop (kbbq.cc:370) only reads that have a partner in the fixed file are consumed
+                const size_t first = sb.lo, last = std::min(sb.hi, fx.n());
+                const uint32_t n_first = (uint32_t)(last > first ? last - first : 0);
+                if (on_device) {
+                    if (!n_first) return;
+                    kbbq_dbatch* f = session.upload_range(fx, first, last, sb.gpu);
+                    const int rc = kbbq_fixed_errors(c, d, f, n_first, nullptr);
+                    kbbq_batch_free(c, f);
+                    if (rc != KBBQ_OK) kbbq::throw_last(rc);
+                    return;
+                }
+                // a read owns its words of `bits`, so ranges of reads go to threads.  (The reference reads past the end of
+                // a fixed read that is shorter than its partner; here the bases without a partner count as error-free.)
+                std::vector<uint32_t> bits(std::max<uint64_t>(sb.n_words, 1), 0);
                 std::vector<std::thread> th;
                 for (unsigned t = 0; t < nt; ++t)
                     th.emplace_back([&, t] {
                         const size_t span = last > first ? last - first : 0;
                         for (size_t i = first + span * t / nt; i < first + span * (t + 1) / nt; ++i) {
                             const size_t L = std::min<size_t>(store.off[i + 1] - store.off[i], fx.off[i + 1] - fx.off[i]);
-                            const uint32_t wo = session.word_off(b)[i - first];
+                            const uint32_t wo = sb.word_off[i - first];
                             for (size_t j = 0; j < L; ++j)
                                 if (store.seq[store.off[i] + j] != fx.seq[fx.off[i] + j]) bits[wo + (j >> 5)] |= 1u << (j & 31);
                         }
                     });
                 for (auto& t : th) t.join();
-                const uint32_t n_first = (uint32_t)(last > first ? last - first : 0);
-                if (kbbq_consume_errors_n(session.ctx(), session.batches()[b], bits.data(), n_first) != KBBQ_OK) kbbq::throw_last(-3);
-            }
+                if (kbbq_consume_errors_n(c, d, bits.data(), n_first) != KBBQ_OK) kbbq::throw_last(-3);
+            });
             data = recalibrateutils::download_covariates(session, n_rg, (int)std::max<uint32_t>(1, store.max_len));
         }
 
+        if (reportfn != "") {  // GATK-style text report of the count tables (the reference's gatkreport.hh was written for this)
+            std::vector<std::string> names(n_rg);
+            for (const auto& kv : readutils::CReadData::rg_to_int)
+                if (kv.second >= 0 && kv.second < n_rg) names[kv.second] = kv.first;
+            std::vector<const char*> np;
+            for (int r = 0; r < n_rg; ++r) np.push_back(names[r].empty() ? nullptr : names[r].c_str());
+            if (kbbq_report_tables_host(reportfn.c_str(), data.n_rg, data.max_cycle, data.d_rgc.data(), data.d_qc.data(), data.d_cyc.data(),
+                                        data.d_dic.data(), np.data()) != KBBQ_OK)
+                std::cerr << put_now << " Warning: " << kbbq_last_error() << std::endl;
+        }
         std::cerr << put_now << " Training model" << std::endl;
         covariateutils::dq_t dqs = data.get_dqs();
         timer.mark("model fit");

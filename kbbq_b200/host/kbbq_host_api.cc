@@ -35,55 +35,227 @@ Session& Session::current() {
 }
 void Session::set_current(Session* s) { g_current = s; }
 
-Session::Session(int k, int n_rg, int max_cycle, int device) : k_(k) {
-    CK(kbbq_ctx_create(device, k, n_rg, max_cycle, &ctx_));
+template <class T>
+void Pinned<T>::resize(size_t n) {
+    release();
+    void* p = nullptr;
+    CK(kbbq_host_alloc(std::max<size_t>(n, 1) * sizeof(T), &p));
+    p_ = static_cast<T*>(p);
+    n_ = n;
+}
+template <class T>
+void Pinned<T>::release() {
+    if (p_) kbbq_host_free(p_);
+    p_ = nullptr;
+    n_ = 0;
+}
+template class Pinned<uint64_t>;
+template class Pinned<uint32_t>;
+template class Pinned<uint8_t>;
+
+Session::Session(int k, int n_rg, int max_cycle, int device) : Session(k, n_rg, max_cycle, std::vector<int>{device}) {}
+
+Session::Session(int k, int n_rg, int max_cycle, const std::vector<int>& devices) : devices_(devices), k_(k) {
+    if (devices.empty()) throw std::invalid_argument("a Session needs at least one device");
+    try {
+        for (int d : devices) {
+            kbbq_ctx* c = nullptr;
+            CK(kbbq_ctx_create(d, k, n_rg, max_cycle, &c));
+            ctx_.push_back(c);
+        }
+    } catch (...) {
+        for (kbbq_ctx* c : ctx_) kbbq_ctx_destroy(c);
+        throw;
+    }
+    streaming_.assign(ctx_.size(), false);
     if (!g_current) g_current = this;
 }
 Session::~Session() {
-    for (kbbq_dbatch* b : batches_) kbbq_batch_free(ctx_, b);
-    kbbq_ctx_destroy(ctx_);
+    for (SessionBatch& b : batches_)
+        if (b.dev) kbbq_batch_free(ctx_[b.gpu], b.dev);
+    for (kbbq_ctx* c : ctx_) kbbq_ctx_destroy(c);
     if (g_current == this) g_current = nullptr;
+}
+
+// Pack reads [sb.lo, sb.hi) of the store into the kbbq_batch layout.  With `pinned_copy` the arrays are the batch's own
+// pinned members (kept for re-streaming); otherwise thread-local scratch that lives until the next call on this thread.
+void Session::pack(const ReadStore& rs, SessionBatch& sb, bool pinned_copy, kbbq_batch& hb, std::vector<uint16_t>*) {
+    const size_t m = sb.hi - sb.lo;
+    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max<size_t>(1, ctx_.size())));
+    std::vector<uint64_t> off(m + 1);
+    for (size_t i = 0; i <= m; ++i) off[i] = rs.off[sb.lo + i] - rs.off[sb.lo];
+    uint64_t nw = 0;
+    uint32_t ml = 0;
+    CK(kbbq_pack_size(m, off.data(), &nw, &ml));
+    sb.n_words = nw;
+    sb.max_len = ml;
+    sb.word_off.resize(m + 1);
+    // kbbq_pack_reads writes every word and byte (padding included): no need to zero hundreds of MB first
+    thread_local Column<uint64_t> t_bases;
+    thread_local Column<uint32_t> t_nmask, t_len;
+    thread_local Column<uint8_t> t_qual;
+    uint64_t* bases;
+    uint32_t *nmask, *len;
+    uint8_t* qual;
+    const size_t nw1 = std::max<uint64_t>(nw, 1);
+    if (pinned_copy) {
+        sb.bases.resize(nw1); sb.nmask.resize(nw1); sb.qual.resize(nw1 * 32); sb.len.resize(std::max<size_t>(m, 1)); sb.qmask.resize(nw1 * 2);
+        bases = sb.bases.data(); nmask = sb.nmask.data(); qual = sb.qual.data(); len = sb.len.data();
+        sb.has_host_copy = true;
+    } else {
+        t_bases.resize(nw1); t_nmask.resize(nw1); t_qual.resize(nw1 * 32); t_len.resize(std::max<size_t>(m, 1));
+        bases = t_bases.data(); nmask = t_nmask.data(); qual = t_qual.data(); len = t_len.data();
+    }
+    if (nw == 0) { bases[0] = 0; nmask[0] = 0; std::memset(qual, 0, 32); }
+    CK(kbbq_pack_reads(m, rs.seq.data() + rs.off[sb.lo], off.data(), rs.qual.data() + rs.off[sb.lo], bases, nmask, qual, sb.word_off.data(), len, nt));
+    uint64_t slots = 0;
+    for (size_t i = 0; i < m; ++i) slots += len[i] >= (uint32_t)k_ ? len[i] - (uint32_t)k_ + 1 : 0;
+    sb.slots = slots;
+    hb.n_reads = (uint32_t)m; hb.max_len = ml; hb.n_words = nw;
+    hb.bases = bases; hb.nmask = nmask; hb.qual = qual; hb.word_off = sb.word_off.data();
+    hb.len = len; hb.rg = rs.rg.data() + sb.lo; hb.second = rs.second.data() + sb.lo;
+    hb.qmask = nullptr;  // resident batches: derived on the device (the upload is synchronous anyway)
+    if (pinned_copy) {   // streamed batches bring the masks, so that pass 2 never waits for more than its own upload
+        CK(kbbq_quality_masks(nw, qual, sb.qmask.data(), nt));
+        hb.qmask = sb.qmask.data();
+    }
+}
+
+static void host_batch_of(const ReadStore& rs, const SessionBatch& sb, kbbq_batch& hb) {
+    hb.n_reads = (uint32_t)(sb.hi - sb.lo); hb.max_len = sb.max_len; hb.n_words = sb.n_words;
+    hb.bases = sb.bases.data(); hb.nmask = sb.nmask.data(); hb.qual = sb.qual.data(); hb.word_off = sb.word_off.data();
+    hb.len = sb.len.data(); hb.rg = rs.rg.data() + sb.lo; hb.second = rs.second.data() + sb.lo; hb.qmask = sb.qmask.data();
 }
 
 void Session::ensure_resident(const ReadStore& rs) {
     if (resident_ == &rs) return;
     if (resident_) throw std::runtime_error("a Session holds one input at a time");
-    const size_t n = rs.n();
-    const size_t per_batch = 1u << 21;  // 2 M reads per batch keeps word offsets well inside 32 bits
-    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const size_t n = rs.n(), G = ctx_.size();
+    // at most 2 M reads per batch keeps word offsets well inside 32 bits; several GPUs each get a share of a small input
+    size_t per_batch = 1u << 21;
+    if (G > 1) per_batch = std::max<size_t>(1, std::min(per_batch, (n + G - 1) / G));
     for (size_t lo = 0; lo < n || (n == 0 && lo == 0); lo += per_batch) {
-        const size_t hi = std::min(n, lo + per_batch);
-        const size_t m = hi - lo;
-        std::vector<uint64_t> off(m + 1);
-        for (size_t i = 0; i <= m; ++i) off[i] = rs.off[lo + i] - rs.off[lo];
-        uint64_t nw = 0;
-        uint32_t ml = 0;
-        CK(kbbq_pack_size(m, off.data(), &nw, &ml));
-        // kbbq_pack_reads writes every word and byte (padding included): no need to zero 350 MB first
-        Column<uint64_t> bases;
-        Column<uint32_t> nmask;
-        Column<uint8_t> qual;
-        bases.resize(std::max<uint64_t>(nw, 1));
-        nmask.resize(std::max<uint64_t>(nw, 1));
-        qual.resize(std::max<uint64_t>(nw, 1) * 32);
-        if (nw == 0) { bases[0] = 0; nmask[0] = 0; std::memset(qual.data(), 0, 32); }
-        std::vector<uint32_t> word_off(m + 1), len(std::max<size_t>(m, 1));
-        CK(kbbq_pack_reads(m, rs.seq.data() + rs.off[lo], off.data(), rs.qual.data() + rs.off[lo], bases.data(), nmask.data(),
-                           qual.data(), word_off.data(), len.data(), nt));
-        kbbq_batch hb;
-        hb.n_reads = (uint32_t)m; hb.max_len = ml; hb.n_words = nw;
-        hb.bases = bases.data(); hb.nmask = nmask.data(); hb.qual = qual.data(); hb.word_off = word_off.data();
-        hb.len = len.data(); hb.rg = rs.rg.data() + lo; hb.second = rs.second.data() + lo;
-        hb.qmask = nullptr;  // derived on the device: this upload is synchronous anyway
-        kbbq_dbatch* db = nullptr;
-        CK(kbbq_batch_upload(ctx_, &hb, &db));
-        batches_.push_back(db);
-        ranges_.emplace_back(lo, hi);
-        word_off_.push_back(std::move(word_off));
-        n_words_.push_back(nw);
+        SessionBatch sb;
+        sb.lo = lo;
+        sb.hi = std::min(n, lo + per_batch);
+        sb.gpu = (int)(batches_.size() % G);
+        batches_.push_back(std::move(sb));
         if (n == 0) break;
     }
+    // what a GPU's share would take resident (inputs, flags, new qualities), against what it has left beside the filters
+    // and the staging arrays of one batch's inserts
+    std::vector<uint64_t> need(G, 0), biggest(G, 0);
+    for (const SessionBatch& sb : batches_) {
+        const uint64_t bases = rs.off[sb.hi] - rs.off[sb.lo], reads = sb.hi - sb.lo;
+        const uint64_t words = bases / 32 + reads;  // upper bound
+        need[sb.gpu] += words * 96 + reads * 32;
+        biggest[sb.gpu] = std::max(biggest[sb.gpu], bases * 16 + (words * 96 + reads * 32));
+    }
+    for (size_t g = 0; g < G; ++g) {
+        uint64_t budget = 0;
+        if (const char* e = getenv("KBBQ_RESIDENT_BYTES")) {
+            budget = std::strtoull(e, nullptr, 10);
+        } else {
+            uint64_t free_b = 0, total_b = 0;
+            CK(kbbq_device_memory(devices_[g], &free_b, &total_b));
+            const uint64_t reserve = biggest[g] + (2ull << 30);
+            budget = free_b > reserve ? free_b - reserve : 0;
+        }
+        streaming_[g] = need[g] > budget;
+    }
+    // pack (and upload the resident ones), one host thread per GPU
+    std::vector<std::exception_ptr> err(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            try {
+                for (SessionBatch& sb : batches_) {
+                    if ((size_t)sb.gpu != g) continue;
+                    kbbq_batch hb;
+                    pack(rs, sb, streaming_[g], hb, nullptr);
+                    if (!streaming_[g]) CK(kbbq_batch_upload(ctx_[g], &hb, &sb.dev));
+                }
+            } catch (...) {
+                err[g] = std::current_exception();
+            }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : err)
+        if (e) std::rethrow_exception(e);
+    uint64_t first = 0;  // the one serial sampling stream (htsiter.cc:113-129): a batch starts where the batches before it end
+    for (SessionBatch& sb : batches_) {
+        sb.first_slot = first;
+        first += sb.slots;
+    }
     resident_ = &rs;
+}
+
+void Session::for_each_batch(const std::function<void(kbbq_ctx*, kbbq_dbatch*, SessionBatch&)>& fn) {
+    if (!resident_) throw std::runtime_error("no input is resident");
+    const size_t G = ctx_.size();
+    std::vector<std::exception_ptr> err(G);
+    auto work = [&](size_t g) {
+        try {
+            std::vector<SessionBatch*> mine;
+            for (SessionBatch& sb : batches_)
+                if ((size_t)sb.gpu == g) mine.push_back(&sb);
+            if (!streaming_[g]) {
+                for (SessionBatch* sb : mine) fn(ctx_[g], sb->dev, *sb);
+                return;
+            }
+            // streamed: batch i+1 travels (copy stream) while the kernels of batch i run; two batches in device memory
+            auto upload = [&](SessionBatch* sb) {
+                kbbq_batch hb;
+                host_batch_of(*resident_, *sb, hb);
+                kbbq_dbatch* d = nullptr;
+                CK(kbbq_batch_upload_stream(ctx_[g], &hb, &d));
+                return d;
+            };
+            kbbq_dbatch* next = mine.empty() ? nullptr : upload(mine[0]);
+            for (size_t i = 0; i < mine.size(); ++i) {
+                kbbq_dbatch* cur = next;
+                next = nullptr;
+                try {
+                    if (i + 1 < mine.size()) next = upload(mine[i + 1]);
+                    fn(ctx_[g], cur, *mine[i]);
+                } catch (...) {
+                    kbbq_sync(ctx_[g]);
+                    kbbq_batch_free(ctx_[g], cur);
+                    if (next) kbbq_batch_free(ctx_[g], next);
+                    throw;
+                }
+                kbbq_batch_free(ctx_[g], cur);  // stream ordered: after the kernels that read it
+            }
+            CK(kbbq_sync(ctx_[g]));
+        } catch (...) {
+            err[g] = std::current_exception();
+        }
+    };
+    if (G == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; ++g) th.emplace_back(work, g);
+        for (auto& t : th) t.join();
+    }
+    for (auto& e : err)
+        if (e) std::rethrow_exception(e);
+}
+
+void Session::merge_filter(int which) {
+    if (ctx_.size() > 1) CK(kbbq_bloom_or_allreduce_local(ctx_.data(), (int)ctx_.size(), which));
+}
+
+kbbq_dbatch* Session::upload_range(const ReadStore& rs, size_t lo, size_t hi, int g) {
+    SessionBatch sb;
+    sb.lo = lo;
+    sb.hi = hi;
+    sb.gpu = g;
+    kbbq_batch hb;
+    pack(rs, sb, false, hb, nullptr);
+    kbbq_dbatch* d = nullptr;
+    CK(kbbq_batch_upload(ctx_[g], &hb, &d));
+    return d;
 }
 
 }  // namespace kbbq
@@ -118,7 +290,8 @@ Bloom::Bloom(unsigned long long projected, double fpr, unsigned long long seed) 
     Session& ses = Session::current();
     slot_ = ses.next_filter_slot();
     if (slot_ > 1) throw std::invalid_argument("this build holds two filters per session (subsampled, trusted)");
-    CK(kbbq_bloom_create(ses.ctx(), slot_, projected, fpr, seed));  // KBBQ_EINVAL -> std::invalid_argument (bloom.cc:18-21)
+    for (kbbq_ctx* c : ses.contexts())  // every GPU holds a full-size filter; partial results are merged after the pass
+        CK(kbbq_bloom_create(c, slot_, projected, fpr, seed));  // KBBQ_EINVAL -> std::invalid_argument (bloom.cc:18-21)
     CK(kbbq_bloom_info(ses.ctx(), slot_, &params));
 }
 void Bloom::insert(const Kmer& kmer) {
@@ -654,7 +827,7 @@ int StoreFile::write() {
     return n;
 }
 
-int StoreFile::write_all(const kbbq::Session& ses, const std::vector<std::vector<uint8_t>>& newq) {
+int StoreFile::write_all(const kbbq::Session& ses, const std::vector<kbbq::Pinned<uint8_t>>& newq) {
     if (!out_ || flush_pending(false) < 0) return -1;
     const kbbq::ReadStore& rs = *store_;
     // Jobs of 8 Ki records are formatted and compressed by a pool (dynamic hand-out: records and compression ratios
@@ -663,9 +836,9 @@ int StoreFile::write_all(const kbbq::Session& ses, const std::vector<std::vector
     const int nt = pool_size(nthreads_);
     struct Job { size_t b, lo, hi; };
     std::vector<Job> jobs;
-    for (size_t b = 0; b < ses.batch_ranges().size(); ++b)
-        for (size_t lo = ses.batch_ranges()[b].first; lo < ses.batch_ranges()[b].second; lo += chunk)
-            jobs.push_back({b, lo, std::min(ses.batch_ranges()[b].second, lo + chunk)});
+    for (size_t b = 0; b < ses.batches().size(); ++b)
+        for (size_t lo = ses.batches()[b].lo; lo < ses.batches()[b].hi; lo += chunk)
+            jobs.push_back({b, lo, std::min(ses.batches()[b].hi, lo + chunk)});
     const size_t window = (size_t)nt * 8;
     std::vector<std::string> outs(jobs.size());
     std::vector<char> done(jobs.size(), 0);
@@ -688,9 +861,9 @@ int StoreFile::write_all(const kbbq::Session& ses, const std::vector<std::vector
                 }
                 const Job& jb = jobs[j];
                 text.clear();
-                const size_t first = ses.batch_ranges()[jb.b].first;
+                const size_t first = ses.batches()[jb.b].lo;
                 for (size_t i = jb.lo; i < jb.hi; ++i)
-                    format_record(i, newq[jb.b].data() + (size_t)ses.word_off(jb.b)[i - first] * 32, text);
+                    format_record(i, newq[jb.b].data() + (size_t)ses.batches()[jb.b].word_off[i - first] * 32, text);
                 std::string z;
                 const bool ok = bgzf_compress(text, z);
                 std::lock_guard<std::mutex> lk(mu);
@@ -970,11 +1143,13 @@ void subsample_kmers(htsiter::KmerSubsampler& s, bloom::Bloom& sampled) {
     ses.ensure_resident(s.file->store());
     if (sampled.slot() != KBBQ_FILTER_SAMPLED) throw std::invalid_argument("the first Bloom of a session is the subsampled one");
     // Random::Seed takes a uint32 (the uint64 seed is truncated by overload resolution, htsiter.hh:143)
-    CK(kbbq_sampler_seed(ses.ctx(), (uint32_t)s.seed, s.alpha));
-    for (kbbq_dbatch* b : ses.batches()) {
-        CK(kbbq_pass1_subsample(ses.ctx(), b));
-        s.total_kmers += kbbq_batch_slots(b);
-    }
+    for (kbbq_ctx* c : ses.contexts()) CK(kbbq_sampler_seed(c, (uint32_t)s.seed, s.alpha));
+    ses.for_each_batch([](kbbq_ctx* c, kbbq_dbatch* d, kbbq::SessionBatch& sb) {
+        CK(kbbq_sampler_seek(c, sb.first_slot));  // one serial stream over the whole file, whichever GPU holds the batch
+        CK(kbbq_pass1_subsample(c, d));
+    });
+    for (const kbbq::SessionBatch& sb : ses.batches()) s.total_kmers += sb.slots;
+    ses.merge_filter(KBBQ_FILTER_SAMPLED);
     s.not_eof = false;
 }
 
@@ -983,8 +1158,9 @@ void find_trusted_kmers(htsiter::HTSFile* file, bloom::Bloom& trusted, const blo
     ses.ensure_resident(file->store());
     if (k != ses.k() || (int)thresholds.size() < k + 1) throw std::invalid_argument("k / thresholds do not match the session");
     (void)trusted; (void)sampled;
-    CK(kbbq_set_thresholds(ses.ctx(), thresholds.data()));
-    for (kbbq_dbatch* b : ses.batches()) CK(kbbq_pass2_find_trusted(ses.ctx(), b, nullptr));
+    for (kbbq_ctx* c : ses.contexts()) CK(kbbq_set_thresholds(c, thresholds.data()));
+    ses.for_each_batch([](kbbq_ctx* c, kbbq_dbatch* d, kbbq::SessionBatch&) { CK(kbbq_pass2_find_trusted(c, d, nullptr)); });
+    ses.merge_filter(KBBQ_FILTER_TRUSTED);
 }
 
 static void densify(covariateutils::CCovariateData& d, int R, int C) {
@@ -1036,6 +1212,16 @@ covariateutils::CCovariateData download_covariates(Session& ses, int R, int C) {
     d.d_cyc.resize((size_t)R * 94 * 2 * C * 2);
     d.d_dic.resize((size_t)R * 94 * 16 * 2);
     CK(kbbq_covariates_download(ses.ctx(), d.d_rgc.data(), d.d_qc.data(), d.d_cyc.data(), d.d_dic.data()));
+    if (ses.n_gpus() > 1) {  // the SUM merge of the per-GPU partial tables (a few hundred KB each) happens here, on the host
+        std::vector<uint64_t> a(d.d_rgc.size()), b(d.d_qc.size()), c(d.d_cyc.size()), e(d.d_dic.size());
+        for (int g = 1; g < ses.n_gpus(); ++g) {
+            CK(kbbq_covariates_download(ses.ctx(g), a.data(), b.data(), c.data(), e.data()));
+            for (size_t i = 0; i < a.size(); ++i) d.d_rgc[i] += a[i];
+            for (size_t i = 0; i < b.size(); ++i) d.d_qc[i] += b[i];
+            for (size_t i = 0; i < c.size(); ++i) d.d_cyc[i] += c[i];
+            for (size_t i = 0; i < e.size(); ++i) d.d_dic[i] += e[i];
+        }
+    }
     densify(d, R, C);
     return d;
 }
@@ -1045,8 +1231,8 @@ covariateutils::CCovariateData get_covariatedata(htsiter::HTSFile* file, const b
     ses.ensure_resident(file->store());
     if (k != ses.k()) throw std::invalid_argument("k does not match the session");
     (void)trusted;
-    CK(kbbq_covariates_reset(ses.ctx()));
-    for (kbbq_dbatch* b : ses.batches()) CK(kbbq_pass3_covariates(ses.ctx(), b, nullptr));
+    for (kbbq_ctx* c : ses.contexts()) CK(kbbq_covariates_reset(c));
+    ses.for_each_batch([](kbbq_ctx* c, kbbq_dbatch* d, kbbq::SessionBatch&) { CK(kbbq_pass3_covariates(c, d, nullptr)); });
     const int R = (int)std::max<size_t>(1, readutils::CReadData::rg_to_int.size());
     return download_covariates(ses, R, (int)std::max<uint32_t>(1, file->store().max_len));
 }
@@ -1066,25 +1252,25 @@ void recalibrate_and_write(htsiter::HTSFile* in, const covariateutils::dq_t& dqs
         for (size_t qq = 0; qq < dqs.dinucdq[r].size(); ++qq)
             for (size_t n = 0; n < dqs.dinucdq[r][qq].size(); ++n) di[((size_t)r * 94 + qq) * 16 + n] = dqs.dinucdq[r][qq][n];
     }
-    CK(kbbq_set_model(ses.ctx(), m.data(), g.data(), q.data(), cy.data(), di.data()));
+    for (kbbq_ctx* c : ses.contexts()) CK(kbbq_set_model(c, m.data(), g.data(), q.data(), cy.data(), di.data()));
     if (in->open_out(outfn) < 0) return;  // error!! TODO (recalibrateutils.cc:92-95)
-    std::vector<std::vector<uint8_t>> newq(ses.batches().size());
-    for (size_t b = 0; b < ses.batches().size(); ++b) {
-        newq[b].resize(std::max<uint64_t>(ses.n_words(b), 1) * 32);
-        CK(kbbq_pass4_recalibrate(ses.ctx(), ses.batches()[b], newq[b].data()));
-    }
+    std::vector<kbbq::Pinned<uint8_t>> newq(ses.batches().size());  // pinned: the device-to-host copies overlap the lookups
+    for (size_t b = 0; b < ses.batches().size(); ++b) newq[b].resize(std::max<uint64_t>(ses.batches()[b].n_words, 1) * 32);
+    ses.for_each_batch([&](kbbq_ctx* c, kbbq_dbatch* d, kbbq::SessionBatch& sb) {
+        CK(kbbq_pass4_recalibrate(c, d, newq[&sb - ses.batches().data()].data()));
+    });
     // fast path: format + compress in parallel, BGZF blocks written in input order
     if (auto* fq = dynamic_cast<htsiter::StoreFile*>(in)) {
-        fq->write_all(ses, newq);
+        if (fq->write_all(ses, newq) < 0) throw std::runtime_error("writing the output failed");
         return;
     }
     // generic path, one record at a time like the reference's loop (recalibrateutils.cc:96-104)
     size_t b = 0, idx = 0;
     const kbbq::ReadStore& rs = in->store();
     while (in->next() >= 0) {
-        while (idx >= ses.batch_ranges()[b].second) ++b;
+        while (idx >= ses.batches()[b].hi) ++b;
         const size_t L = rs.off[idx + 1] - rs.off[idx];
-        const uint8_t* src = newq[b].data() + (size_t)ses.word_off(b)[idx - ses.batch_ranges()[b].first] * 32;
+        const uint8_t* src = newq[b].data() + (size_t)ses.batches()[b].word_off[idx - ses.batches()[b].lo] * 32;
         in->recalibrate(std::vector<uint8_t>(src, src + L));
         ++idx;
         if (in->write() < 0) return;  // error! TODO (recalibrateutils.cc:101-103)

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <memory>
 #include <cstring>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -74,32 +75,87 @@ struct ReadStore {
     std::vector<uint64_t> ref_len;
 };
 
-// One GPU context plus the resident batches of one input.
+// Page-locked host array (kbbq_host_alloc): uploads from it and downloads into it are asynchronous.
+template <class T>
+class Pinned {
+public:
+    Pinned() = default;
+    Pinned(const Pinned&) = delete;
+    Pinned& operator=(const Pinned&) = delete;
+    Pinned(Pinned&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    Pinned& operator=(Pinned&& o) noexcept { if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; } return *this; }
+    ~Pinned() { release(); }
+    void resize(size_t n);  // contents are NOT preserved
+    void release();
+    T* data() { return p_; }
+    const T* data() const { return p_; }
+    size_t size() const { return n_; }
+    T& operator[](size_t i) { return p_[i]; }
+    const T& operator[](size_t i) const { return p_[i]; }
+
+private:
+    T* p_ = nullptr;
+    size_t n_ = 0;
+};
+
+// One batch of the input as the Session holds it: reads [lo, hi) of the store, dealt to one GPU.
+struct SessionBatch {
+    size_t lo = 0, hi = 0;
+    int gpu = 0;
+    uint64_t n_words = 0, slots = 0, first_slot = 0;  // k-mer slots of the batch / of all batches before it (the sampling stream)
+    uint32_t max_len = 0;
+    std::vector<uint32_t> word_off;                   // kept for the writer
+    kbbq_dbatch* dev = nullptr;                       // resident copy, or nullptr while evicted
+    // packed host copy (pinned), kept only when the GPU's batches do not all fit in its memory
+    Pinned<uint64_t> bases;
+    Pinned<uint32_t> nmask, len, qmask;
+    Pinned<uint8_t> qual;
+    bool has_host_copy = false;
+};
+
+// The GPU contexts of one run plus the batches of one input.
+//
+// Reads are cut into batches of at most 2 M reads and dealt round-robin to the GPUs; every GPU holds full-size filters
+// and count tables, and the partial results are merged after passes 1-3 (kbbq_bloom_or_allreduce_local over peer memory;
+// the count tables, a few hundred KB, are summed on the host) -- SURVEY.md section 8(e).  Batches stay resident across
+// the passes while they fit; a GPU whose share does not fit keeps packed, pinned host copies instead and streams them
+// through its memory once per pass, the upload of batch i+1 (kbbq_batch_upload_stream) overlapping the kernels of batch i
+// -- as the reference re-reads its file once per pass (kbbq.cc:232,258,336,365,456), minus the parsing.
+// KBBQ_RESIDENT_BYTES overrides the per-GPU budget (tests force streaming with it).
 class Session {
 public:
     Session(int k, int n_rg, int max_cycle, int device = 0);
+    Session(int k, int n_rg, int max_cycle, const std::vector<int>& devices);
     ~Session();
     Session(const Session&) = delete;
-    kbbq_ctx* ctx() const { return ctx_; }
+    int n_gpus() const { return (int)ctx_.size(); }
+    kbbq_ctx* ctx(int g = 0) const { return ctx_[g]; }
+    const std::vector<kbbq_ctx*>& contexts() const { return ctx_; }
     int k() const { return k_; }
-    // pack + upload the store once; later calls are no-ops
+    // pack the store into batches once (uploading those that stay resident); later calls are no-ops
     void ensure_resident(const ReadStore& rs);
-    const std::vector<kbbq_dbatch*>& batches() const { return batches_; }
-    const std::vector<std::pair<size_t, size_t>>& batch_ranges() const { return ranges_; }
-    const std::vector<uint32_t>& word_off(size_t b) const { return word_off_[b]; }
-    uint64_t n_words(size_t b) const { return n_words_[b]; }
+    std::vector<SessionBatch>& batches() { return batches_; }
+    const std::vector<SessionBatch>& batches() const { return batches_; }
+    bool streaming(int g) const { return streaming_[g]; }
+    // Run fn(ctx, device batch, batch) for every batch, one host thread per GPU, each GPU's batches in input order;
+    // streamed batches are uploaded one ahead and freed after their turn.  The first exception of any thread is rethrown.
+    void for_each_batch(const std::function<void(kbbq_ctx*, kbbq_dbatch*, SessionBatch&)>& fn);
+    // merge the partial filters of all GPUs (no-op on one GPU)
+    void merge_filter(int which);
+    // pack + upload reads [lo, hi) of ANOTHER store to GPU g (--fixed mode's second file); the caller frees the batch
+    kbbq_dbatch* upload_range(const ReadStore& rs, size_t lo, size_t hi, int g);
     static Session& current();           // the session the mirror classes use
     static void set_current(Session* s);
     int next_filter_slot() { return next_slot_++; }
 
 private:
-    kbbq_ctx* ctx_ = nullptr;
+    void pack(const ReadStore& rs, SessionBatch& sb, bool pinned_copy, kbbq_batch& hb, std::vector<uint16_t>* rg_tmp);
+    std::vector<kbbq_ctx*> ctx_;
+    std::vector<int> devices_;
+    std::vector<bool> streaming_;
     int k_;
     const ReadStore* resident_ = nullptr;
-    std::vector<kbbq_dbatch*> batches_;
-    std::vector<std::pair<size_t, size_t>> ranges_;
-    std::vector<std::vector<uint32_t>> word_off_;
-    std::vector<uint64_t> n_words_;
+    std::vector<SessionBatch> batches_;
     int next_slot_ = 0;
 };
 
@@ -222,7 +278,7 @@ public:
     int write() override;
     const kbbq::ReadStore& store() const override { return *store_; }
     // mirror-only: write every record with new qualities (layout of kbbq_batch.qual per batch), in input order
-    int write_all(const kbbq::Session& s, const std::vector<std::vector<uint8_t>>& newq);
+    int write_all(const kbbq::Session& s, const std::vector<kbbq::Pinned<uint8_t>>& newq);
 
 protected:
     StoreFile(std::shared_ptr<kbbq::ReadStore> st, int nthreads) : store_(std::move(st)), nthreads_(nthreads) {}

@@ -152,3 +152,93 @@ def test_cli_fixed_mode_with_a_shorter_fixed_file(tmp_path):
     assert r.returncode == 0
     got, _ = _run(args, tmp_path)
     assert got == gzip.open(tmp_path / "ref.gz").read()
+
+
+def _run_env(args, tmp_path, env):
+    out = tmp_path / "out_env.gz"
+    with open(out, "wb") as fo:
+        r = subprocess.run([CLI] + args, stdout=fo, stderr=subprocess.PIPE, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stderr.decode()
+    return gzip.open(out).read(), r.stderr.decode()
+
+
+def _big_fastq(tmp_path, n_frac=0.001, seed=79):
+    import sys
+    sys.path.insert(0, ROOT)
+    from kbbq_b200 import synth
+
+    rs = synth.make_reads(200000, 20, 100, seed=seed, n_rg=3, n_frac=n_frac)
+    fq = str(tmp_path / "big.fq")
+    synth.to_fastq(rs, fq)
+    return rs, fq
+
+
+def test_cli_streamed_through_the_device_gives_the_resident_answer(tmp_path):
+    """Inputs larger than device memory are streamed through it once per pass, batch i+1 travelling while batch i is
+    computed (VERDICT r1 'missing' 1).  KBBQ_RESIDENT_BYTES=0 forces that path on a small input; the output must not
+    change by a byte, nor may the host-side or device-side --fixed comparison differ."""
+    rs, fq = _big_fastq(tmp_path)
+    args = ["--seed", "2854027472", "-k", "32", "-g", "200000", "-c", "20", fq]
+    want, _ = _run(args, tmp_path)
+    got, _ = _run_env(args, tmp_path, {"KBBQ_RESIDENT_BYTES": "0"})
+    assert got == want
+    ref = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref")
+    if os.path.exists(ref):
+        with open(tmp_path / "ref.gz", "wb") as fo:
+            r = subprocess.run([ref] + args[2:], stdout=fo, stderr=subprocess.PIPE)
+        assert r.returncode == 0
+        assert got == gzip.open(tmp_path / "ref.gz").read()
+
+
+def test_cli_fixed_mode_device_and_host_comparisons_agree(tmp_path):
+    import numpy as np
+    import sys
+    sys.path.insert(0, ROOT)
+    from kbbq_b200 import synth
+
+    rs, fq = _big_fastq(tmp_path, n_frac=0.002, seed=80)
+    fx = str(tmp_path / "fixed.fq")
+    clean = rs.subset(0, rs.n)
+    clean.seq = np.ascontiguousarray(clean.clean_seq)
+    synth.to_fastq(clean, fx)
+    args = ["-k", "32", "-f", fx, fq]
+    dev, _ = _run(args, tmp_path)
+    host, _ = _run_env(args, tmp_path, {"KBBQ_FIXED_ON_HOST": "1"})
+    streamed, _ = _run_env(args, tmp_path, {"KBBQ_RESIDENT_BYTES": "0"})
+    assert dev == host == streamed
+    ref = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref")
+    if os.path.exists(ref):
+        with open(tmp_path / "ref.gz", "wb") as fo:
+            r = subprocess.run([ref] + args, stdout=fo, stderr=subprocess.PIPE)
+        assert r.returncode == 0
+        assert dev == gzip.open(tmp_path / "ref.gz").read()
+
+
+def test_cli_sharded_over_gpus_gives_the_single_gpu_answer(tmp_path):
+    """--gpus N: reads dealt to N GPUs inside the C++ host, partial filters merged over peer memory, count tables summed
+    (SURVEY.md section 8(e)); byte-identical output, resident and streamed."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from kbbq_b200 import api
+
+    n = api.lib().kbbq_device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs on the box")
+    rs, fq = _big_fastq(tmp_path)
+    args = ["--seed", "2854027472", "-k", "32", "-g", "200000", "-c", "20", fq]
+    want, _ = _run(args, tmp_path)
+    for g in sorted({2, min(n, 4), n}):
+        got, _ = _run(["--gpus", str(g)] + args, tmp_path)
+        assert got == want, f"--gpus {g}"
+    got, _ = _run_env(["--gpus", "2"] + args, tmp_path, {"KBBQ_RESIDENT_BYTES": "0"})
+    assert got == want
+
+
+def test_cli_writes_a_gatk_style_report(tmp_path):
+    rs, fq = _big_fastq(tmp_path)
+    rep = str(tmp_path / "recal.table")
+    _run(["--seed", "2854027472", "-k", "32", "-g", "200000", "-c", "20", "--report", rep, fq], tmp_path)
+    text = open(rep).read()
+    assert text.startswith("#:GATKReport.v1.1:3") and "RecalTable2" in text
+    obs = [int(line.split()[4]) for line in text.split("#:GATKTable:RecalTable0:")[1].split("\n\n")[0].splitlines()[2:]]
+    assert sum(obs) == rs.total_bases
