@@ -206,6 +206,9 @@ uint64_t kbbq_batch_slots(const kbbq_dbatch* b);
 /* ---- passes (each is asynchronous on the context's stream unless a host output pointer is given) ------------------ */
 /* htsiter::KmerSubsampler(file,k,alpha,seed) (htsiter.hh:143): seeds the sampling stream, position 0 */
 int kbbq_sampler_seed(kbbq_ctx* ctx, uint32_t seed, double alpha);
+/* the same from the generator's state (minion::Random::state(), minion.hpp:88): a KmerSubsampler that was constructed
+ * by the reference's own code keeps no seed, only its engine */
+int kbbq_sampler_set_state(kbbq_ctx* ctx, const uint64_t state[4], double alpha);
 /* position of the sampling stream in draws; set it when batches are dealt to several GPUs */
 int kbbq_sampler_seek(kbbq_ctx* ctx, uint64_t slot_ordinal);
 /* recalibrateutils::subsample_kmers (recalibrateutils.cc:7-13) over one batch; advances the stream by the batch's slots */

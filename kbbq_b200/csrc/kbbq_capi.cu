@@ -400,6 +400,10 @@ __global__ void __launch_bounds__(256) synth_reads_kernel(SynthSpec s, unsigned 
         m2 |= (uint32_t)(q <= 2) << i;
         m6 |= (uint32_t)(q <= 6) << i;
     }
+    if (cnt < 32) {  // padding bytes hold quality 0: kbbq_quality_masks flags them too (every consumer masks by length)
+        m2 |= ~0u << cnt;
+        m6 |= ~0u << cnt;
+    }
     bases[gw] = bw;
     nmask[gw] = 0;
     uint4* qo = reinterpret_cast<uint4*>(qual + gw * 32);
@@ -1272,11 +1276,22 @@ uint64_t kbbq_batch_slots(const kbbq_dbatch* b) { return b ? b->n_slots : 0; }
 void* kbbq_batch_device_newqual(kbbq_dbatch* b) { return b ? b->d_newqual : nullptr; }
 
 // ---- pass 1 --------------------------------------------------------------------------------------------------------
+static int sampler_install(kbbq_ctx* ctx, const uint64_t state[4], double alpha);
+
 int kbbq_sampler_seed(kbbq_ctx* ctx, uint32_t seed, double alpha) {
-    if (int rc = use(ctx)) return rc;
     host::Xoshiro256ss r;
     r.seed(seed);
-    std::memcpy(ctx->sampler_state0, r.s, 32);
+    return sampler_install(ctx, r.s, alpha);
+}
+
+int kbbq_sampler_set_state(kbbq_ctx* ctx, const uint64_t state[4], double alpha) {
+    if (!state) return fail(KBBQ_EINVAL, "null state");
+    return sampler_install(ctx, state, alpha);
+}
+
+static int sampler_install(kbbq_ctx* ctx, const uint64_t state[4], double alpha) {
+    if (int rc = use(ctx)) return rc;
+    std::memcpy(ctx->sampler_state0, state, 32);
     ctx->sampler_pos = 0;
     ctx->alpha = alpha;
     ctx->sampler_seeded = true;

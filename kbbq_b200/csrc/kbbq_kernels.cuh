@@ -612,36 +612,37 @@ covariate_count_kernel(BatchView b, FlatMap fm, CountView cv, const uint32_t* __
                 hw.nflags &= ~(1u << j);
             }
         }
-        uint32_t last_key = 0xFFFFFFFFu;
-        uint32_t* row = rows;
-        bool have_row = false;
         const int n = hw.len - hw.i0 < 16 ? hw.len - hw.i0 : 16;
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-            const int qi = half_word_qual(hw, j);
+        const uint32_t qw[4] = {hw.q.x, hw.q.y, hw.q.z, hw.q.w};
+        const int cyc0 = hw.sec * C + hw.i0;  // the half word's first cycle cell within a row
+        // fully unrolled: the quality byte of step j is a fixed byte of a fixed register, and no branch depends on what
+        // the neighbouring lanes hold except the (rare) error and the (rare) first meeting with a row
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j >= n) break;
+            const uint32_t qi = (qw[j >> 2] >> (8 * (j & 3))) & 255u;
             if (qi > KBBQ_MAXQ) continue;  // a quality the tables cannot index is skipped (and reported: qual_range_kernel)
-            const uint32_t key = hw.rgrow + (uint32_t)qi;
-            if (key != last_key) {
+            const uint32_t key = hw.rgrow + qi;
+            uint32_t v = key < KBBQ_HIST_DIRECT_RG * KBBQ_NQ ? slot_of[key] : KBBQ_HIST_NOSLOT;
+            if (v >= (uint32_t)S && v != KBBQ_HIST_NOSLOT) {  // first meeting with the row (or somebody is claiming it)
                 const int slot = hist_slot(slot_of, tags, n_used, S, key);
-                have_row = slot >= 0;
-                row = rows + (size_t)(have_row ? slot : 0) * row_cells;
-                last_key = key;
+                v = slot >= 0 ? (uint32_t)slot : KBBQ_HIST_NOSLOT;
             }
-            const int i = hw.i0 + j;
             const bool er = (e16 >> j) & 1u;
             // CDinucCovariate: i >= 1, both bases ACGT, qual >= 6
             const bool di = qi >= 6 && ((hw.nflags >> j) & 3u) == 0;
             const uint32_t x = (uint32_t)(hw.codes >> (2 * j)) & 15u;  // previous base in the low pair
             const uint32_t d = ((x & 3u) << 2) | (x >> 2);
-            if (have_row) {
-                atomicAdd(row + hw.sec * C + i, 1u);
-                if (er) atomicAdd(row + 2 * C + hw.sec * C + i, 1u);
-                if (di) {
-                    atomicAdd(row + 4 * C + d, 1u);
-                    if (er) atomicAdd(row + 4 * C + 16 + d, 1u);
+            if (v != KBBQ_HIST_NOSLOT) {
+                uint32_t* row = rows + (size_t)v * row_cells;
+                atomicAdd(row + cyc0 + j, 1u);
+                if (di) atomicAdd(row + 4 * C + d, 1u);
+                if (er) {
+                    atomicAdd(row + 2 * C + cyc0 + j, 1u);
+                    if (di) atomicAdd(row + 4 * C + 16 + d, 1u);
                 }
             } else {  // no private row: straight to the tables, all four of them
-                unsigned long long* cc = cv.cyc + (((size_t)key * 2 + hw.sec) * (size_t)C + i) * 2;
+                unsigned long long* cc = cv.cyc + ((size_t)key * 2 * (size_t)C + cyc0 + j) * 2;
                 atomicAdd(cc + 1, 1ull);
                 atomicAdd(cv.qc + (size_t)key * 2 + 1, 1ull);
                 atomicAdd(cv.rgc + 2 * (hw.rgrow / KBBQ_NQ) + 1, 1ull);
@@ -853,27 +854,35 @@ pass4_apply_kernel(BatchView b, FlatMap fm, ModelView mv, int n_rg, uint8_t* __r
     for (unsigned long long h = first_half + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; h < end_half; h += stride) {
         HalfWord hw;
         if (!load_half_word(b, fm, h, end_half, hw)) continue;  // past the read's end: the output stays zero like the input
-        uint32_t res[4] = {hw.q.x, hw.q.y, hw.q.z, hw.q.w};
+        const uint32_t qw[4] = {hw.q.x, hw.q.y, hw.q.z, hw.q.w};
+        uint32_t res[4];
         const int n = hw.len - hw.i0 < 16 ? hw.len - hw.i0 : 16;
+        const uint32_t cy0 = (hw.rgrow * 2u + (uint32_t)hw.sec) * (uint32_t)C + (uint32_t)hw.i0;  // cy index of quality 0 at the first base
+        const uint32_t di0 = hw.rgrow * 17u, di0g = hw.rgrow * 16u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int qi = (int)((res[j >> 2] >> (8 * (j & 3))) & 255u);
-            if (j < n && qi >= 6 && qi <= KBBQ_MAXQ) {  // minqual: lower qualities pass through unchanged (so does anything the tables cannot index)
-                const size_t row = hw.rgrow + qi;
-                const int i = hw.i0 + j;
-                const bool has_di = ((hw.nflags >> j) & 3u) == 0;  // this base and the one before it are ACGT (and i > 0)
-                const uint32_t x = (uint32_t)(hw.codes >> (2 * j)) & 15u;  // previous base in the low pair
-                const uint32_t dn = ((x & 3u) << 2) | (x >> 2);
-                int v;
-                if (SMEM) {
-                    v = st.cy[(row * 2 + hw.sec) * (size_t)C + i] + st.dib[row * 17 + (has_di ? dn : 16u)];
-                } else {
-                    v = mv.base[row] + mv.cy[(row * 2 + hw.sec) * (size_t)C + i];
-                    if (has_di) v += mv.di[row * 16 + dn];
+        for (int w = 0; w < 4; ++w) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * w + jj;
+                const uint32_t qi = (qw[w] >> (8 * jj)) & 255u;
+                uint32_t nv = qi;
+                if (j < n && qi >= 6 && qi <= KBBQ_MAXQ) {  // minqual: lower qualities pass through unchanged (so does anything the tables cannot index)
+                    const bool has_di = ((hw.nflags >> j) & 3u) == 0;  // this base and the one before it are ACGT (and i > 0)
+                    const uint32_t x = (uint32_t)(hw.codes >> (2 * j)) & 15u;  // previous base in the low pair
+                    const uint32_t dn = ((x & 3u) << 2) | (x >> 2);
+                    int v;
+                    if (SMEM) {
+                        v = st.cy[cy0 + qi * 2u * (uint32_t)C + j] + st.dib[di0 + qi * 17u + (has_di ? dn : 16u)];
+                    } else {
+                        v = mv.base[hw.rgrow + qi] + mv.cy[cy0 + qi * 2u * (uint32_t)C + j];
+                        if (has_di) v += mv.di[di0g + qi * 16u + dn];
+                    }
+                    nv = (uint32_t)(v < 0 ? 0 : (v > KBBQ_MAXQ ? KBBQ_MAXQ : v));
                 }
-                v = v < 0 ? 0 : (v > KBBQ_MAXQ ? KBBQ_MAXQ : v);
-                res[j >> 2] = (res[j >> 2] & ~(255u << (8 * (j & 3)))) | ((uint32_t)v << (8 * (j & 3)));
+                packed |= nv << (8 * jj);
             }
+            res[w] = packed;
         }
         *reinterpret_cast<uint4*>(out + (size_t)hw.gw * 32 + hw.o) = make_uint4(res[0], res[1], res[2], res[3]);
     }

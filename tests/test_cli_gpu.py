@@ -242,3 +242,37 @@ def test_cli_writes_a_gatk_style_report(tmp_path):
     assert text.startswith("#:GATKReport.v1.1:3") and "RecalTable2" in text
     obs = [int(line.split()[4]) for line in text.split("#:GATKTable:RecalTable0:")[1].split("\n\n")[0].splitlines()[2:]]
     assert sum(obs) == rs.total_bases
+
+
+@pytest.mark.parametrize("kind", ["fastq", "bam"])
+def test_reference_main_bound_to_the_c_abi_matches_the_reference(tmp_path, kind):
+    """oracle/_ref/kbbq_ref_b200 = the reference's UNMODIFIED main(), file classes, threshold maths and model fit linked
+    with integration/recalibrateutils_b200.cc (the four pass drivers over include/kbbq_b200.h) instead of its
+    recalibrateutils.cc: the drop-in boundary, compiled.  Its output must be the reference CLI's, byte for byte."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref")
+    bound = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref_b200")
+    if not (os.path.exists(ref) and os.path.exists(bound)):
+        pytest.skip("oracle/_ref/kbbq_ref{,_b200} not present (built where /root/reference exists)")
+    import sys
+    sys.path.insert(0, ROOT)
+    from kbbq_b200 import synth
+
+    rs = synth.make_reads(100000, 20, 100, seed=81, n_rg=3, n_frac=0.001)
+    if kind == "fastq":
+        inp = str(tmp_path / "in.fq")
+        synth.to_fastq(rs, inp)
+        args = ["-k", "32", "-g", "100000", "-c", "20", inp]
+    else:
+        inp = str(tmp_path / "in.bam")
+        synth.to_bam(rs, inp, genome_len=100000, rev_every=5, with_oq=True)
+        args = ["-k", "32", "-c", "20", "--set-oq", inp]
+    outs = []
+    for exe in (ref, bound):
+        with open(tmp_path / "o.gz", "wb") as fo:
+            r = subprocess.run([exe] + args, stdout=fo, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()
+        outs.append((gzip.open(tmp_path / "o.gz").read(), r.stderr.decode()))
+    assert outs[0][0] == outs[1][0]
+    # same seed (time()/getpid() pinned in both), same counters reported by main()
+    pick = lambda log: [l.split("]", 1)[1] for l in log.splitlines() if "Sampled" in l or "Seed" in l or "false positive" in l]
+    assert pick(outs[0][1]) == pick(outs[1][1])
