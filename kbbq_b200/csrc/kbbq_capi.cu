@@ -91,6 +91,10 @@ struct kbbq_ctx {
     bool timed = false;
     uint64_t launches = 0;
     Filter filt[2];
+    // bumped whenever a filter's bits may have been REMOVED or replaced (create, clear, upload, load): a batch remembers
+    // the epoch at which it inserted k-mers, and a later pass skips the probes of k-mers it knows to be present only
+    // while the epoch still matches (merges and further inserts only add bits: they keep the knowledge valid)
+    uint64_t epoch[2] = {1, 1};
     // sampler
     bool sampler_seeded = false;
     uint64_t sampler_state0[4] = {0, 0, 0, 0};  // state right after Seed()
@@ -152,6 +156,9 @@ struct kbbq_dbatch {
     uint8_t* d_second = nullptr;
     unsigned long long* d_slot_off = nullptr;
     uint32_t* d_sample_bits = nullptr;
+    uint64_t sample_epoch = 0;      // ctx->epoch[SAMPLED] when pass 1 inserted this batch's sampled k-mers (0: never)
+    uint32_t* d_ins_bits = nullptr;  // per k-mer (word layout): inserted into `trusted` by pass 2
+    uint64_t ins_epoch = 0;         // ctx->epoch[TRUSTED] when pass 2 did
     uint32_t* d_err_bits = nullptr;
     uint32_t* d_word_read = nullptr;  // read index of every word (flat traversal), made on demand for non-uniform batches
     uint32_t uniform_wpr = 0;         // words per read when every read occupies the same number of words, else 0
@@ -761,6 +768,7 @@ int kbbq_bloom_create(kbbq_ctx* ctx, int which, uint64_t projected, double fpr, 
         cudaFree(f.d_inserted);
         f = Filter();
     }
+    ++ctx->epoch[which];
     f.geom = g;
     CU(cudaMalloc(&f.d_words, g.table_bits / 8));
     f.d_patterns = ctx->d_pattern_pool + (size_t)which * KBBQ_NUM_PATTERNS * 8;
@@ -786,6 +794,7 @@ int kbbq_bloom_clear(kbbq_ctx* ctx, int which) {
     if (int rc = use(ctx)) return rc;
     if (int rc = filter_ok(ctx, which)) return rc;
     Filter& f = ctx->filt[which];
+    ++ctx->epoch[which];
     CU(cudaMemsetAsync(f.d_words, 0, f.geom.table_bits / 8, ctx->stream));
     CU(cudaMemsetAsync(f.d_inserted, 0, 8, ctx->stream));
     return KBBQ_OK;
@@ -813,6 +822,7 @@ int kbbq_bloom_upload(kbbq_ctx* ctx, int which, const uint64_t* words, uint64_t 
     if (int rc = use(ctx)) return rc;
     if (int rc = filter_ok(ctx, which)) return rc;
     Filter& f = ctx->filt[which];
+    ++ctx->epoch[which];
     if (words) CU(cudaMemcpyAsync(f.d_words, words, f.geom.table_bits / 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(f.d_inserted, &inserted, 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1123,7 +1133,7 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaStream_t st = ctx ? ctx->stream : nullptr;
     void* ptrs[] = {b->d_bases, b->d_nmask, b->d_qual, b->d_qmask, b->d_word_off, b->d_len, b->d_rg, b->d_second, b->d_slot_off,
-                    b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual, b->d_tflags, b->d_repair, b->d_word_read};
+                    b->d_sample_bits, b->d_err_bits, b->d_mod, b->d_newqual, b->d_tflags, b->d_repair, b->d_word_read, b->d_ins_bits};
     if (b->qual_ready) {
         if (ctx && !b->qual_waited) cudaStreamWaitEvent(st, b->qual_ready, 0);  // d_qual is freed in `st`'s order
         cudaEventDestroy(b->qual_ready);
@@ -1383,6 +1393,7 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
         }
     }
     pass_end(ctx);
+    b->sample_epoch = b->n_slots ? ctx->epoch[KBBQ_FILTER_SAMPLED] : 0;
     ctx->sampler_pos += b->n_slots;
     return KBBQ_OK;
 }
@@ -1442,11 +1453,15 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         const BloomView sv = ctx->filt[KBBQ_FILTER_SAMPLED].view(), tv = ctx->filt[KBBQ_FILTER_TRUSTED].view();
         uint32_t* eo = err_bits ? b->d_err_bits : nullptr;
         // one hash computation per k-mer for both filters when their salts agree (same seed: always, in the reference)
+        // knowledge carried between the passes of one batch (see kbbq_ctx::epoch): KBBQ_NO_KNOWN_BITS=1 switches it off
+        static const bool use_known = getenv("KBBQ_NO_KNOWN_BITS") == nullptr;
+        const uint32_t* known = use_known && b->d_sample_bits && b->sample_epoch == ctx->epoch[KBBQ_FILTER_SAMPLED] ? b->d_sample_bits : nullptr;
+        if (use_known && !b->d_ins_bits) CU(cudaMallocAsync(&b->d_ins_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
         const bool shared_hash = sv.salt0 == tv.salt0 && sv.salt1 == tv.salt1 && !getenv("KBBQ_P2_SEPARATE_HASH");
         const int max_kmers = std::max(1, (int)b->max_len - ctx->k + 1);
         const size_t smem = shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0;
         const int threads = KBBQ_WARPS_PER_BLOCK * 32;
-#define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers)
+#define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers, known, b->d_ins_bits)
         if (shared_hash) {
             if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, true);
             else if (mode == INS_TEST_FIRST) P2_LAUNCH(INS_TEST_FIRST, true);
@@ -1463,6 +1478,7 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         }
     }
     pass_end(ctx);
+    b->ins_epoch = b->d_ins_bits && b->n_reads ? ctx->epoch[KBBQ_FILTER_TRUSTED] : 0;
     return fetch_bits(ctx, b, err_bits);
 }
 
@@ -1483,7 +1499,8 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         const BloomView tv = ctx->filt[KBBQ_FILTER_TRUSTED].view();
         mark_kernel(ctx, "pass3_scan_kernel");
         pass3_scan_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work);
+            b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work,
+            b->d_ins_bits && b->ins_epoch == ctx->epoch[KBBQ_FILTER_TRUSTED] && !getenv("KBBQ_NO_KNOWN_BITS") ? b->d_ins_bits : nullptr);
         if (int rc = check_launch(ctx, "pass3_scan_kernel")) return rc;
         mark_kernel(ctx, "pass3_repair_kernel");
         pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(

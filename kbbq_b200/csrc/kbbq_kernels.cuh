@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
 template <int MODE, bool SHARED_HASH>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P2_MIN_BLOCKS)
 pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, const int* __restrict__ thresholds,
-                     uint32_t* __restrict__ err_out, StageSink sink, int max_kmers) {
+                     uint32_t* __restrict__ err_out, StageSink sink, int max_kmers, const uint32_t* __restrict__ known_bits,
+                     uint32_t* __restrict__ ins_out) {
     extern __shared__ uint2 p2_hash[];  // [warps][max_kmers]: .x = hash_ap8(key, salt0), .y = pattern (0xFFFFFFFF: invalid k-mer)
     __shared__ int thr[KBBQ_MAX_K + 1];
     __shared__ uint32_t Pm_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
@@ -437,19 +438,28 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         if (nk <= 0) continue;  // out of contract in the reference (bloom.cc:30 underflows)
         const uint32_t wo = b.word_off[r];
         const CSeqRef s{b.bases + wo, b.nmask + wo, len};
-        // kmer_present (bloom.cc:35-47)
+        // kmer_present (bloom.cc:35-47).  A valid k-mer that pass 1 sampled from this very batch was inserted into
+        // `sampled` then (known_bits = that pass's sample bits, given only while the filter has not been cleared since):
+        // it is present without asking -- a Bloom filter has no false negatives -- and its 64-byte probe is saved.
+        const unsigned long long so = b.slot_off[r];
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
             uint64_t key = 0;
             const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+            bool known = false;
+            if (known_bits && valid) {
+                const unsigned long long slot = so + (unsigned)j;
+                known = (__ldg(known_bits + (slot >> 5)) >> (slot & 31)) & 1u;
+            }
             uint32_t m;
             if (SHARED_HASH) {
                 const uint32_t h = hash_ap8(key, sampled.salt0), pat = valid ? bloom_pattern(sampled, key) : 0xFFFFFFFFu;
                 if (j < nk) HP[j] = make_uint2(h, pat);
-                m = warp_bloom_query_bp(sampled, valid, bloom_block_of_hash(sampled, h), pat);
+                m = warp_bloom_query_bp(sampled, valid && !known, bloom_block_of_hash(sampled, h), pat);
             } else {
-                m = warp_bloom_query<true>(sampled, valid, key);
+                m = warp_bloom_query<true>(sampled, valid && !known, key);
             }
+            m |= __ballot_sync(KBBQ_FULL, known);
             if (lane == 0) Pm[j0 >> 5] = m;
         }
         __syncwarp();
@@ -477,11 +487,19 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
                 const uint2 hp = j < nk ? HP[j] : make_uint2(0u, 0xFFFFFFFFu);
                 const bool ins = j < nk && hp.y != 0xFFFFFFFFu && count_window32(Em, j, j + k) == 0;
                 const uint64_t blk = bloom_block_of_hash(trusted, hp.x);
+                if (ins_out) {  // which k-mers went into `trusted`: pass 3's scan need not ask about them
+                    const uint32_t im = __ballot_sync(KBBQ_FULL, ins);
+                    if (lane == 0) ins_out[wo + (j0 >> 5)] = im;
+                }
                 if (MODE == INS_STAGED) inserted += warp_stage_insert_bp(sink, cur, ins, blk, hp.y);
                 else inserted += warp_bloom_insert_bp<MODE == INS_TEST_FIRST>(trusted, ins, blk, hp.y, stage);
             } else {
                 uint64_t key = 0;
                 const bool ins = j < nk && count_window32(Em, j, j + k) == 0 && kmer_key(s, j, k, 0, -1, key);
+                if (ins_out) {
+                    const uint32_t im = __ballot_sync(KBBQ_FULL, ins);
+                    if (lane == 0) ins_out[wo + (j0 >> 5)] = im;
+                }
                 if (MODE == INS_STAGED) inserted += warp_stage_insert(trusted, sink, cur, ins, key);
                 else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(trusted, ins, key, stage);
             }
@@ -708,7 +726,8 @@ covariate_count_kernel(BatchView b, FlatMap fm, CountView cv, const uint32_t* __
 #endif
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
 pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
-                  uint32_t* __restrict__ mod_out, uint32_t* __restrict__ repair_list, unsigned int* __restrict__ repair_count) {
+                  uint32_t* __restrict__ mod_out, uint32_t* __restrict__ repair_list, unsigned int* __restrict__ repair_count,
+                  const uint32_t* __restrict__ known_bits) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
@@ -723,7 +742,10 @@ pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ 
                 const int j = j0 + lane;
                 uint64_t key = 0;
                 const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
-                const uint32_t m = warp_bloom_query<true>(trusted, valid, key);
+                // k-mers pass 2 inserted from this very batch (known_bits, per k-mer in the word layout; given only while
+                // `trusted` has not been cleared since) are present without asking: a third of all probes at 30X
+                const uint32_t known = known_bits ? __ldg(known_bits + wo + (j0 >> 5)) : 0u;
+                const uint32_t m = warp_bloom_query<true>(trusted, valid && !((known >> lane) & 1u), key) | known;
                 const int cnt = nk - j0 < 32 ? nk - j0 : 32;
                 all_trusted = all_trusted && m == (cnt < 32 ? (1u << cnt) - 1u : ~0u);
                 if (lane == 0) tflags[wo + (j0 >> 5)] = m;
@@ -743,6 +765,17 @@ pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ 
 __device__ __noinline__ uint32_t probe_ballot(const BloomView* f, bool valid, uint64_t key) {
     return __ballot_sync(KBBQ_FULL, valid && bloom_contains_dev(*f, key));
 }
+// Wide questions (a walk over up to 32 consecutive k-mers) may use the four-lanes-per-probe form instead: half the L1
+// wavefronts and DRAM sectors in flight per probe once the filter lives in HBM; slower while it sits in the L2 (round 1).
+// KBBQ_P3R_COOP: 0 = one lane per probe always, N > 0 = cooperative for questions of more than N k-mers.
+#ifndef KBBQ_P3R_COOP
+#define KBBQ_P3R_COOP 0
+#endif
+__device__ __noinline__ uint32_t probe_coop_ballot(const BloomView* f, bool valid, uint64_t key) {
+    const uint32_t vmask = __ballot_sync(KBBQ_FULL, valid);
+    if (vmask == 0) return 0;
+    return coop_probe_impl<2>(f->words, f->patterns, valid ? bloom_block(*f, key) : 0, valid ? bloom_pattern(*f, key) : 0, vmask);
+}
 struct DevQuery {
     const BloomView* f;  // in shared memory: a kernel parameter has no address an out-of-line function could take
     template <class F>
@@ -751,6 +784,7 @@ struct DevQuery {
         const int lane = threadIdx.x & 31;
         uint64_t key = 0;
         const bool valid = lane < count && fn(lane, key);
+        if (KBBQ_P3R_COOP > 0 && count > KBBQ_P3R_COOP) return probe_coop_ballot(f, valid, key);
         return probe_ballot(f, valid, key);
 #else
         (void)count; (void)fn;
