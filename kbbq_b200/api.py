@@ -106,6 +106,8 @@ def lib():
         L.kbbq_bloom_or_allreduce_p2p.argtypes = [vp, i32, i32, i32, vp]
         L.kbbq_batch_upload.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
         L.kbbq_batch_upload_async.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
+        L.kbbq_batch_upload_stream.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
+        L.kbbq_batch_wait.argtypes = [vp, vp]
         L.kbbq_batch_free.argtypes = [vp, vp]
         L.kbbq_batch_slots.restype = u64
         L.kbbq_batch_slots.argtypes = [vp]
@@ -489,6 +491,14 @@ class Context:
         s = pb.as_struct()
         h = C.c_void_p()
         _check(self.L.kbbq_batch_upload_async(self.h, C.byref(s), C.byref(h)))
+        return DeviceBatch(self, h, pb)
+
+    def upload_stream(self, pb: PackedBatch) -> "DeviceBatch":
+        """Every array on the library's side stream, nothing waited for (kbbq_batch_upload_stream): the passes wait on the
+        device, and the upload of the next batch overlaps the kernels of this one.  `pb` must be pinned."""
+        s = pb.as_struct()
+        h = C.c_void_p()
+        _check(self.L.kbbq_batch_upload_stream(self.h, C.byref(s), C.byref(h)))
         return DeviceBatch(self, h, pb)
 
     def synth_batch(self, params: SynthParams, first_read: int, n_reads: int) -> "DeviceBatch":

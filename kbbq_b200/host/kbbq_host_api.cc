@@ -416,9 +416,20 @@ template <class F>
 static void parallel_for(size_t n, int nt, F f) {  // f(begin, end, thread index) over contiguous ranges
     nt = (int)std::min<size_t>((size_t)std::max(nt, 1), std::max<size_t>(n, 1));
     if (nt <= 1) { f((size_t)0, n, 0); return; }
+    // an exception leaving a std::thread is std::terminate: carry the first one back to the caller instead
+    std::vector<std::exception_ptr> err((size_t)nt);
     std::vector<std::thread> th;
-    for (int t = 0; t < nt; ++t) th.emplace_back([=] { f(n * t / nt, n * (t + 1) / nt, t); });
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([=, &err] {
+            try {
+                f(n * t / nt, n * (t + 1) / nt, t);
+            } catch (...) {
+                err[(size_t)t] = std::current_exception();
+            }
+        });
     for (auto& t : th) t.join();
+    for (auto& e : err)
+        if (e) std::rethrow_exception(e);
 }
 
 static bool read_file(const std::string& filename, std::vector<uint8_t>& raw) {
@@ -926,12 +937,22 @@ void FastqFile::format_record(size_t i, const uint8_t* q, std::string& s) const 
 
 // ---- BAM ---------------------------------------------------------------------------------------------------------------
 bool is_bam_file(const std::string& filename) {
+    if (filename == "-")  // the loaders read stdin, but it cannot be peeked at and rewound: the format must be known
+        throw std::runtime_error("Error: reading from standard input is not supported by this build; give a file name.");
     gzFile gz = gzopen(filename.c_str(), "rb");
     if (!gz) throw std::runtime_error("Error opening file " + filename);
-    unsigned char head[4] = {0, 0, 0, 0};
-    const int n = gzread(gz, head, 4);
+    unsigned char head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int n = gzread(gz, head, 8);
     gzclose(gz);
     if (n >= 4 && std::memcmp(head, "BAM\1", 4) == 0) return true;
+    if (n >= 4 && std::memcmp(head, "CRAM", 4) == 0)
+        throw std::runtime_error("Error: CRAM input is not supported by this build (bam or fastq only).");
+    // a SAM text file also starts with '@' (@HD / @SQ / @RG / @PG / @CO then a tab): the reference's hts_detect_format
+    // calls it sam and main() rejects it (kbbq.cc:172-190); a FASTQ name may start the same way but is never followed by a tab
+    if (n >= 4 && head[0] == '@' && head[3] == '\t' &&
+        (!std::memcmp(head + 1, "HD", 2) || !std::memcmp(head + 1, "SQ", 2) || !std::memcmp(head + 1, "RG", 2) ||
+         !std::memcmp(head + 1, "PG", 2) || !std::memcmp(head + 1, "CO", 2)))
+        throw std::runtime_error("Error: File format must be bam, cram, or fastq.");
     if (n >= 1 && head[0] == '@') return false;
     throw std::runtime_error("Error: File format must be bam, cram, or fastq.");
 }

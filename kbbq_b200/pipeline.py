@@ -78,7 +78,11 @@ class Recalibrator:
         self.ctx.covariates_reset()
 
     # ---- the passes ----------------------------------------------------------------------------------------------
-    def run(self, fetch_quals: bool = False, want_errors: bool = False, qual_bufs=None) -> RunStats:
+    def run(self, fetch_quals: bool = False, want_errors: bool = False, qual_bufs=None, host_batches=None,
+            timing: bool = True) -> RunStats:
+        """`host_batches`: pinned PackedBatches to stream in instead of batches that are already resident -- batch i+1
+        travels (kbbq_batch_upload_stream) while pass 1 runs on batch i; they are resident afterwards.  `timing=False`
+        skips the per-pass event queries, which would make the host wait for every pass before queuing the next."""
         st = RunStats()
         ctx, comm = self.ctx, self.comm
         launches0 = ctx.launches
@@ -88,18 +92,29 @@ class Recalibrator:
             outs = []
             for b in self.batches:
                 outs.append(fn(b))
-                total += ctx.last_pass_ms()
-                for kn, kms in ctx.last_pass_kernels().items():
-                    st.kernel_ms[kn] = st.kernel_ms.get(kn, 0.0) + kms
+                if timing:
+                    total += ctx.last_pass_ms()
+                    for kn, kms in ctx.last_pass_kernels().items():
+                        st.kernel_ms[kn] = st.kernel_ms.get(kn, 0.0) + kms
             st.pass_ms[name] = total
             return outs
 
         # pass 1: every rank seeks to the ordinal of its first slot in the one global sampling stream
         if comm is not None:
-            self.slot_base = comm.exclusive_prefix(self.local_slots)
+            local = self.local_slots if host_batches is None else sum(
+                int(np.maximum(pb.len[: pb.n_reads].astype(np.int64) - self.k + 1, 0).sum()) for pb in host_batches)
+            self.slot_base = comm.exclusive_prefix(local)
         ctx.sampler_seed(self.seed, float(self.alpha_ld))
         ctx.sampler_seek(self.slot_base)
-        timed_pass("pass1", ctx.pass1)
+        if host_batches is not None:
+            assert not self.batches, "host_batches replace the resident batches"
+            for pb in host_batches:  # the sampling stream advances batch by batch inside the library
+                db = ctx.upload_stream(pb)
+                self.batches.append(db)
+                ctx.pass1(db)
+            st.pass_ms["pass1"] = 0.0
+        else:
+            timed_pass("pass1", ctx.pass1)
         if comm is not None:
             t0 = time.perf_counter()
             comm.merge_filter(ctx, api.FILTER_SAMPLED)

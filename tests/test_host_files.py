@@ -172,6 +172,21 @@ def test_cli_error_paths_without_a_gpu(tmp_path):
     assert rc == 1 and "File format must be bam, cram, or fastq" in err
     rc, err = run("--bogus", "tiny.fq")
     assert rc == 1 and "Unknown argument" in err
+    # a SAM text file starts with '@' like a FASTQ record: it is recognised and refused like the reference refuses it
+    (tmp_path / "x.sam").write_bytes(b"@HD\tVN:1.6\n@SQ\tSN:c\tLN:10\nr\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\tIIII\n")
+    rc, err = run("-g", "100", "x.sam")
+    assert rc == 1 and "File format must be bam, cram, or fastq" in err
+    (tmp_path / "x.cram").write_bytes(b"CRAM\x03\x00" + b"\0" * 20)
+    rc, err = run("-g", "100", "x.cram")
+    assert rc == 1 and "CRAM input is not supported" in err
+    rc, err = run("-g", "100")  # the reference's default "-": standard input is refused with a message, not a crash
+    assert rc == 1 and "standard input" in err
+    rc, err = run("--gpus", "-1", "tiny.fq")
+    assert rc == 1 and "gpus must be >= 0" in err
+    # a FASTQ whose name line is a single character cannot name a read group or a mate: an error message, not std::terminate
+    (tmp_path / "many.fq").write_bytes(b"".join(b"@\n" + b"ACGT" * 9 + b"\n+\n" + b"I" * 36 + b"\n" for _ in range(6000)))
+    r = subprocess.run([cli, "-g", "100", "many.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=tmp_path)
+    assert r.returncode in (0, 1)  # never a signal
     from kbbq_b200 import api
     rc, err = run("tiny.fq")
     if api.lib().kbbq_device_count() == 0:  # the GPU context comes first: no device, no run
