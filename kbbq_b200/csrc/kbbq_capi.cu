@@ -3,7 +3,6 @@
 #include "../../include/kbbq_b200.h"
 
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -298,66 +297,63 @@ int slot_prefix(kbbq_ctx* ctx, const uint32_t* d_len, uint32_t n, unsigned long 
     return KBBQ_OK;
 }
 
-// How the pass-1 / pass-2 kernels insert (kbbq_kernels.cuh: INS_*): directly while the filter fits the L2, through a
-// sorted staging array once it does not (and the staging arrays fit a sane share of the device).
-// KBBQ_INSERT_MODE=0|1|2 overrides (measurement, tests).
+// How the pass-1 / pass-2 kernels insert (kbbq_kernels.cuh: INS_*): directly while the filter fits the L2; through
+// bucketed staging once it does not AND the batch brings at least two items per 64-byte block of the table (sparser than
+// that, a slice's lines are touched about once either way and the staging traffic buys nothing) AND the staging array
+// fits a sane share of the device; read-before-OR otherwise.  KBBQ_INSERT_MODE=0|1|2 overrides (measurement, tests).
+int stage_shift() {  // KBBQ_STAGE_SHIFT: tests cut a small filter into many buckets with it
+    const char* e = getenv("KBBQ_STAGE_SHIFT");  // read per call: tests change it between runs of one process
+    return e ? std::max(0, std::min(40, atoi(e))) : KBBQ_STAGE_BUCKET_SHIFT;
+}
 int insert_mode(const kbbq_ctx* ctx, int which, uint64_t n_slots) {
-    if (const char* e = getenv("KBBQ_INSERT_MODE")) return atoi(e);
-    if (ctx->filt[which].geom.table_bits / 8 <= (size_t)ctx->l2_bytes * 3 / 4) return INS_DIRECT;
-    return n_slots * 16 <= (24ull << 30) ? INS_STAGED : INS_TEST_FIRST;
+    const host::BloomGeom& g = ctx->filt[which].geom;
+    const uint64_t n_buckets = (g.n_blocks + (1ull << stage_shift()) - 1) >> stage_shift();
+    if (const char* e = getenv("KBBQ_INSERT_MODE")) return atoi(e) == INS_STAGED && n_buckets > 2048 ? INS_TEST_FIRST : atoi(e);
+    if (g.table_bits / 8 <= (size_t)ctx->l2_bytes * 3 / 4) return INS_DIRECT;
+    return n_slots >= 2 * g.n_blocks && n_buckets <= 2048 && n_slots * 10 <= (24ull << 30) ? INS_STAGED : INS_TEST_FIRST;
 }
 
 struct Staging {  // device buffers of one staged-insert launch; released in stream order when it goes out of scope
     kbbq_ctx* ctx = nullptr;
-    unsigned long long *items = nullptr, *sorted = nullptr, *cursor = nullptr;
-    uint64_t capacity = 0;
+    unsigned long long *items = nullptr, *cursor = nullptr;
+    StageSink sink{nullptr, nullptr, 0, 0, 0, KBBQ_STAGE_BUCKET_SHIFT};
     Staging() = default;
     Staging(const Staging&) = delete;
     Staging& operator=(const Staging&) = delete;
     ~Staging() {
         if (!ctx) return;
         if (items) cudaFreeAsync(items, ctx->stream);
-        if (sorted) cudaFreeAsync(sorted, ctx->stream);
         if (cursor) cudaFreeAsync(cursor, ctx->stream);
     }
+    size_t smem() const { return (size_t)sink.n_buckets * 12; }  // per block: state (8 B) + overflow flag (4 B) per bucket
 };
-int staging_begin(kbbq_ctx* ctx, uint64_t n_slots, int grid_warps, Staging& st) {
+// one region per 16 MiB slice of filter `which`: the expected share of a batch whose every slot inserts, a quarter more,
+// plus one granule per thread block (each block leaves its last granule of a region part empty)
+int staging_begin(kbbq_ctx* ctx, int which, uint64_t n_slots, int grid_blocks, Staging& st) {
     st.ctx = ctx;
-    // every insert takes one item; closing a granule wastes at most 31 of its 512 items (a warp appends <= 32 at a time),
-    // and every warp leaves its last granule partly used
-    st.capacity = n_slots + n_slots / 8 + (uint64_t)(grid_warps + 1) * KBBQ_STAGE_GRANULE * 2;
-    CU(cudaMallocAsync(&st.items, st.capacity * 8, ctx->stream));
-    CU(cudaMallocAsync(&st.sorted, st.capacity * 8, ctx->stream));
-    CU(cudaMallocAsync(&st.cursor, 8, ctx->stream));
-    CU(cudaMemsetAsync(st.cursor, 0, 8, ctx->stream));
+    const host::BloomGeom& g = ctx->filt[which].geom;
+    StageSink& k = st.sink;
+    k.shift = stage_shift();
+    k.n_buckets = (uint32_t)((g.n_blocks + (1ull << k.shift) - 1) >> k.shift);
+    k.granule = k.n_buckets > 512 ? 32 : 128;
+    if (const char* e = getenv("KBBQ_STAGE_CAP")) {  // tests: a tiny region forces the overflow path
+        k.cap = std::max<unsigned long long>(k.granule, strtoull(e, nullptr, 10) / k.granule * k.granule);
+    } else {
+        const unsigned long long want = n_slots / k.n_buckets + n_slots / k.n_buckets / 4 + (unsigned long long)(grid_blocks + 1) * k.granule;
+        k.cap = (want + k.granule - 1) / k.granule * k.granule;
+    }
+    CU(cudaMallocAsync(&st.items, (size_t)k.n_buckets * k.cap * 8, ctx->stream));
+    CU(cudaMallocAsync(&st.cursor, (size_t)k.n_buckets * 8, ctx->stream));
+    CU(cudaMemsetAsync(st.cursor, 0, (size_t)k.n_buckets * 8, ctx->stream));
+    k.items = st.items;
+    k.cursor = st.cursor;
     return KBBQ_OK;
 }
-// sort the staged (block, pattern) items by block range and apply them to filter `which`
+// apply the staged (block, pattern) items to filter `which`, region after region; nothing comes back to the host
 int staging_apply(kbbq_ctx* ctx, int which, Staging& st) {
-    unsigned long long n_items = 0;
-    CU(cudaMemcpyAsync(&n_items, st.cursor, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (n_items > st.capacity) return fail(KBBQ_ECUDA, "staged inserts overflowed their buffer");
-    if (n_items == 0) return KBBQ_OK;
-    const Filter& f = ctx->filt[which];
-    // buckets of 2^18 blocks = 16 MiB of table: sort on the block bits above them (items are (block << 16) | pattern)
-    int top = 0;
-    while ((1ull << top) < f.geom.n_blocks) ++top;
-    const int begin_bit = 16 + 18, end_bit = std::max(16 + top, begin_bit + 1);
-    const unsigned long long* src = st.items;
-    if (16 + top > begin_bit) {
-        size_t tmp_bytes = 0;
-        CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, st.items, st.sorted, n_items, begin_bit, end_bit, ctx->stream));
-        void* tmp = nullptr;
-        CU(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), ctx->stream));
-        cudaError_t e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, st.items, st.sorted, n_items, begin_bit, end_bit, ctx->stream);
-        cudaFreeAsync(tmp, ctx->stream);
-        if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("staged insert sort: ") + cudaGetErrorString(e));
-        src = st.sorted;
-    }
-    mark_kernel(ctx, "bloom_insert_sorted_kernel");
-    bloom_insert_sorted_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f.view(), src, n_items);
-    return check_launch(ctx, "bloom_insert_sorted_kernel");
+    mark_kernel(ctx, "bloom_apply_staged_kernel");
+    bloom_apply_staged_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->filt[which].view(), st.sink);
+    return check_launch(ctx, "bloom_apply_staged_kernel");
 }
 
 int filter_ok(kbbq_ctx* ctx, int which) {
@@ -1375,14 +1371,12 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
         const int grid = read_grid(ctx, b->n_reads);
         const int mode = insert_mode(ctx, KBBQ_FILTER_SAMPLED, b->n_slots);
         Staging st;
-        StageSink sink{nullptr, nullptr};
-        if (mode == INS_STAGED) {
-            if (int rc = staging_begin(ctx, b->n_slots, grid * KBBQ_WARPS_PER_BLOCK, st)) return rc;
-            sink = StageSink{st.items, st.cursor};
-        }
+        if (mode == INS_STAGED)
+            if (int rc = staging_begin(ctx, KBBQ_FILTER_SAMPLED, b->n_slots, grid, st)) return rc;
+        const StageSink sink = st.sink;
         const BloomView fv = ctx->filt[KBBQ_FILTER_SAMPLED].view();
         if (mode == INS_STAGED)
-            pass1_insert_kernel<INS_STAGED><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
+            pass1_insert_kernel<INS_STAGED><<<grid, KBBQ_WARPS_PER_BLOCK * 32, st.smem(), ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
         else if (mode == INS_TEST_FIRST)
             pass1_insert_kernel<INS_TEST_FIRST><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
         else
@@ -1445,28 +1439,35 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         const int grid = read_grid(ctx, b->n_reads);
         const int mode = insert_mode(ctx, KBBQ_FILTER_TRUSTED, b->n_slots);
         Staging st;
-        StageSink sink{nullptr, nullptr};
-        if (mode == INS_STAGED) {
-            if (int rc = staging_begin(ctx, b->n_slots, grid * KBBQ_WARPS_PER_BLOCK, st)) return rc;
-            sink = StageSink{st.items, st.cursor};
-        }
+        if (mode == INS_STAGED)
+            if (int rc = staging_begin(ctx, KBBQ_FILTER_TRUSTED, b->n_slots, grid, st)) return rc;
+        const StageSink sink = st.sink;
         const BloomView sv = ctx->filt[KBBQ_FILTER_SAMPLED].view(), tv = ctx->filt[KBBQ_FILTER_TRUSTED].view();
         uint32_t* eo = err_bits ? b->d_err_bits : nullptr;
         // one hash computation per k-mer for both filters when their salts agree (same seed: always, in the reference)
         // knowledge carried between the passes of one batch (see kbbq_ctx::epoch): KBBQ_NO_KNOWN_BITS=1 switches it off
-        static const bool use_known = getenv("KBBQ_NO_KNOWN_BITS") == nullptr;
+        const bool use_known = getenv("KBBQ_NO_KNOWN_BITS") == nullptr;
         const uint32_t* known = use_known && b->d_sample_bits && b->sample_epoch == ctx->epoch[KBBQ_FILTER_SAMPLED] ? b->d_sample_bits : nullptr;
         if (use_known && !b->d_ins_bits) CU(cudaMallocAsync(&b->d_ins_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
         const bool shared_hash = sv.salt0 == tv.salt0 && sv.salt1 == tv.salt1 && !getenv("KBBQ_P2_SEPARATE_HASH");
         const int max_kmers = std::max(1, (int)b->max_len - ctx->k + 1);
-        const size_t smem = shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0;
+        const size_t smem = (shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0) + (mode == INS_STAGED ? st.smem() : 0);
         const int threads = KBBQ_WARPS_PER_BLOCK * 32;
-#define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers, known, b->d_ins_bits)
-        if (shared_hash) {
+#define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S, PF><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers, known, b->d_ins_bits)
+        // filters beyond the L2: prefetch the blocks of all of a read's k-mers before probing (KBBQ_NO_PREFETCH=1: off)
+        const bool prefetch = shared_hash && ctx->filt[KBBQ_FILTER_SAMPLED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4 && !getenv("KBBQ_NO_PREFETCH");
+        if (shared_hash && prefetch) {
+            constexpr bool PF = true;
+            if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, true);
+            else if (mode == INS_TEST_FIRST) P2_LAUNCH(INS_TEST_FIRST, true);
+            else P2_LAUNCH(INS_DIRECT, true);
+        } else if (shared_hash) {
+            constexpr bool PF = false;
             if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, true);
             else if (mode == INS_TEST_FIRST) P2_LAUNCH(INS_TEST_FIRST, true);
             else P2_LAUNCH(INS_DIRECT, true);
         } else {
+            constexpr bool PF = false;
             if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, false);
             else if (mode == INS_TEST_FIRST) P2_LAUNCH(INS_TEST_FIRST, false);
             else P2_LAUNCH(INS_DIRECT, false);
@@ -1498,9 +1499,15 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         CU(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned int), ctx->stream));  // [0] repair-list length, [1] work counter
         const BloomView tv = ctx->filt[KBBQ_FILTER_TRUSTED].view();
         mark_kernel(ctx, "pass3_scan_kernel");
-        pass3_scan_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work,
-            b->d_ins_bits && b->ins_epoch == ctx->epoch[KBBQ_FILTER_TRUSTED] && !getenv("KBBQ_NO_KNOWN_BITS") ? b->d_ins_bits : nullptr);
+        const uint32_t* known = b->d_ins_bits && b->ins_epoch == ctx->epoch[KBBQ_FILTER_TRUSTED] && !getenv("KBBQ_NO_KNOWN_BITS") ? b->d_ins_bits : nullptr;
+        const int max_kmers = std::max(1, (int)b->max_len - ctx->k + 1);
+        // a filter beyond the L2: prefetch the blocks of all of a read's k-mers before probing (KBBQ_NO_PREFETCH=1: off)
+        if (ctx->filt[KBBQ_FILTER_TRUSTED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4 && !getenv("KBBQ_NO_PREFETCH"))
+            pass3_scan_kernel<true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2), ctx->stream>>>(
+                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
+        else
+            pass3_scan_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
         if (int rc = check_launch(ctx, "pass3_scan_kernel")) return rc;
         mark_kernel(ctx, "pass3_repair_kernel");
         pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(

@@ -49,6 +49,8 @@ struct CSeqRef {
 };
 
 #define KBBQ_WARPS_PER_BLOCK 8
+#define KBBQ_HP_INVALID 0xFFFFFFFFu  // (hash, pattern) parked in shared memory: pattern slot of a k-mer that holds a non-ACGT base
+#define KBBQ_HP_KNOWN 0xFFFFFFFEu    // ... of a k-mer known to be present (no probe)
 #define KBBQ_FULL 0xffffffffu
 
 // ---- filter probes ------------------------------------------------------------------------------------------------
@@ -57,6 +59,11 @@ __device__ __forceinline__ void ldg256(const unsigned long long* p, unsigned lon
                                        unsigned long long& c, unsigned long long& d) {
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
+// Bring the line of a filter block into the L2 without holding a register for it.  A warp that probes one 32-k-mer
+// round at a time has 32 blocks in flight and spends its life waiting for DRAM (the scan moved 4.0 TB/s where the same
+// probes, unburdened, move 5.1); prefetching the blocks of ALL of a read's k-mers first puts ~120 in flight per warp
+// and turns the rounds that follow into L2 hits.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // pattern_blocked_bf::contains (bloom.hh:276-292): (block & pattern) == pattern over 512 bits, one lane per key
 __device__ __forceinline__ bool bloom_contains_dev(const BloomView& f, uint64_t key) {
     const uint64_t blk = bloom_block(f, key);
@@ -175,52 +182,105 @@ struct InsertStage {
 // Insert modes of the pass-1 and pass-2 kernels (a template parameter; the launch picks by filter size):
 //   INS_DIRECT      atomicOr straight into the table -- filters that sit in the L2
 //   INS_TEST_FIRST  the same, reading the block first (above)
-//   INS_STAGED      do not touch the table: append (block, pattern) to a staging array; the host then sorts the
-//                   array by block range (cub radix sort on the bucket bits) and bloom_insert_sorted_kernel applies it,
+//   INS_STAGED      do not touch the table: append (block, pattern) to the staging region of its 16 MiB slice of the
+//                   table (below); bloom_apply_staged_kernel then applies region after region,
 //                   so that at any moment all SMs update one L2-sized slice of an HBM-sized table instead of scattering
 //                   128-byte line fills and dirty write-backs over all of it.  Same bits: OR is order independent.
 enum { INS_DIRECT = 0, INS_TEST_FIRST = 1, INS_STAGED = 2 };
-#define KBBQ_STAGE_GRANULE 512                  // items a warp reserves at a time from the staging array
-#define KBBQ_STAGE_SENTINEL 0xFFFFFFFFFFFFFFFFull  // filler of unused reservation tails; sorts last, applies nothing
+#define KBBQ_STAGE_SENTINEL 0xFFFFFFFFFFFFFFFFull  // filler of unused granule tails; applies nothing
+#define KBBQ_STAGE_BUCKET_SHIFT 18                 // a bucket = 2^18 blocks = 16 MiB of table
+#define KBBQ_STAGE_MAX_BUCKETS 4096
 
+// INS_STAGED without a sort: the staging array is cut into one REGION per bucket (16 MiB slice of the table), and items
+// go straight to their bucket's region.  Each thread block owns, per bucket, one granule of the region at a time
+// (`state` in shared memory: granule base + 1 in the high bits, items used in the low 16); an item takes the next
+// place of its block's granule with one shared-memory atomic, and the thread that finds the granule full reserves the
+// next one from the region's cursor in global memory (one global atomic per `granule` items).  A region that is full --
+// a skewed input: millions of copies of one k-mer -- sends its bucket's remaining items straight into the table
+// (atomicOr, unsorted), so any input stays exact.  Nothing is counted on the host: bloom_apply_staged_kernel reads the
+// cursors itself.  (Round 1 staged in arrival order, then radix-sorted by bucket with cub and read the item count
+// back in the middle of the pass.)
 struct StageSink {
-    unsigned long long* items;     // staging array: (block << 16) | pattern
-    unsigned long long* cursor;    // items reserved so far (a multiple of the granule)
+    unsigned long long* items;      // [n_buckets * cap]: (block << 16) | pattern
+    unsigned long long* cursor;     // [n_buckets] items reserved in each region (a multiple of the granule)
+    unsigned long long cap;         // items per region (a multiple of the granule)
+    uint32_t n_buckets, granule;
+    int shift;                      // bucket = block >> shift (KBBQ_STAGE_BUCKET_SHIFT; smaller in tests)
 };
-struct StageCursor {  // per warp, in registers (uniform across the lanes)
-    unsigned long long base;
-    uint32_t used;
-};
-// append the (block, pattern) of the lanes with `ins` set; returns how many.  All 32 lanes must call.
-__device__ __forceinline__ int warp_stage_insert_bp(const StageSink& sink, StageCursor& cur, bool ins, uint64_t blk, uint32_t pat) {
+#define KBBQ_STAGE_USED(s) ((uint32_t)((s) & 0xFFFFull))
+// shared memory of a staging block: state[n_buckets] then overflow flags[n_buckets] (u32)
+__device__ __forceinline__ void block_stage_open(const StageSink& sink, unsigned long long* state, uint32_t* ovf) {
+    for (uint32_t b = threadIdx.x; b < sink.n_buckets; b += blockDim.x) {
+        state[b] = (unsigned long long)sink.granule;  // no granule yet, and "full": the first item reserves one
+        ovf[b] = 0;
+    }
+    __syncthreads();
+}
+// pattern_blocked_bf::insert straight into the table, one thread (the overflow path)
+__device__ __noinline__ void bloom_insert_bp_thread(const BloomView& f, uint64_t blk, uint32_t pat) {
+    const ulonglong2* P = reinterpret_cast<const ulonglong2*>(f.patterns + (uint64_t)pat * 8);
+    unsigned long long* B = f.words + blk * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const ulonglong2 p = __ldg(P + i);
+        if (p.x) atomicOr(B + 2 * i, p.x);
+        if (p.y) atomicOr(B + 2 * i + 1, p.y);
+    }
+}
+__device__ __forceinline__ void thread_stage_append(const BloomView& f, const StageSink& sink, unsigned long long* state, uint32_t* ovf,
+                                                    uint64_t blk, uint32_t pat) {
+    const uint32_t b = (uint32_t)(blk >> sink.shift);
+    const unsigned long long item = ((unsigned long long)blk << 16) | pat;
+    for (;;) {
+        if (*(volatile uint32_t*)(ovf + b)) {  // the region is full: straight into the table
+            bloom_insert_bp_thread(f, blk, pat);
+            return;
+        }
+        const unsigned long long old = atomicAdd(state + b, 1ull);
+        const uint32_t used = KBBQ_STAGE_USED(old);
+        if (used < sink.granule) {
+            sink.items[(old >> 16) - 1 + used] = item;
+            return;
+        }
+        if (used == sink.granule) {  // this thread reserves the block's next granule of the region
+            const unsigned long long at = atomicAdd(sink.cursor + b, (unsigned long long)sink.granule);
+            if (at + sink.granule <= sink.cap) {
+                const unsigned long long base = (unsigned long long)b * sink.cap + at;
+                sink.items[base] = item;
+                __threadfence_block();
+                atomicExch(state + b, ((base + 1) << 16) | 1ull);
+            } else {
+                atomicExch(ovf + b, 1u);
+                bloom_insert_bp_thread(f, blk, pat);
+            }
+            return;
+        }
+        // somebody is reserving: wait for the new granule (or the overflow flag), then try again
+        while (KBBQ_STAGE_USED(*(volatile unsigned long long*)(state + b)) > sink.granule && !*(volatile uint32_t*)(ovf + b)) __nanosleep(40);
+    }
+}
+// all 32 lanes call; returns how many lanes had an item
+__device__ __forceinline__ int warp_stage_insert_bp(const BloomView& f, const StageSink& sink, unsigned long long* state, uint32_t* ovf, bool ins,
+                                                    uint64_t blk, uint32_t pat) {
     const uint32_t imask = __ballot_sync(KBBQ_FULL, ins);
-    if (imask == 0) return 0;
-    const int lane = threadIdx.x & 31, n = __popc(imask);
-    if (cur.used + (uint32_t)n > KBBQ_STAGE_GRANULE) {  // close the granule with filler, reserve the next one
-        for (uint32_t i = cur.used + lane; i < KBBQ_STAGE_GRANULE; i += 32) sink.items[cur.base + i] = KBBQ_STAGE_SENTINEL;
-        unsigned long long nb = 0;
-        if (lane == 0) nb = atomicAdd(sink.cursor, (unsigned long long)KBBQ_STAGE_GRANULE);
-        cur.base = __shfl_sync(KBBQ_FULL, nb, 0);
-        cur.used = 0;
+    if (ins) thread_stage_append(f, sink, state, ovf, blk, pat);
+    __syncwarp();
+    return __popc(imask);
+}
+__device__ __forceinline__ int warp_stage_insert(const BloomView& f, const StageSink& sink, unsigned long long* state, uint32_t* ovf, bool ins,
+                                                 uint64_t key) {
+    return warp_stage_insert_bp(f, sink, state, ovf, ins, ins ? bloom_block(f, key) : 0, ins ? bloom_pattern(f, key) : 0);
+}
+// fill the unused tail of every granule this block still holds
+__device__ __forceinline__ void block_stage_close(const StageSink& sink, const unsigned long long* state) {
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    for (uint32_t b = wib; b < sink.n_buckets; b += nwb) {
+        const unsigned long long s = state[b];
+        if ((s >> 16) == 0) continue;  // never reserved a granule of this region
+        const uint32_t used = KBBQ_STAGE_USED(s) < sink.granule ? KBBQ_STAGE_USED(s) : sink.granule;
+        for (uint32_t i = used + lane; i < sink.granule; i += 32) sink.items[(s >> 16) - 1 + i] = KBBQ_STAGE_SENTINEL;
     }
-    if (ins) {
-        const int rank = __popc(imask & ((1u << lane) - 1));
-        sink.items[cur.base + cur.used + rank] = ((unsigned long long)blk << 16) | pat;
-    }
-    cur.used += (uint32_t)n;
-    return n;
-}
-__device__ __forceinline__ int warp_stage_insert(const BloomView& f, const StageSink& sink, StageCursor& cur, bool ins, uint64_t key) {
-    return warp_stage_insert_bp(sink, cur, ins, ins ? bloom_block(f, key) : 0, ins ? bloom_pattern(f, key) : 0);
-}
-__device__ __forceinline__ void warp_stage_open(const StageSink& sink, StageCursor& cur) {
-    unsigned long long nb = 0;
-    if ((threadIdx.x & 31) == 0) nb = atomicAdd(sink.cursor, (unsigned long long)KBBQ_STAGE_GRANULE);
-    cur.base = __shfl_sync(KBBQ_FULL, nb, 0);
-    cur.used = 0;
-}
-__device__ __forceinline__ void warp_stage_close(const StageSink& sink, const StageCursor& cur) {
-    for (uint32_t i = cur.used + (threadIdx.x & 31); i < KBBQ_STAGE_GRANULE; i += 32) sink.items[cur.base + i] = KBBQ_STAGE_SENTINEL;
 }
 
 template <bool TEST_FIRST>
@@ -373,13 +433,15 @@ template <int MODE>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel(BatchView b, BloomView f, int k,
                                                                                   const uint32_t* __restrict__ sample_bits,
                                                                                   StageSink sink) {
+    extern __shared__ unsigned long long p1_stage_state[];  // INS_STAGED: state[n_buckets], then flags[n_buckets]
     __shared__ InsertStage stage_all[KBBQ_WARPS_PER_BLOCK];
     InsertStage& stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
-    StageCursor cur{0, 0};
-    if (MODE == INS_STAGED) warp_stage_open(sink, cur);
+    unsigned long long* sstate = p1_stage_state;
+    uint32_t* sovf = reinterpret_cast<uint32_t*>(p1_stage_state + sink.n_buckets);
+    if (MODE == INS_STAGED) block_stage_open(sink, sstate, sovf);
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
         const int len = (int)b.len[r];
         const int nk = len - k + 1;
@@ -396,11 +458,11 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
                 if ((__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u)
                     ins = kmer_key(s, j, k, 0, -1, key);  // an invalid k-mer still consumed its draw
             }
-            if (MODE == INS_STAGED) inserted += warp_stage_insert(f, sink, cur, ins, key);
+            if (MODE == INS_STAGED) inserted += warp_stage_insert(f, sink, sstate, sovf, ins, key);
             else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(f, ins, key, stage);
         }
     }
-    if (MODE == INS_STAGED) warp_stage_close(sink, cur);
+    if (MODE == INS_STAGED) block_stage_close(sink, sstate);
     if (lane == 0 && inserted) atomicAdd(f.inserted, inserted);
 }
 
@@ -411,7 +473,9 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
 // SHARED_HASH: both filters were built with the same seed, so salt_[0] and salt_[1] agree (the reference's filters
 // always do: bloom.hh:389, kbbq.cc:265-266) and a k-mer's block hash and pattern number are computed once, for the
 // query of `sampled`, and kept in shared memory for the insert into `trusted` (dynamic: 8 bytes per k-mer and warp).
-template <int MODE, bool SHARED_HASH>
+// PREFETCH (with SHARED_HASH; `sampled` lives in HBM): hash every k-mer and prefetch its block first, probe afterwards
+// (see prefetch_l2).
+template <int MODE, bool SHARED_HASH, bool PREFETCH>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P2_MIN_BLOCKS)
 pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, const int* __restrict__ thresholds,
                      uint32_t* __restrict__ err_out, StageSink sink, int max_kmers, const uint32_t* __restrict__ known_bits,
@@ -430,8 +494,10 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
     uint2* HP = p2_hash + (size_t)wib * (SHARED_HASH ? max_kmers : 0);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
-    StageCursor cur{0, 0};
-    if (MODE == INS_STAGED) warp_stage_open(sink, cur);
+    // INS_STAGED: the staging state follows the hashes in dynamic shared memory: state[n_buckets], then flags[n_buckets]
+    unsigned long long* sstate = reinterpret_cast<unsigned long long*>(p2_hash + (SHARED_HASH ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers : 0));
+    uint32_t* sovf = reinterpret_cast<uint32_t*>(sstate + sink.n_buckets);
+    if (MODE == INS_STAGED) block_stage_open(sink, sstate, sovf);
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
         const int len = (int)b.len[r];
         const int nk = len - k + 1;
@@ -442,6 +508,32 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         // `sampled` then (known_bits = that pass's sample bits, given only while the filter has not been cleared since):
         // it is present without asking -- a Bloom filter has no false negatives -- and its 64-byte probe is saved.
         const unsigned long long so = b.slot_off[r];
+        if (SHARED_HASH && PREFETCH) {
+            for (int j0 = 0; j0 < nk; j0 += 32) {
+                const int j = j0 + lane;
+                uint64_t key = 0;
+                const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+                bool known = false;
+                if (known_bits && valid) {
+                    const unsigned long long slot = so + (unsigned)j;
+                    known = (__ldg(known_bits + (slot >> 5)) >> (slot & 31)) & 1u;
+                }
+                const uint32_t h = hash_ap8(key, sampled.salt0);
+                if (valid && !known) prefetch_l2(sampled.words + bloom_block_of_hash(sampled, h) * 8);
+                // the pattern number is kept for the insert into `trusted`; bit 31 marks "present without asking"
+                if (j < nk) HP[j] = make_uint2(h, valid ? bloom_pattern(sampled, key) | (known ? 0x80000000u : 0u) : KBBQ_HP_INVALID);
+            }
+            __syncwarp();
+            for (int j0 = 0; j0 < nk; j0 += 32) {
+                const int j = j0 + lane;
+                uint2 hp = j < nk ? HP[j] : make_uint2(0u, KBBQ_HP_INVALID);
+                const bool valid = hp.y != KBBQ_HP_INVALID, known = valid && (hp.y & 0x80000000u);
+                uint32_t m = warp_bloom_query_bp(sampled, valid && !known, bloom_block_of_hash(sampled, hp.x), hp.y & 0xFFFFu);
+                m |= __ballot_sync(KBBQ_FULL, known);
+                if (known) HP[j].y = hp.y & 0xFFFFu;  // back to a plain pattern number for the insert loop
+                if (lane == 0) Pm[j0 >> 5] = m;
+            }
+        } else
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
             uint64_t key = 0;
@@ -491,7 +583,7 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
                     const uint32_t im = __ballot_sync(KBBQ_FULL, ins);
                     if (lane == 0) ins_out[wo + (j0 >> 5)] = im;
                 }
-                if (MODE == INS_STAGED) inserted += warp_stage_insert_bp(sink, cur, ins, blk, hp.y);
+                if (MODE == INS_STAGED) inserted += warp_stage_insert_bp(trusted, sink, sstate, sovf, ins, blk, hp.y);
                 else inserted += warp_bloom_insert_bp<MODE == INS_TEST_FIRST>(trusted, ins, blk, hp.y, stage);
             } else {
                 uint64_t key = 0;
@@ -500,13 +592,13 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
                     const uint32_t im = __ballot_sync(KBBQ_FULL, ins);
                     if (lane == 0) ins_out[wo + (j0 >> 5)] = im;
                 }
-                if (MODE == INS_STAGED) inserted += warp_stage_insert(trusted, sink, cur, ins, key);
+                if (MODE == INS_STAGED) inserted += warp_stage_insert(trusted, sink, sstate, sovf, ins, key);
                 else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(trusted, ins, key, stage);
             }
         }
         __syncwarp();
     }
-    if (MODE == INS_STAGED) warp_stage_close(sink, cur);
+    if (MODE == INS_STAGED) block_stage_close(sink, sstate);
     if (lane == 0 && inserted) atomicAdd(trusted.inserted, inserted);
 }
 
@@ -724,11 +816,16 @@ covariate_count_kernel(BatchView b, FlatMap fm, CountView cv, const uint32_t* __
 #ifndef KBBQ_P3_MIN_BLOCKS
 #define KBBQ_P3_MIN_BLOCKS 4
 #endif
+// PREFETCH (filters that live in HBM): first hash every k-mer of the read, prefetch its block and park (hash, pattern)
+// in shared memory (8 bytes per k-mer and warp, dynamic); then probe round by round from there.
+template <bool PREFETCH>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
 pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
                   uint32_t* __restrict__ mod_out, uint32_t* __restrict__ repair_list, unsigned int* __restrict__ repair_count,
-                  const uint32_t* __restrict__ known_bits) {
+                  const uint32_t* __restrict__ known_bits, int max_kmers) {
+    extern __shared__ uint2 scan_hash[];  // PREFETCH: [warps][max_kmers]
     const int lane = threadIdx.x & 31;
+    uint2* HP = scan_hash + (size_t)(threadIdx.x >> 5) * (PREFETCH ? max_kmers : 0);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = warp; r < b.n_reads; r += nwarps) {
         const int len = (int)b.len[r];
@@ -738,18 +835,39 @@ pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ 
         bool all_trusted = true;
         if (nk > 0) {
             const CSeqRef s{b.bases + wo, b.nmask + wo, len};
+            if (PREFETCH) {
+                for (int j0 = 0; j0 < nk; j0 += 32) {
+                    const int j = j0 + lane;
+                    uint64_t key = 0;
+                    const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+                    const uint32_t known = known_bits ? __ldg(known_bits + wo + (j0 >> 5)) : 0u;
+                    const bool ask = valid && !((known >> lane) & 1u);
+                    const uint32_t h = hash_ap8(key, trusted.salt0);
+                    if (ask) prefetch_l2(trusted.words + bloom_block_of_hash(trusted, h) * 8);
+                    if (j < nk) HP[j] = make_uint2(h, ask ? bloom_pattern(trusted, key) : valid ? KBBQ_HP_KNOWN : KBBQ_HP_INVALID);
+                }
+                __syncwarp();
+            }
             for (int j0 = 0; j0 < nk; j0 += 32) {
                 const int j = j0 + lane;
-                uint64_t key = 0;
-                const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+                uint32_t m;
                 // k-mers pass 2 inserted from this very batch (known_bits, per k-mer in the word layout; given only while
-                // `trusted` has not been cleared since) are present without asking: a third of all probes at 30X
-                const uint32_t known = known_bits ? __ldg(known_bits + wo + (j0 >> 5)) : 0u;
-                const uint32_t m = warp_bloom_query<true>(trusted, valid && !((known >> lane) & 1u), key) | known;
+                // `trusted` has not been cleared since) are present without asking: a third of all k-mers at 30X
+                if (PREFETCH) {
+                    const uint2 hp = j < nk ? HP[j] : make_uint2(0u, KBBQ_HP_INVALID);
+                    m = warp_bloom_query_bp(trusted, hp.y < KBBQ_HP_KNOWN, bloom_block_of_hash(trusted, hp.x), hp.y) |
+                        __ballot_sync(KBBQ_FULL, hp.y == KBBQ_HP_KNOWN);
+                } else {
+                    uint64_t key = 0;
+                    const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+                    const uint32_t known = known_bits ? __ldg(known_bits + wo + (j0 >> 5)) : 0u;
+                    m = warp_bloom_query<true>(trusted, valid && !((known >> lane) & 1u), key) | known;
+                }
                 const int cnt = nk - j0 < 32 ? nk - j0 : 32;
                 all_trusted = all_trusted && m == (cnt < 32 ? (1u << cnt) - 1u : ~0u);
                 if (lane == 0) tflags[wo + (j0 >> 5)] = m;
             }
+            __syncwarp();
         }
         // fewer than k bases (out of contract in the reference, bloom.cc:30): untouched, like a clean read
         if (all_trusted || nk <= 0) {
@@ -922,14 +1040,24 @@ pass4_apply_kernel(BatchView b, FlatMap fm, ModelView mv, int n_rg, uint8_t* __r
     }
 }
 
-// ---- applying a sorted staging array (INS_STAGED): four lanes per item, items in block order -----------------------
-__global__ void __launch_bounds__(256) bloom_insert_sorted_kernel(BloomView f, const unsigned long long* __restrict__ items,
-                                                                  unsigned long long n) {
+// ---- applying the staged items (INS_STAGED): four lanes per item, region after region --------------------------------
+// The flattened index space is n_buckets x cap; a position beyond its region's cursor holds nothing.  Consecutive
+// positions belong to one region, so at any moment all SMs update one 16 MiB slice of the table.
+__global__ void __launch_bounds__(256) bloom_apply_staged_kernel(BloomView f, StageSink sink) {
+    const unsigned long long total = (unsigned long long)sink.n_buckets * sink.cap;
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long stride = ((unsigned long long)gridDim.x * blockDim.x) >> 2;
     const int sub = (int)(threadIdx.x & 3);
-    for (unsigned long long i = t >> 2; i < n; i += stride) {
-        const unsigned long long it = __ldg(items + i);
+    for (unsigned long long i = t >> 2; i < total; i += stride) {
+        const unsigned long long bkt = i / sink.cap, o = i - bkt * sink.cap;
+        unsigned long long filled = __ldg(sink.cursor + bkt);
+        if (filled > sink.cap) filled = sink.cap - sink.cap % sink.granule;  // reservations past the end were refused
+        if (o >= filled) {  // nothing further in this region: jump to the next one (keeping this thread's lane phase)
+            const unsigned long long next = (bkt + 1) * sink.cap, skip = (next - i + stride - 1) / stride;
+            i += (skip - 1) * stride;
+            continue;
+        }
+        const unsigned long long it = __ldg(sink.items + i);
         if (it == KBBQ_STAGE_SENTINEL) continue;
         ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(f.patterns + (it & 0xFFFFull) * 8) + sub);
         unsigned long long* B = f.words + (it >> 16) * 8 + 2 * sub;

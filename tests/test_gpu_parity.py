@@ -290,12 +290,18 @@ def test_human_scale_filters_address_every_block():
     ctx.close()
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_insert_modes_for_large_filters_give_the_same_bits(mode, monkeypatch):
+@pytest.mark.parametrize("mode,shift,cap", [("1", None, None), ("2", None, None), ("2", "6", None), ("2", "6", "256"), ("2", "4", "128")])
+def test_insert_modes_for_large_filters_give_the_same_bits(mode, shift, cap, monkeypatch):
     """Filters larger than the L2 are filled through other code paths (kbbq_kernels.cuh INS_TEST_FIRST: read before OR;
-    INS_STAGED: stage (block, pattern), radix-sort by block range, apply): forced here on a small input, every
-    intermediate and the filters' words must still equal the oracle's."""
+    INS_STAGED: (block, pattern) items staged into one region per slice of the table, then applied region after region):
+    forced here on a small input -- with the slices shrunk so that there are hundreds of them (KBBQ_STAGE_SHIFT), and with
+    regions so small that most items take the overflow path (KBBQ_STAGE_CAP) -- every intermediate and the filters'
+    words must still equal the oracle's."""
     monkeypatch.setenv("KBBQ_INSERT_MODE", mode)
+    if shift:
+        monkeypatch.setenv("KBBQ_STAGE_SHIFT", shift)
+    if cap:
+        monkeypatch.setenv("KBBQ_STAGE_CAP", cap)
     G, cov, L, k = 80000, 30, 150, 32
     rs = synth.make_reads(G, cov, L, seed=61, n_rg=2, n_frac=0.002, ragged=True, min_len=40)
     common.compare(common.run_gpu(rs, k, G, cov, 2024, n_batches=2), common.run_port(rs, k, G, cov, 2024))
@@ -400,3 +406,35 @@ def test_fixed_mode_on_the_device_matches_port(ragged):
     db.free()
     df.free()
     ctx.close()
+
+
+def test_known_present_kmers_change_nothing(monkeypatch):
+    """Pass 2 skips the probes of k-mers pass 1 sampled from the same batch, pass 3's scan those pass 2 inserted (a Bloom
+    filter has no false negatives); with the shortcut switched off the run must give the same bits -- and clearing a
+    filter between the passes must switch it off by itself (kbbq_ctx::epoch)."""
+    G, cov, L, k = 80000, 30, 150, 32
+    rs = synth.make_reads(G, cov, L, seed=62, n_rg=2, n_frac=0.002)
+    with_bits = common.run_gpu(rs, k, G, cov, 77, n_batches=2)
+    monkeypatch.setenv("KBBQ_NO_KNOWN_BITS", "1")
+    without = common.run_gpu(rs, k, G, cov, 77, n_batches=2)
+    common.compare(with_bits, without)
+    monkeypatch.delenv("KBBQ_NO_KNOWN_BITS")
+    # pass 1 on a batch, then the sampled filter is cleared and rebuilt from OTHER reads: the batch's sample bits must
+    # not be trusted any more
+    from kbbq_b200.pipeline import Recalibrator
+    other = synth.make_reads(G, cov, L, seed=63, n_rg=2)
+    rc = Recalibrator(k, 2, L, G, cov, 77)
+    db, do = rc.ctx.upload(api.PackedBatch(rs)), rc.ctx.upload(api.PackedBatch(other))
+    rc.ctx.sampler_seed(77, float(rc.alpha_ld))
+    rc.ctx.pass1(db)
+    rc.ctx.bloom_clear(api.FILTER_SAMPLED)
+    rc.ctx.sampler_seek(0)
+    rc.ctx.pass1(do)
+    th = rc.ctx.compute_thresholds(rc.alpha_ld)
+    bits = rc.ctx.pass2(db, want_errors=True)
+    want = P.PortPipeline(rs, k)
+    sampled = P.PortBloom(rc.approx_kmers, 0.01)
+    P.PortPipeline(other, k).subsample(sampled, float(rc.alpha_ld), 77)
+    pb = api.PackedBatch(rs)
+    assert np.array_equal(pb.unpack_bits(bits, rs.total_bases), want.infer_errors(sampled, th))
+    rc.close()
