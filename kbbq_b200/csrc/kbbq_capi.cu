@@ -27,6 +27,14 @@ namespace {
 
 thread_local std::string g_err;
 
+// host threads the library may use for the model fit: 16 at most, fewer when several processes share the box
+// (KBBQ_HOST_THREADS, e.g. cores / ranks: bench.py sets it)
+int host_threads() {
+    unsigned n = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("KBBQ_HOST_THREADS")) n = (unsigned)std::max(1, std::min(64, atoi(e)));
+    return (int)n;
+}
+
 int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -352,7 +360,7 @@ int staging_begin(kbbq_ctx* ctx, int which, uint64_t n_slots, int grid_blocks, S
 // apply the staged (block, pattern) items to filter `which`, region after region; nothing comes back to the host
 int staging_apply(kbbq_ctx* ctx, int which, Staging& st) {
     mark_kernel(ctx, "bloom_apply_staged_kernel");
-    bloom_apply_staged_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->filt[which].view(), st.sink);
+    bloom_apply_staged_kernel<<<ctx->sm_count * 8, 256, ((size_t)st.sink.n_buckets + 1) * 8, ctx->stream>>>(ctx->filt[which].view(), st.sink);
     return check_launch(ctx, "bloom_apply_staged_kernel");
 }
 
@@ -532,7 +540,7 @@ int kbbq_rng_state(uint32_t seed, uint64_t skip, uint64_t state[4]) {
 int kbbq_fit_model_host(int n_rg, int max_cycle, const uint64_t* rgc, const uint64_t* qc, const uint64_t* cyc,
                         const uint64_t* dic, int32_t* meanq, int32_t* rgdq, int32_t* qdq, int32_t* cydq, int32_t* didq) {
     if (n_rg < 1 || max_cycle < 1) return fail(KBBQ_EINVAL, "bad table extents");
-    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const int nt = host_threads();
     host::fit_model(n_rg, max_cycle, rgc, qc, cyc, dic, meanq, rgdq, qdq, cydq, didq, nt);
     return KBBQ_OK;
 }
@@ -1454,8 +1462,10 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         const size_t smem = (shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0) + (mode == INS_STAGED ? st.smem() : 0);
         const int threads = KBBQ_WARPS_PER_BLOCK * 32;
 #define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S, PF><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers, known, b->d_ins_bits)
-        // filters beyond the L2: prefetch the blocks of all of a read's k-mers before probing (KBBQ_NO_PREFETCH=1: off)
-        const bool prefetch = shared_hash && ctx->filt[KBBQ_FILTER_SAMPLED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4 && !getenv("KBBQ_NO_PREFETCH");
+        // KBBQ_PREFETCH=1 (measurement): prefetch the blocks of all of a read's k-mers into the L2 before probing.  Measured
+        // on the config-3 shape it LOSES -- 44 -> 68 ms here, 37 -> 53 ms in pass 3's scan: the prefetched lines are evicted
+        // by the other 4700 warps' before their probes arrive, and are then fetched a second time -- so it stays off.
+        const bool prefetch = shared_hash && ctx->filt[KBBQ_FILTER_SAMPLED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4 && getenv("KBBQ_PREFETCH");
         if (shared_hash && prefetch) {
             constexpr bool PF = true;
             if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, true);
@@ -1501,8 +1511,8 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         mark_kernel(ctx, "pass3_scan_kernel");
         const uint32_t* known = b->d_ins_bits && b->ins_epoch == ctx->epoch[KBBQ_FILTER_TRUSTED] && !getenv("KBBQ_NO_KNOWN_BITS") ? b->d_ins_bits : nullptr;
         const int max_kmers = std::max(1, (int)b->max_len - ctx->k + 1);
-        // a filter beyond the L2: prefetch the blocks of all of a read's k-mers before probing (KBBQ_NO_PREFETCH=1: off)
-        if (ctx->filt[KBBQ_FILTER_TRUSTED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4 && !getenv("KBBQ_NO_PREFETCH"))
+        // KBBQ_PREFETCH=1 (measurement; off because it loses, see pass 2)
+        if (ctx->filt[KBBQ_FILTER_TRUSTED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4 && getenv("KBBQ_PREFETCH"))
             pass3_scan_kernel<true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2), ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
         else
@@ -1652,7 +1662,7 @@ int kbbq_fit_model(kbbq_ctx* ctx, int32_t* meanq, int32_t* rgdq, int32_t* qdq, i
     const uint64_t* qc = rgc + ctx->n_rgc;
     const uint64_t* cyc = qc + ctx->n_qc;
     const uint64_t* dic = cyc + ctx->n_cyc;
-    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const int nt = host_threads();
     host::fit_model(R, C, rgc, qc, cyc, dic, m.data(), g.data(), q.data(), cy.data(), di.data(), nt);
     if (meanq) std::memcpy(meanq, m.data(), m.size() * 4);
     if (rgdq) std::memcpy(rgdq, g.data(), g.size() * 4);

@@ -435,7 +435,9 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
                                                                                   StageSink sink) {
     extern __shared__ unsigned long long p1_stage_state[];  // INS_STAGED: state[n_buckets], then flags[n_buckets]
     __shared__ InsertStage stage_all[KBBQ_WARPS_PER_BLOCK];
+    __shared__ uint16_t pos_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAX_READ_LEN];  // start positions of a read's sampled k-mers
     InsertStage& stage = stage_all[threadIdx.x >> 5];
+    uint16_t* pos = pos_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
@@ -449,18 +451,29 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
         const uint32_t wo = b.word_off[r];
         const CSeqRef s{b.bases + wo, b.nmask + wo, len};
         const unsigned long long so = b.slot_off[r];
+        // the sampled positions first (a bit test and a ballot per 32 slots), then keys for those only, 32 at a time:
+        // at alpha = 7/30 a 150-base read has 28 of them -- one dense round instead of four quarter-full ones
+        int total = 0;
         for (int j0 = 0; j0 < nk; j0 += 32) {
             const int j = j0 + lane;
-            bool ins = false;
-            uint64_t key = 0;
+            bool hit = false;
             if (j < nk) {
                 const unsigned long long slot = so + (unsigned)j;
-                if ((__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u)
-                    ins = kmer_key(s, j, k, 0, -1, key);  // an invalid k-mer still consumed its draw
+                hit = (__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u;
             }
+            const uint32_t m = __ballot_sync(KBBQ_FULL, hit);
+            if (hit) pos[total + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+            total += __popc(m);
+        }
+        __syncwarp();
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            uint64_t key = 0;
+            const bool ins = t < total && kmer_key(s, (int)pos[t], k, 0, -1, key);  // an invalid k-mer still consumed its draw
             if (MODE == INS_STAGED) inserted += warp_stage_insert(f, sink, sstate, sovf, ins, key);
             else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(f, ins, key, stage);
         }
+        __syncwarp();
     }
     if (MODE == INS_STAGED) block_stage_close(sink, sstate);
     if (lane == 0 && inserted) atomicAdd(f.inserted, inserted);
@@ -1041,23 +1054,48 @@ pass4_apply_kernel(BatchView b, FlatMap fm, ModelView mv, int n_rg, uint8_t* __r
 }
 
 // ---- applying the staged items (INS_STAGED): four lanes per item, region after region --------------------------------
-// The flattened index space is n_buckets x cap; a position beyond its region's cursor holds nothing.  Consecutive
-// positions belong to one region, so at any moment all SMs update one 16 MiB slice of the table.
+// Every block first forms the running totals of the regions' fill counts (shared memory, n_buckets + 1 entries); the
+// grid then strides over the DENSE sequence of filled positions -- region 0's items, then region 1's, ... -- so that at
+// any moment all SMs update the same 16 MiB slice of the table, whatever share of each region is filled.
 __global__ void __launch_bounds__(256) bloom_apply_staged_kernel(BloomView f, StageSink sink) {
-    const unsigned long long total = (unsigned long long)sink.n_buckets * sink.cap;
+    extern __shared__ unsigned long long fill_end[];  // [n_buckets + 1]: fill_end[b] = items in regions 0 .. b-1
+    __shared__ unsigned long long warp_tot[8];
+    {   // exclusive scan of the (clamped) cursors: each thread owns a contiguous run of regions
+        const uint32_t per = (sink.n_buckets + blockDim.x - 1) / blockDim.x;
+        const uint32_t lo = threadIdx.x * per, hi = lo + per < sink.n_buckets ? lo + per : sink.n_buckets;
+        unsigned long long mine = 0;
+        for (uint32_t bkt = lo; bkt < hi; ++bkt) {
+            const unsigned long long c = __ldg(sink.cursor + bkt);
+            mine += c < sink.cap ? c : sink.cap;  // reservations past the end of a region were refused
+        }
+        unsigned long long incl = mine;
+        const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long y = __shfl_up_sync(KBBQ_FULL, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (lane == 31) warp_tot[wib] = incl;
+        __syncthreads();
+        unsigned long long before = incl - mine;
+        for (int w = 0; w < wib; ++w) before += warp_tot[w];
+        for (uint32_t bkt = lo; bkt < hi; ++bkt) {
+            fill_end[bkt] = before;
+            const unsigned long long c = __ldg(sink.cursor + bkt);
+            before += c < sink.cap ? c : sink.cap;
+        }
+        if (hi == sink.n_buckets && lo < hi) fill_end[sink.n_buckets] = before;
+        if (sink.n_buckets == 0 && threadIdx.x == 0) fill_end[0] = 0;
+        __syncthreads();
+    }
+    const unsigned long long total = fill_end[sink.n_buckets];
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long stride = ((unsigned long long)gridDim.x * blockDim.x) >> 2;
     const int sub = (int)(threadIdx.x & 3);
+    uint32_t bkt = 0;
     for (unsigned long long i = t >> 2; i < total; i += stride) {
-        const unsigned long long bkt = i / sink.cap, o = i - bkt * sink.cap;
-        unsigned long long filled = __ldg(sink.cursor + bkt);
-        if (filled > sink.cap) filled = sink.cap - sink.cap % sink.granule;  // reservations past the end were refused
-        if (o >= filled) {  // nothing further in this region: jump to the next one (keeping this thread's lane phase)
-            const unsigned long long next = (bkt + 1) * sink.cap, skip = (next - i + stride - 1) / stride;
-            i += (skip - 1) * stride;
-            continue;
-        }
-        const unsigned long long it = __ldg(sink.items + i);
+        while (i >= fill_end[bkt + 1]) ++bkt;  // positions only grow: the region index is found by walking on
+        const unsigned long long it = __ldg(sink.items + (unsigned long long)bkt * sink.cap + (i - fill_end[bkt]));
         if (it == KBBQ_STAGE_SENTINEL) continue;
         ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(f.patterns + (it & 0xFFFFull) * 8) + sub);
         unsigned long long* B = f.words + (it >> 16) * 8 + 2 * sub;
