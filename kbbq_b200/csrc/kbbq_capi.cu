@@ -1231,6 +1231,13 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, i
     {   // the qualities (3/5 of the bytes) go last and on the copy stream: pass 1 does not read them and starts
         // as soon as everything above has landed
         cudaError_t e2 = e1;
+        if (mode != 2 && e2 == cudaSuccess) {  // ... and BEHIND everything above: two concurrent copies would share the link,
+            cudaEvent_t small_done = nullptr;  // and the bases pass 1 waits for would arrive at half speed
+            e2 = cudaEventCreateWithFlags(&small_done, cudaEventDisableTiming);
+            if (e2 == cudaSuccess) e2 = cudaEventRecord(small_done, ctx->stream);
+            if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(ctx->copy_stream, small_done, 0);
+            if (small_done) cudaEventDestroy(small_done);
+        }
         if (e2 == cudaSuccess && !h->n_words) e2 = cudaMemsetAsync(b->d_qual, 0, 32, ctx->copy_stream);
         if (e2 == cudaSuccess && h->n_words)
             e2 = cudaMemcpyAsync(b->d_qual, h->qual, (size_t)h->n_words * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
