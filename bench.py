@@ -231,6 +231,85 @@ def run_reference_arm(args):
     return 0
 
 
+# ---- file to file ---------------------------------------------------------------------------------------------------------
+def write_fastq(path, rs):
+    """the read set as 4-line FASTQ (names r<9 digits>/<mate>_RG:Z:rg<id>), assembled as one fixed-width byte matrix"""
+    n, L = rs.n, READ_LEN
+    head = 22
+    rec = np.empty((n, head + 1 + L + 3 + L + 1), dtype=np.uint8)
+    idx = np.arange(n, dtype=np.int64)
+    rec[:, 0], rec[:, 1] = ord("@"), ord("r")
+    for d in range(9):
+        rec[:, 2 + d] = (idx // 10 ** (8 - d) % 10 + 48).astype(np.uint8)
+    rec[:, 11] = ord("/")
+    rec[:, 12] = (49 + rs.second).astype(np.uint8)
+    rec[:, 13:21] = np.frombuffer(b"_RG:Z:rg", dtype=np.uint8)
+    rec[:, 21] = (48 + rs.rg).astype(np.uint8)
+    rec[:, head] = 10
+    rec[:, head + 1 : head + 1 + L] = rs.seq.reshape(n, L)
+    rec[:, head + 1 + L : head + 4 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    rec[:, head + 4 + L : head + 4 + 2 * L] = rs.qual.reshape(n, L) + 33
+    rec[:, -1] = 10
+    rec.tofile(path)
+
+
+def file_to_file_leg():
+    """`e2e_file`: wall time of this repo's kbbq CLI, file to file, on a config-2-sized FASTQ (4.6 Mb genome, 50X,
+    1.53 M reads): read + parse, pack, all passes on the GPU, format, BGZF-compress, write.  The second of two runs."""
+    import tempfile
+    from kbbq_b200 import api
+
+    cli = os.path.join(ROOT, "kbbq_b200", "host", "kbbq")
+    if not os.path.exists(cli):
+        return {"unavailable": "kbbq_b200/host/kbbq is not built"}
+    G, cov = 4_600_000, 50
+    rs = api.synth_host(synth_params(G, 1000), 0, G * cov // READ_LEN, n_threads=os.cpu_count() or 1)
+    with tempfile.TemporaryDirectory() as d:
+        fq, out = os.path.join(d, "c2.fq"), os.path.join(d, "out.fq.gz")
+        write_fastq(fq, rs)
+        walls = []
+        for level in ("6", "1"):
+            for _ in range(2):
+                t0 = time.perf_counter()
+                with open(out, "wb") as fo:
+                    r = subprocess.run([cli, "--seed", str(SEED), "-k", str(K), "-g", str(G), "-c", str(cov), fq], stdout=fo,
+                                       stderr=subprocess.DEVNULL, env=dict(os.environ, KBBQ_BGZF_LEVEL=level))
+                dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return {"unavailable": f"kbbq exited {r.returncode}"}
+            walls.append(dt)
+        size_in, size_out = os.path.getsize(fq), os.path.getsize(out)
+    return {"value": rs.total_bases / walls[1], "unit": "bases/s", "wall_s": walls[1], "bgzf_level": 1,
+            "value_at_zlib_default_level": rs.total_bases / walls[0], "wall_s_at_zlib_default_level": walls[0],
+            "workload": f"config-2-sized FASTQ: {rs.n} reads x {READ_LEN} bp, {size_in / 1e6:.0f} MB in, {size_out / 1e6:.0f} MB of BGZF out",
+            "what": "wall time of kbbq_b200/host/kbbq from input file to output file (process start to exit, CUDA context creation "
+                    "included), second of two runs per compression level; htslib's default level is zlib's (6)"}
+
+
+def bind_to_gpu_numa(local):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned buffers it allocates (first touch) sit on the
+    memory the GPU's PCIe root reads directly: at N=8 eight ranks otherwise push 44 GB per step through whichever node
+    their threads happened to start on.  Best effort: returns the node or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out  # sysfs uses a 4-digit domain
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ---- our arm ----------------------------------------------------------------------------------------------------------
 def algorithmic_bytes(n_reads, L, k, sampled_ins, trusted_ins):
     """bytes each pass must move for a batch of n_reads fixed-length reads.  Per kernel, a pass's bytes
@@ -262,6 +341,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--genome", type=int, default=GENOME, help="per-GPU genome length (default: config 3's 64 Mb)")
     ap.add_argument("--coverage", type=int, default=COVERAGE, help="coverage (default: config 3's 30; config 2: --genome 4600000 --coverage 50)")
+    ap.add_argument("--no-file-leg", action="store_true", help="skip e2e_file (the CLI, file to file, on a config-2-sized FASTQ)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (human-scale shards: 20 GB of pinned memory per rank)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -279,6 +359,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least three untimed steps
+    numa_node = bind_to_gpu_numa(local) if world > 1 else None
     torch.cuda.set_device(local)
     os.environ.setdefault("KBBQ_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))  # the model fit's threads: ranks share the host
     comm = None
@@ -445,6 +526,13 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_run(genomelen, args.coverage, with_all_cores=(world == 1))
 
+    e2e_file = None
+    if rank == 0 and world == 1 and not args.no_file_leg:
+        try:
+            e2e_file = file_to_file_leg()
+        except Exception as e:  # the file leg must never cost the bench line
+            e2e_file = {"unavailable": repr(e)}
+
     if rank == 0:
         cfg = config_dict(world, args.genome, args.coverage)
         print(json.dumps({
@@ -453,11 +541,13 @@ def main():
             "dtype": "u64/u8 integer (long double model fit on host)", "data": "synthetic",
             "config": cfg,
             "e2e": e2e,
+            "e2e_file": e2e_file,
             "gpu_launches": int(launches),
             "clocks": clock_info,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "self_check": {"passed": True, **checks, "digest": digest},
+            "numa_node_rank0": numa_node,
             "breakdown_ms": {"passes": pass_ms, "kernels": kernel_ms, "helper_kernels": helpers, "host": host_ms, "merge": merge_ms,
                              "merge_kernel_or_allreduce_p2p": merge_kernel_ms},
         }))
