@@ -368,6 +368,8 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the one JSON line
+        if os.environ.get("KBBQ_MERGE", "nvls") == "nvls":
+            os.environ.setdefault("KBBQ_FILTER_VMM", "1")  # filters as shareable VMM memory: the switch can OR them (dist.py)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         comm = GpuComm(rank, world, local)
 
@@ -489,7 +491,8 @@ def main():
     # per-rank insert counts for the byte model: merged counters / world is the per-rank average
     ab = algorithmic_bytes(n_reads, READ_LEN, K, sampled_ins // world, trusted_ins // world)
     kernel_ms = {kn: float(np.mean([s.kernel_ms[kn] for s in stats])) for kn in stats[0].kernel_ms}
-    merge_kernel_ms = kernel_ms.pop("or_allreduce_p2p_kernel", None)  # two launches per step (N>1); reported with the merges
+    # the merge kernels: two launches per step (N>1); reported with the merges
+    merge_kernel_ms = kernel_ms.pop("or_allreduce_p2p_kernel", None) or kernel_ms.pop("or_allreduce_mc_kernel", None)
     # helper kernels of the staged inserts (HBM-sized filters) apply what pass 1b / pass 2 staged: their time is in the
     # pass totals; they have no algorithmic bytes of their own
     helpers = {kn: kernel_ms.pop(kn) for kn in list(kernel_ms) if kn not in ab}
@@ -548,6 +551,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "self_check": {"passed": True, **checks, "digest": digest},
             "numa_node_rank0": numa_node,
+            "filter_merge": None if comm is None else comm.last_merge,
             "breakdown_ms": {"passes": pass_ms, "kernels": kernel_ms, "helper_kernels": helpers, "host": host_ms, "merge": merge_ms,
                              "merge_kernel_or_allreduce_p2p": merge_kernel_ms},
         }))

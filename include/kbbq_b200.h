@@ -177,6 +177,24 @@ int kbbq_bloom_load(kbbq_ctx* ctx, int which, const char* path);
 int kbbq_bloom_ipc_handle(kbbq_ctx* ctx, int which, void* handle64);
 int kbbq_bloom_or_allreduce_p2p(kbbq_ctx* ctx, int which, int rank, int world, const void* handles);
 
+/* The merge through NVSwitch multicast (NVLS): the switch ORs the N copies of a word (`multimem.ld_reduce.or`) and
+ * writes the result to all N (`multimem.st`), so 1/N of the array arrives at and leaves each GPU instead of (N-1)/N.
+ * The filters must have been created as shareable virtual-memory-API memory (environment KBBQ_FILTER_VMM=1 at
+ * kbbq_bloom_create; they then cannot be exported with kbbq_bloom_ipc_handle).  One process per GPU:
+ *   rank 0:       kbbq_bloom_mc_create -> a POSIX file descriptor; hand it to the other ranks (SCM_RIGHTS over a Unix socket)
+ *   other ranks:  kbbq_bloom_mc_import(fd)
+ *   every rank:   kbbq_bloom_mc_add_device; barrier (binding blocks until every device has been added);
+ *                 kbbq_bloom_mc_bind; barrier
+ *   per merge:    kbbq_sync + barrier, kbbq_bloom_or_allreduce_mc, kbbq_sync + barrier, counters summed as before
+ * kbbq_bloom_mc_supported: 1 when the filter is VMM memory and the device reports multicast support.  Every call fails
+ * soft (KBBQ_ECUDA / KBBQ_ESTATE with a message); dist.py falls back to the all-gather merge when any rank fails. */
+int kbbq_bloom_mc_supported(kbbq_ctx* ctx, int which);
+int kbbq_bloom_mc_create(kbbq_ctx* ctx, int which, int world, int* fd_out);
+int kbbq_bloom_mc_import(kbbq_ctx* ctx, int which, int world, int fd);
+int kbbq_bloom_mc_add_device(kbbq_ctx* ctx, int which);
+int kbbq_bloom_mc_bind(kbbq_ctx* ctx, int which);
+int kbbq_bloom_or_allreduce_mc(kbbq_ctx* ctx, int which, int rank, int world);
+
 /* The same merge for several contexts of ONE process (a host that drives several GPUs itself): peer access instead of
  * IPC handles, every rank's kernel launched from this one call, the insert counters summed; synchronises every
  * context's stream before and after.  KBBQ_ECUDA when two of the devices cannot map each other's memory. */

@@ -104,6 +104,12 @@ def lib():
         L.kbbq_bloom_load.argtypes = [vp, i32, C.c_char_p]
         L.kbbq_bloom_ipc_handle.argtypes = [vp, i32, vp]
         L.kbbq_bloom_or_allreduce_p2p.argtypes = [vp, i32, i32, i32, vp]
+        L.kbbq_bloom_mc_supported.argtypes = [vp, i32]
+        L.kbbq_bloom_mc_create.argtypes = [vp, i32, i32, C.POINTER(i32)]
+        L.kbbq_bloom_mc_import.argtypes = [vp, i32, i32, i32]
+        L.kbbq_bloom_mc_add_device.argtypes = [vp, i32]
+        L.kbbq_bloom_mc_bind.argtypes = [vp, i32]
+        L.kbbq_bloom_or_allreduce_mc.argtypes = [vp, i32, i32, i32]
         L.kbbq_batch_upload.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
         L.kbbq_batch_upload_async.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
         L.kbbq_batch_upload_stream.argtypes = [vp, C.POINTER(_Batch), C.POINTER(vp)]
@@ -483,6 +489,27 @@ class Context:
         handles = np.ascontiguousarray(handles, dtype=np.uint8)
         assert handles.shape == (world, 64)
         _check(self.L.kbbq_bloom_or_allreduce_p2p(self.h, which, rank, world, _p(handles)))
+
+    # the merge through NVSwitch multicast (kbbq_nvls.cuh); every step fails soft with KbbqError
+    def bloom_mc_supported(self, which: int) -> bool:
+        return bool(self.L.kbbq_bloom_mc_supported(self.h, which))
+
+    def bloom_mc_create(self, which: int, world: int) -> int:
+        fd = C.c_int(-1)
+        _check(self.L.kbbq_bloom_mc_create(self.h, which, world, C.byref(fd)))
+        return int(fd.value)
+
+    def bloom_mc_import(self, which: int, world: int, fd: int):
+        _check(self.L.kbbq_bloom_mc_import(self.h, which, world, fd))
+
+    def bloom_mc_add_device(self, which: int):
+        _check(self.L.kbbq_bloom_mc_add_device(self.h, which))
+
+    def bloom_mc_bind(self, which: int):
+        _check(self.L.kbbq_bloom_mc_bind(self.h, which))
+
+    def bloom_or_allreduce_mc(self, which: int, rank: int, world: int):
+        _check(self.L.kbbq_bloom_or_allreduce_mc(self.h, which, rank, world))
 
     # batches
     def upload(self, pb: PackedBatch) -> "DeviceBatch":

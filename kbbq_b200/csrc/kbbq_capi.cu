@@ -20,6 +20,7 @@
 #include "kbbq_host.h"
 #include "kbbq_kernels.cuh"
 #include "kbbq_synth.cuh"
+#include "kbbq_nvls.cuh"
 
 using namespace kbbq;
 
@@ -54,6 +55,15 @@ struct Filter {
     unsigned long long* d_words = nullptr;
     unsigned long long* d_patterns = nullptr;
     unsigned long long* d_inserted = nullptr;
+    // KBBQ_FILTER_VMM=1: the bit array is virtual-memory-API memory (shareable: it can be bound to a multicast object)
+    bool vmm = false;
+    CUmemGenericAllocationHandle mem = 0;
+    size_t vmm_bytes = 0;
+    // NVSwitch multicast (kbbq_nvls.cuh): the object, what this rank did with it, and its mapping
+    CUmemGenericAllocationHandle mc = 0;
+    bool mc_have = false, mc_added = false, mc_bound = false;
+    unsigned long long* mc_ptr = nullptr;
+    int mc_world = 0;
     // peer mappings of the other ranks' bit arrays (kbbq_bloom_or_allreduce_p2p), opened once per filter
     void* peer[KBBQ_MAX_PEERS] = {};
     int peer_world = 0, peer_rank = -1;
@@ -77,6 +87,65 @@ struct Filter {
     }
 };
 
+}  // namespace
+
+namespace {
+// give back a filter's bit array and whatever multicast state hangs on it
+void filter_release(int device, Filter& f) {
+    const nvls::Driver& d = nvls::driver();
+    f.close_peers();
+    if (f.mc_ptr && d.ok) {
+        d.MemUnmap((CUdeviceptr)f.mc_ptr, f.vmm_bytes);
+        d.MemAddressFree((CUdeviceptr)f.mc_ptr, f.vmm_bytes);
+    }
+    if (f.mc_bound && d.ok) {
+        CUdevice dev;
+        if (d.DeviceGet(&dev, device) == CUDA_SUCCESS) d.MulticastUnbind(f.mc, dev, 0, f.vmm_bytes);
+    }
+    if (f.mc_have && d.ok) d.MemRelease(f.mc);
+    if (f.vmm && d.ok) {
+        d.MemUnmap((CUdeviceptr)f.d_words, f.vmm_bytes);
+        d.MemAddressFree((CUdeviceptr)f.d_words, f.vmm_bytes);
+        d.MemRelease(f.mem);
+    } else {
+        cudaFree(f.d_words);
+    }
+    cudaFree(f.d_inserted);
+    f = Filter();
+}
+// the bit array as shareable virtual-memory-API memory; false (with a reason) when that is not to be had
+bool filter_alloc_vmm(int device, size_t bytes, Filter& f, std::string& why) {
+    const nvls::Driver& d = nvls::driver();
+    size_t padded = 0;
+    if (!nvls::padded_size(device, bytes, padded, why)) return false;
+    const CUmemAllocationProp prop = nvls::alloc_prop(device);
+    CUmemGenericAllocationHandle h = 0;
+    CUresult r = d.MemCreate(&h, padded, &prop, 0);
+    if (r != CUDA_SUCCESS) { why = nvls::cu_error("cuMemCreate", r); return false; }
+    CUdeviceptr va = 0;
+    r = d.MemAddressReserve(&va, padded, 0, 0, 0);
+    if (r != CUDA_SUCCESS) { d.MemRelease(h); why = nvls::cu_error("cuMemAddressReserve", r); return false; }
+    r = d.MemMap(va, padded, 0, h, 0);
+    if (r == CUDA_SUCCESS) {
+        CUmemAccessDesc acc = {};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = d.MemSetAccess(va, padded, &acc, 1);
+        if (r != CUDA_SUCCESS) d.MemUnmap(va, padded);
+    }
+    if (r != CUDA_SUCCESS) {
+        d.MemAddressFree(va, padded);
+        d.MemRelease(h);
+        why = nvls::cu_error("cuMemMap / cuMemSetAccess", r);
+        return false;
+    }
+    f.vmm = true;
+    f.mem = h;
+    f.vmm_bytes = padded;
+    f.d_words = reinterpret_cast<unsigned long long*>(va);
+    return true;
+}
 }  // namespace
 
 #define KBBQ_MAX_PASS_KERNELS 4
@@ -699,11 +768,7 @@ void kbbq_ctx_destroy(kbbq_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& f : c->filt) {
-        f.close_peers();
-        cudaFree(f.d_words);
-        cudaFree(f.d_inserted);
-    }
+    for (auto& f : c->filt) filter_release(c->device, f);
     cudaFree(c->d_jump);
     cudaFree(c->d_lane_jump);
     cudaFree(c->d_thresholds);
@@ -767,14 +832,18 @@ int kbbq_bloom_create(kbbq_ctx* ctx, int which, uint64_t projected, double fpr, 
     Filter& f = ctx->filt[which];
     if (f.exists) {
         CU(cudaStreamSynchronize(ctx->stream));
-        f.close_peers();
-        cudaFree(f.d_words);
-        cudaFree(f.d_inserted);
-        f = Filter();
+        filter_release(ctx->device, f);
     }
     ++ctx->epoch[which];
     f.geom = g;
-    CU(cudaMalloc(&f.d_words, g.table_bits / 8));
+    size_t table_alloc = g.table_bits / 8;
+    if (getenv("KBBQ_FILTER_VMM")) {  // shareable virtual-memory-API memory, so that the array can join a multicast object
+        std::string why;
+        if (filter_alloc_vmm(ctx->device, g.table_bits / 8, f, why)) table_alloc = f.vmm_bytes;
+        else if (getenv("KBBQ_NVLS_VERBOSE")) fprintf(stderr, "[kbbq_b200] filter %d stays cudaMalloc memory: %s\n", which, why.c_str());
+    }
+    if (!f.vmm) CU(cudaMalloc(&f.d_words, g.table_bits / 8));
+    if (table_alloc > g.table_bits / 8) CU(cudaMemsetAsync((char*)f.d_words + g.table_bits / 8, 0, table_alloc - g.table_bits / 8, ctx->stream));
     f.d_patterns = ctx->d_pattern_pool + (size_t)which * KBBQ_NUM_PATTERNS * 8;
     CU(cudaMalloc(&f.d_inserted, 8));
     CU(cudaMemsetAsync(f.d_words, 0, g.table_bits / 8, ctx->stream));
@@ -1053,6 +1122,112 @@ int kbbq_bloom_or_allreduce_p2p(kbbq_ctx* ctx, int which, int rank, int world, c
     default: or_allreduce_p2p_kernel<0><<<grid, 256, 0, ctx->stream>>>(pp, rank, world, n2); break;
     }
     if (int rc = check_launch(ctx, "or_allreduce_p2p_kernel")) return rc;
+    pass_end(ctx);
+    return KBBQ_OK;
+}
+
+// ---- the merge through NVSwitch multicast (kbbq_nvls.cuh) -------------------------------------------------------------
+int kbbq_bloom_mc_supported(kbbq_ctx* ctx, int which) {
+    if (!ctx || (which != 0 && which != 1) || !ctx->filt[which].exists || !ctx->filt[which].vmm) return 0;
+    const nvls::Driver& d = nvls::driver();
+    if (!d.ok || cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+    CUdevice dev;
+    int yes = 0;
+    if (d.DeviceGet(&dev, ctx->device) != CUDA_SUCCESS || d.DeviceGetAttribute(&yes, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) != CUDA_SUCCESS) return 0;
+    return yes ? 1 : 0;
+}
+
+int kbbq_bloom_mc_create(kbbq_ctx* ctx, int which, int world, int* fd_out) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    if (!fd_out || world < 2) return fail(KBBQ_EINVAL, "bad argument");
+    Filter& f = ctx->filt[which];
+    if (!f.vmm) return fail(KBBQ_ESTATE, "the filter was not created as virtual-memory-API memory (KBBQ_FILTER_VMM=1)");
+    if (f.mc_have) return fail(KBBQ_ESTATE, "the filter already has a multicast object");
+    const nvls::Driver& d = nvls::driver();
+    CUmulticastObjectProp prop = {};
+    prop.numDevices = (unsigned)world;
+    prop.size = f.vmm_bytes;
+    prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    CUresult r = d.MulticastCreate(&f.mc, &prop);
+    if (r != CUDA_SUCCESS) return fail(KBBQ_ECUDA, nvls::cu_error("cuMulticastCreate", r));
+    f.mc_have = true;
+    f.mc_world = world;
+    int fd = -1;
+    r = d.MemExportToShareableHandle(&fd, f.mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (r != CUDA_SUCCESS) return fail(KBBQ_ECUDA, nvls::cu_error("cuMemExportToShareableHandle", r));
+    *fd_out = fd;
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_mc_import(kbbq_ctx* ctx, int which, int world, int fd) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    if (!f.vmm) return fail(KBBQ_ESTATE, "the filter was not created as virtual-memory-API memory (KBBQ_FILTER_VMM=1)");
+    if (f.mc_have) return fail(KBBQ_ESTATE, "the filter already has a multicast object");
+    CUresult r = nvls::driver().MemImportFromShareableHandle(&f.mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    if (r != CUDA_SUCCESS) return fail(KBBQ_ECUDA, nvls::cu_error("cuMemImportFromShareableHandle", r));
+    f.mc_have = true;
+    f.mc_world = world;
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_mc_add_device(kbbq_ctx* ctx, int which) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    if (!f.mc_have) return fail(KBBQ_ESTATE, "no multicast object");
+    const nvls::Driver& d = nvls::driver();
+    CUdevice dev;
+    CUresult r = d.DeviceGet(&dev, ctx->device);
+    if (r == CUDA_SUCCESS) r = d.MulticastAddDevice(f.mc, dev);
+    if (r != CUDA_SUCCESS) return fail(KBBQ_ECUDA, nvls::cu_error("cuMulticastAddDevice", r));
+    f.mc_added = true;
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_mc_bind(kbbq_ctx* ctx, int which) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    if (!f.mc_added) return fail(KBBQ_ESTATE, "this rank's device has not been added to the multicast object");
+    const nvls::Driver& d = nvls::driver();
+    CUresult r = d.MulticastBindMem(f.mc, 0, f.mem, 0, f.vmm_bytes, 0);
+    if (r != CUDA_SUCCESS) return fail(KBBQ_ECUDA, nvls::cu_error("cuMulticastBindMem", r));
+    f.mc_bound = true;
+    CUdeviceptr va = 0;
+    r = d.MemAddressReserve(&va, f.vmm_bytes, 0, 0, 0);
+    if (r != CUDA_SUCCESS) return fail(KBBQ_ECUDA, nvls::cu_error("cuMemAddressReserve (multicast)", r));
+    r = d.MemMap(va, f.vmm_bytes, 0, f.mc, 0);
+    if (r == CUDA_SUCCESS) {
+        CUmemAccessDesc acc = {};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = ctx->device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = d.MemSetAccess(va, f.vmm_bytes, &acc, 1);
+        if (r != CUDA_SUCCESS) d.MemUnmap(va, f.vmm_bytes);
+    }
+    if (r != CUDA_SUCCESS) {
+        d.MemAddressFree(va, f.vmm_bytes);
+        return fail(KBBQ_ECUDA, nvls::cu_error("cuMemMap / cuMemSetAccess (multicast)", r));
+    }
+    f.mc_ptr = reinterpret_cast<unsigned long long*>(va);
+    return KBBQ_OK;
+}
+
+int kbbq_bloom_or_allreduce_mc(kbbq_ctx* ctx, int which, int rank, int world) {
+    if (int rc = use(ctx)) return rc;
+    if (int rc = filter_ok(ctx, which)) return rc;
+    Filter& f = ctx->filt[which];
+    if (!f.mc_ptr || world != f.mc_world || rank < 0 || rank >= world) return fail(KBBQ_ESTATE, "the multicast mapping is not set up for this world");
+    const unsigned long long n_words = f.geom.table_bits / 64;
+    const unsigned long long per = (n_words + world - 1) / world;
+    const int grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((per + 255) / 256, (unsigned long long)ctx->sm_count * 16));
+    pass_begin(ctx);
+    mark_kernel(ctx, "or_allreduce_mc_kernel");
+    nvls::or_allreduce_mc_kernel<<<grid, 256, 0, ctx->stream>>>(f.mc_ptr, rank, world, n_words);
+    if (int rc = check_launch(ctx, "or_allreduce_mc_kernel")) return rc;
     pass_end(ctx);
     return KBBQ_OK;
 }

@@ -3,7 +3,9 @@
 One process per GPU; `torch.distributed` is the plumbing.  The path has exactly three exchange steps:
   after pass 1 and pass 2 -- bitwise OR of the Bloom bit arrays and SUM of the insert counters,
   after pass 3          -- SUM of the covariate count tables.
-NCCL has no bitwise-OR reduction, so the OR is this repo's own: on one NVLink/NVSwitch box, ONE kernel per rank over
+NCCL has no bitwise-OR reduction, so the OR is this repo's own.  Where the filters are shareable virtual-memory-API
+memory (KBBQ_FILTER_VMM=1) and the devices support NVSwitch multicast, the switch does it (`kbbq_bloom_or_allreduce_mc`:
+`multimem.ld_reduce.or` + `multimem.st`, 1/N of the array per GPU on the wire).  Otherwise, on one NVLink/NVSwitch box, ONE kernel per rank over
 peer-mapped memory (`kbbq_bloom_or_allreduce_p2p`: rank r ORs slice r of every rank's bit array and writes the result
 into every rank's array -- reduce-scatter and all-gather fused, no staging, 2(N-1)/N of the array per GPU on the
 wire); where peer mapping is not available (KBBQ_MERGE=allgather, or the mapping fails) the fallback all-gathers
@@ -35,6 +37,7 @@ def device_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
 class Comm:
     def __init__(self, rank: int, world: int):
         self.rank, self.world = rank, world
+        self.last_merge = None  # which transport merged the most recent filter: "nvls", "p2p" or "allgather"
 
     # ---- scalars -------------------------------------------------------------------------------------------------
     def exclusive_prefix(self, x: int, device=None) -> int:
@@ -85,11 +88,100 @@ class Comm:
         key = (id(ctx), which, ctx.bloom_device_words(which))
         cache = self.__dict__.setdefault("_handles", {})
         if key not in cache:
-            mine = torch.from_numpy(ctx.bloom_ipc_handle(which)).to(f"cuda:{ctx.device}")
+            try:
+                h = ctx.bloom_ipc_handle(which)
+                ok = 1
+            except api.KbbqError:  # virtual-memory-API filters (KBBQ_FILTER_VMM) have no IPC handle
+                h, ok = np.zeros(64, dtype=np.uint8), 0
+            if self.sum_int(ok) != self.world:
+                cache[key] = None
+                return None
+            mine = torch.from_numpy(h).to(f"cuda:{ctx.device}")
             allh = torch.empty(self.world * 64, dtype=torch.uint8, device=mine.device)
             dist.all_gather_into_tensor(allh, mine)
             cache[key] = allh.cpu().numpy().reshape(self.world, 64)
         return cache[key]
+
+    # ---- NVSwitch multicast (NVLS): the switch ORs the copies -------------------------------------------------------------
+    def _agree(self, ok: bool) -> bool:
+        """every rank succeeded (one all-reduce; also a barrier)"""
+        return self.sum_int(1 if ok else 0) == self.world
+
+    def _mc_ready(self, ctx: api.Context, which: int) -> bool:
+        """Set the multicast object of this filter up once: rank 0 creates it and hands its file descriptor to the other
+        ranks over a Unix socket, every rank adds its device, then binds its copy and maps the object.  Every stage is
+        agreed on by all ranks before the next one starts (binding blocks until every device has been added), and any
+        failure anywhere makes every rank fall back to another merge for good."""
+        import os
+        import socket
+
+        if os.environ.get("KBBQ_MERGE", "nvls") != "nvls" or not isinstance(self, GpuComm):
+            return False
+        state = self.__dict__.setdefault("_mc", {})
+        key = (id(ctx), which, ctx.bloom_device_words(which))
+        if key in state:
+            return state[key]
+        state[key] = False
+        if not self._agree(ctx.bloom_mc_supported(which)):
+            return False
+        path = "/tmp/kbbq_mc_%s_%d_%d.sock" % (os.environ.get("MASTER_PORT", "0"), which, len(state))
+        ok, srv, fd = True, None, -1
+        try:  # stage 1: the object and its descriptor
+            if self.rank == 0:
+                fd = ctx.bloom_mc_create(which, self.world)
+                if os.path.exists(path):
+                    os.unlink(path)
+                srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                srv.bind(path)
+                srv.listen(self.world)
+                srv.settimeout(60)
+        except Exception as e:
+            print(f"[rank {self.rank}] multicast object: {e}", flush=True)
+            ok = False
+        if not self._agree(ok):
+            if srv is not None:
+                srv.close()
+            return False
+        try:  # stage 2: the descriptor travels (SCM_RIGHTS), the other ranks import it
+            if self.rank == 0:
+                for _ in range(self.world - 1):
+                    conn, _ = srv.accept()
+                    socket.send_fds(conn, [b"mc"], [fd])
+                    conn.close()
+            else:
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.settimeout(60)
+                c.connect(path)
+                _, fds, _, _ = socket.recv_fds(c, 16, 1)
+                c.close()
+                ctx.bloom_mc_import(which, self.world, fds[0])
+                os.close(fds[0])
+        except Exception as e:
+            print(f"[rank {self.rank}] multicast descriptor: {e}", flush=True)
+            ok = False
+        finally:
+            if srv is not None:
+                srv.close()
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+        if not self._agree(ok):
+            return False
+        try:  # stage 3: every device joins
+            ctx.bloom_mc_add_device(which)
+        except api.KbbqError as e:
+            print(f"[rank {self.rank}] multicast add device: {e}", flush=True)
+            ok = False
+        if not self._agree(ok):
+            return False
+        try:  # stage 4: bind this rank's copy, map the object
+            ctx.bloom_mc_bind(which)
+        except api.KbbqError as e:
+            print(f"[rank {self.rank}] multicast bind: {e}", flush=True)
+            ok = False
+        state[key] = self._agree(ok)
+        return state[key]
 
     def merge_filter(self, ctx: api.Context, which: int) -> None:
         if self.world == 1:
@@ -97,6 +189,15 @@ class Comm:
         g = ctx.bloom_info(which)
         nbytes = g.table_bits // 8
         counter = device_tensor(ctx.bloom_device_counter(which), 8, ctx.device).view(torch.int64)
+        if self._mc_ready(ctx, which):
+            ctx.sync()          # this rank's inserts are in memory ...
+            self.barrier()      # ... and so are everybody else's
+            ctx.bloom_or_allreduce_mc(which, self.rank, self.world)
+            ctx.sync()
+            self.sum_reduce_(counter)  # doubles as the barrier after: every slice is written everywhere
+            torch.cuda.current_stream().synchronize()
+            self.last_merge = "nvls"
+            return
         handles = self._p2p_handles(ctx, which)
         if handles is not None and not self.__dict__.get("_p2p_broken"):
             ctx.sync()          # this rank's inserts are in memory ...
@@ -111,6 +212,7 @@ class Comm:
             if self.min_int(ok) == 1:   # doubles as the barrier after: every slice is written everywhere
                 self.sum_reduce_(counter)
                 torch.cuda.current_stream().synchronize()
+                self.last_merge = "p2p"
                 return
             self._p2p_broken = True
         ctx.sync()  # the library works on its own stream
@@ -125,6 +227,7 @@ class Comm:
         self.or_reduce_(words, or_kernel)
         self.sum_reduce_(counter)
         torch.cuda.current_stream().synchronize()
+        self.last_merge = "allgather"
 
     def merge_counts(self, ctx: api.Context) -> None:
         if self.world == 1:

@@ -152,7 +152,7 @@ class Recalibrator:
     def _note_merge_kernel(self, st: RunStats) -> None:
         """device time of the peer-memory merge kernel, when that is what merged the filter (it is timed like a pass)"""
         for kn, kms in self.ctx.last_pass_kernels().items():
-            if kn == "or_allreduce_p2p_kernel":
+            if kn in ("or_allreduce_p2p_kernel", "or_allreduce_mc_kernel"):
                 st.kernel_ms[kn] = st.kernel_ms.get(kn, 0.0) + kms
 
     def close(self):

@@ -26,7 +26,8 @@ def main():
     rs = synth.make_reads(G, cov, L, seed=41, n_rg=2, ragged=True, min_len=80, n_frac=0.002)
     b = shard_bounds(rs.n, world)
     mine = rs.subset(int(b[rank]), int(b[rank + 1]))
-    rc = Recalibrator(k, rs.n_rg, L, G, cov, seed, device=local, comm=GpuComm(rank, world, local))
+    comm = GpuComm(rank, world, local)
+    rc = Recalibrator(k, rs.n_rg, L, G, cov, seed, device=local, comm=comm)
     pb = api.PackedBatch(mine)
     rc.add_batch(pb)
     rc.run(fetch_quals=True, want_errors=True)
@@ -56,7 +57,7 @@ def main():
     t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("MGPU PARITY", "OK" if int(t.item()) == 1 else "FAILED", f"world={world} reads={rs.n}", flush=True)
+        print("MGPU PARITY", "OK" if int(t.item()) == 1 else "FAILED", f"world={world} reads={rs.n} merge={comm.last_merge}", flush=True)
     rc.close()
     dist.destroy_process_group()
     sys.exit(0 if int(t.item()) == 1 else 1)

@@ -17,15 +17,18 @@ def _gpus() -> int:
     return api.lib().kbbq_device_count()
 
 
-@pytest.mark.parametrize("merge", ["p2p", "allgather"])
+@pytest.mark.parametrize("merge", ["nvls", "p2p", "allgather"])
 def test_sharded_run_matches_the_oracle_on_every_rank(merge):
     n = _gpus()
     if n < 2:
         pytest.skip("needs at least two GPUs on the box")
     world = 2 if n < 4 else 4
     env = dict(os.environ, KBBQ_MERGE=merge, MASTER_ADDR="127.0.0.1")
+    if merge == "nvls":  # the switch ORs the copies: filters as shareable VMM memory (falls back by itself where unsupported)
+        env["KBBQ_FILTER_VMM"] = "1"
+        env["KBBQ_NVLS_VERBOSE"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29517" if merge == "p2p" else "29518", os.path.join(ROOT, "tests", "mgpu_check.py")]
+           "--master-port", {"p2p": "29517", "allgather": "29518", "nvls": "29519"}[merge], os.path.join(ROOT, "tests", "mgpu_check.py")]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     log = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(log):
