@@ -368,8 +368,10 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the one JSON line
-        if os.environ.get("KBBQ_MERGE", "nvls") == "nvls":
-            os.environ.setdefault("KBBQ_FILTER_VMM", "1")  # filters as shareable VMM memory: the switch can OR them (dist.py)
+        # From four GPUs on the filters are merged by the switch (NVLS: 1 + 1/N of the array per GPU and direction against
+        # 2(N-1)/N for the peer-memory kernel; at N=2 the peer-memory kernel moves less): they must then be shareable VMM memory.
+        if os.environ.get("KBBQ_MERGE", "nvls") == "nvls" and world >= 4:
+            os.environ.setdefault("KBBQ_FILTER_VMM", "1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         comm = GpuComm(rank, world, local)
 

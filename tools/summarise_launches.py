@@ -15,7 +15,7 @@ def short(name):
     name = re.sub(r"^void ", "", name)
     name = re.sub(r"\(.*$", "", name)
     name = re.sub(r"^kbbq::", "", name)
-    return re.sub(r"<.*$", "", name) if name.startswith("cub::") else name
+    return re.sub(r"<.*$", "", name)
 
 
 def main():
