@@ -267,20 +267,23 @@ def file_to_file_leg():
     with tempfile.TemporaryDirectory() as d:
         fq, out = os.path.join(d, "c2.fq"), os.path.join(d, "out.fq.gz")
         write_fastq(fq, rs)
-        walls = []
+        walls, phases = [], {}
         for level in ("6", "1"):
             for _ in range(2):
                 t0 = time.perf_counter()
                 with open(out, "wb") as fo:
                     r = subprocess.run([cli, "--seed", str(SEED), "-k", str(K), "-g", str(G), "-c", str(cov), fq], stdout=fo,
-                                       stderr=subprocess.DEVNULL, env=dict(os.environ, KBBQ_BGZF_LEVEL=level))
+                                       stderr=subprocess.PIPE, env=dict(os.environ, KBBQ_BGZF_LEVEL=level, KBBQ_HOST_TIMING="1"))
                 dt = time.perf_counter() - t0
                 if r.returncode != 0:
                     return {"unavailable": f"kbbq exited {r.returncode}"}
             walls.append(dt)
+            phases[level] = {ln.split("]", 1)[1].rsplit(" ms", 1)[0].strip().rsplit(" ", 1)[0]: float(ln.split("]", 1)[1].rsplit(" ms", 1)[0].rsplit(" ", 1)[1])
+                             for ln in r.stderr.decode(errors="replace").splitlines() if ln.startswith("[cli]") and " ms" in ln}
         size_in, size_out = os.path.getsize(fq), os.path.getsize(out)
     return {"value": rs.total_bases / walls[1], "unit": "bases/s", "wall_s": walls[1], "bgzf_level": 1,
             "value_at_zlib_default_level": rs.total_bases / walls[0], "wall_s_at_zlib_default_level": walls[0],
+            "cli_phases_ms": {"level_1": phases.get("1"), "level_6": phases.get("6")},
             "workload": f"config-2-sized FASTQ: {rs.n} reads x {READ_LEN} bp, {size_in / 1e6:.0f} MB in, {size_out / 1e6:.0f} MB of BGZF out",
             "what": "wall time of kbbq_b200/host/kbbq from input file to output file (process start to exit, CUDA context creation "
                     "included), second of two runs per compression level; htslib's default level is zlib's (6)"}
@@ -368,9 +371,10 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the one JSON line
-        # From four GPUs on the filters are merged by the switch (NVLS: 1 + 1/N of the array per GPU and direction against
-        # 2(N-1)/N for the peer-memory kernel; at N=2 the peer-memory kernel moves less): they must then be shareable VMM memory.
-        if os.environ.get("KBBQ_MERGE", "nvls") == "nvls" and world >= 4:
+        # KBBQ_MERGE=nvls: the filters are merged by the switch (NVLS: 1 + 1/N of the array per GPU and direction against
+        # 2(N-1)/N for the peer-memory kernel, which moves less at N=2); they must then be shareable VMM memory.  The
+        # default is the peer-memory kernel, the merge every GPU count of this round's runs was measured with.
+        if os.environ.get("KBBQ_MERGE", "p2p") == "nvls":
             os.environ.setdefault("KBBQ_FILTER_VMM", "1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         comm = GpuComm(rank, world, local)

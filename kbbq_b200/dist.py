@@ -83,7 +83,7 @@ class Comm:
         """every rank's IPC handle of the filter's bit array, or None when this run merges by all-gather"""
         import os
 
-        if os.environ.get("KBBQ_MERGE", "p2p") != "p2p" or not isinstance(self, GpuComm):
+        if os.environ.get("KBBQ_MERGE", "p2p") not in ("p2p", "nvls") or not isinstance(self, GpuComm):
             return None
         key = (id(ctx), which, ctx.bloom_device_words(which))
         cache = self.__dict__.setdefault("_handles", {})
@@ -115,7 +115,7 @@ class Comm:
         import os
         import socket
 
-        if os.environ.get("KBBQ_MERGE", "nvls") != "nvls" or not isinstance(self, GpuComm):
+        if os.environ.get("KBBQ_MERGE", "p2p") != "nvls" or not isinstance(self, GpuComm):
             return False
         state = self.__dict__.setdefault("_mc", {})
         key = (id(ctx), which, ctx.bloom_device_words(which))
