@@ -1731,7 +1731,7 @@ int kbbq_consume_errors_n(kbbq_ctx* ctx, const kbbq_dbatch* cb, const uint32_t* 
     }
     pass_end(ctx);
     CU(cudaStreamSynchronize(ctx->stream));  // err_bits is the caller's buffer
-    return KBBQ_OK;
+    return check_quals(ctx);
 }
 
 int kbbq_fixed_errors(kbbq_ctx* ctx, const kbbq_dbatch* cb, const kbbq_dbatch* fixed, uint32_t n_first, uint32_t* err_bits) {

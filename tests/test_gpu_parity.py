@@ -438,3 +438,45 @@ def test_known_present_kmers_change_nothing(monkeypatch):
     pb = api.PackedBatch(rs)
     assert np.array_equal(pb.unpack_bits(bits, rs.total_bases), want.infer_errors(sampled, th))
     rc.close()
+
+
+def test_streamed_upload_gives_the_resident_answer():
+    """kbbq_batch_upload_stream: every array on the side stream, nothing waited for; the passes wait on the device.  Two
+    pinned batches fed that way (pipeline.run(host_batches=...)) must give what the ordinary upload gives."""
+    G, cov, L, k = 80000, 30, 150, 32
+    rs = synth.make_reads(G, cov, L, seed=64, n_rg=2, n_frac=0.002)
+    want = common.run_gpu(rs, k, G, cov, 99, n_batches=2)
+    from kbbq_b200.pipeline import Recalibrator
+    rc = Recalibrator(k, rs.n_rg, L, G, cov, 99)
+    half = rs.n // 2
+    parts = [rs.subset(0, half), rs.subset(half, rs.n)]
+    pbs = [api.PackedBatch(p, pinned=True) for p in parts]
+    rc.run(fetch_quals=True, want_errors=True, host_batches=pbs, timing=False)
+    assert np.array_equal(rc.ctx.bloom_words(0), want["sampled_words"]) and np.array_equal(rc.ctx.bloom_words(1), want["trusted_words"])
+    newq = np.concatenate([pb.unpack_qual(q, p.total_bases) for pb, q, p in zip(pbs, rc.last_quals, parts)])
+    assert np.array_equal(newq, want["newqual"])
+    e3 = np.concatenate([pb.unpack_bits(e, p.total_bases) for pb, e, p in zip(pbs, rc.last_errors3, parts)])
+    assert np.array_equal(e3, want["pass3_errors"])
+    for a, b in zip(rc.ctx.covariates(), (want["rgc"], want["qc"], want["cyc"], want["dic"])):
+        assert np.array_equal(a, b)
+    rc.close()
+
+
+def test_quality_above_93_in_a_hand_filled_batch_is_reported_not_indexed():
+    """kbbq_batch is a public struct: a caller may fill it without kbbq_pack_reads.  A quality above 93 would index the
+    count and model tables out of bounds: the upload flags it on the device, the count and apply kernels skip
+    the base, and the next synchronising call returns KBBQ_ERANGE."""
+    rs = synth.make_reads(20000, 10, 100, seed=7, n_rg=1)
+    pb = api.PackedBatch(rs)
+    pb.qual[5] = 200
+    ctx = api.Context(32, 1, 100)
+    db = ctx.upload(pb)
+    flags = np.zeros(rs.total_bases, dtype=np.uint8)
+    with pytest.raises(api.KbbqError) as e:
+        ctx.consume_errors(db, pb.pack_bits(flags))
+        ctx.sync()
+    assert e.value.code == -5 and "quality above 93" in str(e.value)
+    rgc, qc, cyc, dic = ctx.covariates()
+    assert int(rgc[0, 1]) == rs.total_bases - 1  # every base but the bad one was counted, nothing out of bounds
+    db.free()
+    ctx.close()
