@@ -63,7 +63,7 @@ typedef struct kbbq_batch {
     uint32_t max_len;
     uint64_t n_words;
     const uint64_t* bases;    /* [n_words] */
-    const uint32_t* nmask;    /* [n_words] */
+    const uint32_t* nmask;    /* [n_words]; may be NULL: the batch holds no non-ACGT base */
     const uint8_t* qual;      /* [32*n_words] */
     const uint32_t* word_off; /* [n_reads+1] */
     const uint32_t* len;      /* [n_reads] */

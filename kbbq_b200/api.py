@@ -308,14 +308,22 @@ class PackedBatch:
     def as_struct(self) -> _Batch:
         b = _Batch()
         b.n_reads, b.max_len, b.n_words = self.n_reads, self.max_len, self.n_words
-        b.bases, b.nmask, b.qual = _p(self.bases), _p(self.nmask), _p(self.qual)
+        b.bases, b.nmask, b.qual = _p(self.bases), (_p(self.nmask) if self.has_n else None), _p(self.qual)
         b.word_off, b.len, b.rg, b.second = _p(self.word_off), _p(self.len), _p(self.rg), _p(self.second)
         b.qmask = _p(self.qmask)
         return b
 
     @property
+    def has_n(self) -> bool:
+        """any non-ACGT base in the batch?  A batch without one sends no N masks (kbbq_batch::nmask may be NULL)."""
+        if getattr(self, "_has_n", None) is None:
+            self._has_n = bool(self.nmask[: max(self.n_words, 1)].any())
+        return self._has_n
+
+    @property
     def h2d_bytes(self) -> int:
-        return self.n_words * (8 + 4 + 32 + (8 if self.qmask is not None else 0)) + (self.n_reads + 1) * 4 + self.n_reads * (4 + 2 + 1)
+        return (self.n_words * (8 + (4 if self.has_n else 0) + 32 + (8 if self.qmask is not None else 0)) + (self.n_reads + 1) * 4
+                + self.n_reads * (4 + 2 + 1))
 
     def unpack_bits(self, bits: np.ndarray, total_bases: int) -> np.ndarray:
         """bit masks in word layout -> one byte per base, reads concatenated (the oracle's layout)."""
