@@ -371,11 +371,6 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the one JSON line
-        # KBBQ_MERGE=nvls: the filters are merged by the switch (NVLS: 1 + 1/N of the array per GPU and direction against
-        # 2(N-1)/N for the peer-memory kernel, which moves less at N=2); they must then be shareable VMM memory.  The
-        # default is the peer-memory kernel, the merge every GPU count of this round's runs was measured with.
-        if os.environ.get("KBBQ_MERGE", "p2p") == "nvls":
-            os.environ.setdefault("KBBQ_FILTER_VMM", "1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         comm = GpuComm(rank, world, local)
 

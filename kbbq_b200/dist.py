@@ -39,6 +39,21 @@ class Comm:
         self.rank, self.world = rank, world
         self.last_merge = None  # which transport merged the most recent filter: "nvls", "p2p" or "allgather"
 
+    @property
+    def merge_mode(self) -> str:
+        """KBBQ_MERGE = auto (default) | nvls | p2p | allgather.  auto: through the switch from four GPUs on (1 + 1/N of the
+        array per GPU and direction against the peer-memory kernel's 2(N-1)/N: fewer bytes from N = 4), the peer-memory
+        kernel below.  Whatever is asked for falls back when it is not to be had (nvls -> p2p -> allgather)."""
+        import os
+
+        m = os.environ.get("KBBQ_MERGE", "auto")
+        if m == "auto":
+            m = "nvls" if self.world >= 4 else "p2p"
+        return m
+
+    def wants_nvls(self) -> bool:
+        return self.world > 1 and self.merge_mode == "nvls" and isinstance(self, GpuComm)
+
     # ---- scalars -------------------------------------------------------------------------------------------------
     def exclusive_prefix(self, x: int, device=None) -> int:
         """sum of x over the ranks below this one: the ordinal of this rank's first k-mer slot."""
@@ -83,7 +98,7 @@ class Comm:
         """every rank's IPC handle of the filter's bit array, or None when this run merges by all-gather"""
         import os
 
-        if os.environ.get("KBBQ_MERGE", "p2p") not in ("p2p", "nvls") or not isinstance(self, GpuComm):
+        if self.merge_mode not in ("p2p", "nvls") or not isinstance(self, GpuComm):
             return None
         key = (id(ctx), which, ctx.bloom_device_words(which))
         cache = self.__dict__.setdefault("_handles", {})
@@ -115,14 +130,14 @@ class Comm:
         import os
         import socket
 
-        if os.environ.get("KBBQ_MERGE", "p2p") != "nvls" or not isinstance(self, GpuComm):
+        if not self.wants_nvls():
             return False
         state = self.__dict__.setdefault("_mc", {})
         key = (id(ctx), which, ctx.bloom_device_words(which))
         if key in state:
             return state[key]
         state[key] = False
-        if not self._agree(ctx.bloom_mc_supported(which)):
+        if not self._agree(ctx.bloom_mc_supported(which) and not os.environ.get("KBBQ_NVLS_FAIL")):  # (the variable: tests of the fallback)
             return False
         path = "/tmp/kbbq_mc_%s_%d_%d.sock" % (os.environ.get("MASTER_PORT", "0"), which, len(state))
         ok, srv, fd = True, None, -1
@@ -182,6 +197,10 @@ class Comm:
             ok = False
         state[key] = self._agree(ok)
         return state[key]
+
+    def mc_ready(self, ctx: api.Context, which: int) -> bool:
+        """set the multicast merge of this filter up (collective); False when it is not to be had"""
+        return self._mc_ready(ctx, which)
 
     def merge_filter(self, ctx: api.Context, which: int) -> None:
         if self.world == 1:

@@ -48,8 +48,30 @@ class Recalibrator:
         self.comm = comm
         self.batches: list[api.DeviceBatch] = []
         self.slot_base = 0
-        self.ctx.bloom_create(api.FILTER_SAMPLED, self.approx_kmers, self.SAMPLER_FPR)
-        self.ctx.bloom_create(api.FILTER_TRUSTED, self.approx_kmers, self.TRUSTED_FPR)
+        self._create_filters()
+
+    def _create_filters(self):
+        """The two filters.  When the merges are to go through the NVSwitch (Comm.wants_nvls) they are created as shareable
+        virtual-memory-API memory and their multicast objects are set up right away (collectively); if any rank cannot
+        have that, every rank re-creates them as ordinary device memory, which the peer-memory merge can export."""
+        import os
+
+        want = self.comm is not None and self.comm.wants_nvls()
+        had = os.environ.get("KBBQ_FILTER_VMM")
+        if want:
+            os.environ["KBBQ_FILTER_VMM"] = "1"
+        try:
+            self.ctx.bloom_create(api.FILTER_SAMPLED, self.approx_kmers, self.SAMPLER_FPR)
+            self.ctx.bloom_create(api.FILTER_TRUSTED, self.approx_kmers, self.TRUSTED_FPR)
+        finally:
+            if want and had is None:
+                del os.environ["KBBQ_FILTER_VMM"]
+        if want:
+            ok = self.comm.mc_ready(self.ctx, api.FILTER_SAMPLED)
+            ok = self.comm.mc_ready(self.ctx, api.FILTER_TRUSTED) and ok
+            if not ok:
+                self.ctx.bloom_create(api.FILTER_SAMPLED, self.approx_kmers, self.SAMPLER_FPR)
+                self.ctx.bloom_create(api.FILTER_TRUSTED, self.approx_kmers, self.TRUSTED_FPR)
 
     # ---- data ------------------------------------------------------------------------------------------------------
     def add_batch(self, pb: api.PackedBatch) -> api.DeviceBatch:
