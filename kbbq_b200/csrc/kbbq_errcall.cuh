@@ -141,14 +141,18 @@ struct ErrCaller {
 
     // bases of "ACGT" (or "TGCA") that differ from s[p], packed 2 bits each in test order
     KBBQ_HD uint32_t candidates(const SeqRef& s, int p, bool reverse_order, int& ncand) {
-        uint32_t pack = 0;
-        ncand = 0;
-        KBBQ_NOUNROLL
-        for (int ci = 0; ci < 4; ++ci) {
-            const int c = reverse_order ? 3 - ci : ci;  // bloom.cc:140-141
-            if (!seq_eq(s, p, c)) pack |= (uint32_t)c << (2 * ncand++);
+        // all four bases in test order (bloom.cc:140-141), two bits each: ACGT = 0xE4, TGCA = 0x1B; a real base at p is
+        // cut out of the sequence by closing the gap above it (an N keeps all four)
+        const uint32_t order = reverse_order ? 0x1Bu : 0xE4u;
+        if (seq_is_n(s, p)) {
+            ncand = 4;
+            return order;
         }
-        return pack;
+        const int code = seq_code(s, p);
+        const int at = reverse_order ? 3 - code : code;  // where the read's own base sits in the test order
+        const uint32_t low = order & ((1u << (2 * at)) - 1u);
+        ncand = 3;
+        return low | ((order >> (2 * at + 2)) << (2 * at));
     }
 
     // What the pre-test and the walks over the k-mers containing position p found, remembered between
