@@ -1693,12 +1693,18 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         mark_kernel(ctx, "pass3_scan_kernel");
         const uint32_t* known = b->d_ins_bits && b->ins_epoch == ctx->epoch[KBBQ_FILTER_TRUSTED] && !getenv("KBBQ_NO_KNOWN_BITS") ? b->d_ins_bits : nullptr;
         const int max_kmers = std::max(1, (int)b->max_len - ctx->k + 1);
-        // KBBQ_PREFETCH=1 (measurement; off because it loses, see pass 2)
-        if (ctx->filt[KBBQ_FILTER_TRUSTED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4 && getenv("KBBQ_PREFETCH"))
-            pass3_scan_kernel<true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2), ctx->stream>>>(
+        // A filter beyond the L2: two rounds of probes in flight per warp (DEEP; KBBQ_SCAN_DEEP=0 switches it off).
+        // KBBQ_PREFETCH=1 (measurement; off because it loses, see pass 2).
+        const bool big = ctx->filt[KBBQ_FILTER_TRUSTED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4;
+        const char* deep_env = getenv("KBBQ_SCAN_DEEP");
+        if (big && getenv("KBBQ_PREFETCH"))
+            pass3_scan_kernel<true, false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2), ctx->stream>>>(
+                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
+        else if (deep_env ? atoi(deep_env) != 0 : big)
+            pass3_scan_kernel<false, true><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
         else
-            pass3_scan_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+            pass3_scan_kernel<false, false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
         if (int rc = check_launch(ctx, "pass3_scan_kernel")) return rc;
         mark_kernel(ctx, "pass3_repair_kernel");

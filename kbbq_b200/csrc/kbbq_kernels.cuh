@@ -142,6 +142,46 @@ __device__ __forceinline__ uint32_t coop_probe_impl(const unsigned long long* __
     }
     return result;
 }
+// TWO 32-probe queries at once: the block loads of all 64 probes are issued before anything is consumed, the patterns
+// (L2 hits) follow in two halves.  ncu on the config-3 scan: 14 of 18 cycles per issue are long-scoreboard stalls and
+// the DRAM system is 40 % busy -- the probes are latency bound, what helps is more of them in flight per warp.
+__device__ __forceinline__ void coop_probe_pair(const unsigned long long* __restrict__ words, const unsigned long long* __restrict__ patterns,
+                                                uint64_t blkA, uint32_t patA, uint32_t vmaskA, uint64_t blkB, uint32_t patB, uint32_t vmaskB,
+                                                uint32_t& resA, uint32_t& resB) {
+    const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
+    uint4 x[8];
+    uint32_t pn[8];
+    bool v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int src = 8 * (i & 3) + grp;
+        const uint64_t b = __shfl_sync(KBBQ_FULL, i < 4 ? blkA : blkB, src);
+        pn[i] = __shfl_sync(KBBQ_FULL, i < 4 ? patA : patB, src);
+        v[i] = ((i < 4 ? vmaskA : vmaskB) >> src) & 1u;
+        x[i] = make_uint4(0, 0, 0, 0);
+        if (v[i]) x[i] = __ldg(reinterpret_cast<const uint4*>(words + b * 8) + sub);
+    }
+    uint32_t res[2] = {0, 0};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint4 y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            y[i] = make_uint4(0, 0, 0, 0);
+            if (v[4 * half + i]) y[i] = __ldg(reinterpret_cast<const uint4*>(patterns + (uint64_t)pn[4 * half + i] * 8) + sub);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 xx = x[4 * half + i];
+            const bool ok = v[4 * half + i] && ((~xx.x & y[i].x) | (~xx.y & y[i].y) | (~xx.z & y[i].z) | (~xx.w & y[i].w)) == 0;
+            uint32_t m = __ballot_sync(KBBQ_FULL, ok);
+            m &= (m >> 1) & (m >> 2) & (m >> 3) & 0x11111111u;  // all four quarters of a probe agree
+            res[half] |= gather_nibble_flags(m) << (8 * i);
+        }
+    }
+    resA = res[0];
+    resB = res[1];
+}
 // out-of-line copy for the error-calling kernel, which asks from a dozen places
 __device__ __noinline__ uint32_t coop_probe_call(const unsigned long long* words, const unsigned long long* patterns,
                                                  uint64_t blk, uint32_t pat, uint32_t vmask) {
@@ -831,8 +871,13 @@ covariate_count_kernel(BatchView b, FlatMap fm, CountView cv, const uint32_t* __
 #endif
 // PREFETCH (filters that live in HBM): first hash every k-mer of the read, prefetch its block and park (hash, pattern)
 // in shared memory (8 bytes per k-mer and warp, dynamic); then probe round by round from there.
-template <bool PREFETCH>
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3_MIN_BLOCKS)
+// DEEP (filters that live in HBM): two 32-k-mer rounds per step, all 64 block loads in flight together
+// (coop_probe_pair).
+#ifndef KBBQ_P3D_MIN_BLOCKS
+#define KBBQ_P3D_MIN_BLOCKS 4
+#endif
+template <bool PREFETCH, bool DEEP>
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, DEEP ? KBBQ_P3D_MIN_BLOCKS : KBBQ_P3_MIN_BLOCKS)
 pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
                   uint32_t* __restrict__ mod_out, uint32_t* __restrict__ repair_list, unsigned int* __restrict__ repair_count,
                   const uint32_t* __restrict__ known_bits, int max_kmers) {
@@ -861,11 +906,40 @@ pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ 
                 }
                 __syncwarp();
             }
+            // k-mers pass 2 inserted from this very batch (known_bits, per k-mer in the word layout; given only while
+            // `trusted` has not been cleared since) are present without asking: a third of all k-mers at 30X
+            if (DEEP && !PREFETCH) {
+                for (int j0 = 0; j0 < nk; j0 += 64) {
+                    uint64_t blk[2] = {0, 0};
+                    uint32_t pat[2] = {0, 0}, vm[2], kn[2], m[2];
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int j = j0 + 32 * h2 + lane;
+                        uint64_t key = 0;
+                        const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+                        kn[h2] = known_bits && j0 + 32 * h2 < nk ? __ldg(known_bits + wo + ((j0 + 32 * h2) >> 5)) : 0u;
+                        const bool ask = valid && !((kn[h2] >> lane) & 1u);
+                        vm[h2] = __ballot_sync(KBBQ_FULL, ask);
+                        if (ask) {
+                            blk[h2] = bloom_block(trusted, key);
+                            pat[h2] = bloom_pattern(trusted, key);
+                        }
+                    }
+                    coop_probe_pair(trusted.words, trusted.patterns, blk[0], pat[0], vm[0], blk[1], pat[1], vm[1], m[0], m[1]);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int jj = j0 + 32 * h2;
+                        if (jj >= nk) break;
+                        const uint32_t mm = m[h2] | kn[h2];
+                        const int cnt = nk - jj < 32 ? nk - jj : 32;
+                        all_trusted = all_trusted && mm == (cnt < 32 ? (1u << cnt) - 1u : ~0u);
+                        if (lane == 0) tflags[wo + (jj >> 5)] = mm;
+                    }
+                }
+            } else
             for (int j0 = 0; j0 < nk; j0 += 32) {
                 const int j = j0 + lane;
                 uint32_t m;
-                // k-mers pass 2 inserted from this very batch (known_bits, per k-mer in the word layout; given only while
-                // `trusted` has not been cleared since) are present without asking: a third of all k-mers at 30X
                 if (PREFETCH) {
                     const uint2 hp = j < nk ? HP[j] : make_uint2(0u, KBBQ_HP_INVALID);
                     m = warp_bloom_query_bp(trusted, hp.y < KBBQ_HP_KNOWN, bloom_block_of_hash(trusted, hp.x), hp.y) |
