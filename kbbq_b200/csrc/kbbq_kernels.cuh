@@ -526,9 +526,10 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
 // SHARED_HASH: both filters were built with the same seed, so salt_[0] and salt_[1] agree (the reference's filters
 // always do: bloom.hh:389, kbbq.cc:265-266) and a k-mer's block hash and pattern number are computed once, for the
 // query of `sampled`, and kept in shared memory for the insert into `trusted` (dynamic: 8 bytes per k-mer and warp).
-// PREFETCH (with SHARED_HASH; `sampled` lives in HBM): hash every k-mer and prefetch its block first, probe afterwards
-// (see prefetch_l2).
-template <int MODE, bool SHARED_HASH, bool PREFETCH>
+// QMODE (with SHARED_HASH; `sampled` lives in HBM): 0 = one 32-k-mer query at a time; 2 = two at a time, all 64 block loads
+// in flight together (coop_probe_pair); 1 = hash every k-mer and prefetch its block first, probe afterwards (prefetch_l2:
+// measured, loses, kept as a dead end).
+template <int MODE, bool SHARED_HASH, int QMODE>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P2_MIN_BLOCKS)
 pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, const int* __restrict__ thresholds,
                      uint32_t* __restrict__ err_out, StageSink sink, int max_kmers, const uint32_t* __restrict__ known_bits,
@@ -561,7 +562,7 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
         // `sampled` then (known_bits = that pass's sample bits, given only while the filter has not been cleared since):
         // it is present without asking -- a Bloom filter has no false negatives -- and its 64-byte probe is saved.
         const unsigned long long so = b.slot_off[r];
-        if (SHARED_HASH && PREFETCH) {
+        if (SHARED_HASH && QMODE == 1) {
             for (int j0 = 0; j0 < nk; j0 += 32) {
                 const int j = j0 + lane;
                 uint64_t key = 0;
@@ -585,6 +586,33 @@ pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, c
                 m |= __ballot_sync(KBBQ_FULL, known);
                 if (known) HP[j].y = hp.y & 0xFFFFu;  // back to a plain pattern number for the insert loop
                 if (lane == 0) Pm[j0 >> 5] = m;
+            }
+        } else if (SHARED_HASH && QMODE == 2) {
+            for (int j0 = 0; j0 < nk; j0 += 64) {
+                uint64_t blk[2] = {0, 0};
+                uint32_t pat[2] = {0, 0}, vm[2], kn[2], m[2];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int j = j0 + 32 * h2 + lane;
+                    uint64_t key = 0;
+                    const bool valid = j < nk && kmer_key(s, j, k, 0, -1, key);
+                    bool known = false;
+                    if (known_bits && valid) {
+                        const unsigned long long slot = so + (unsigned)j;
+                        known = (__ldg(known_bits + (slot >> 5)) >> (slot & 31)) & 1u;
+                    }
+                    const uint32_t h = hash_ap8(key, sampled.salt0);
+                    pat[h2] = valid ? bloom_pattern(sampled, key) : 0xFFFFFFFFu;
+                    if (j < nk) HP[j] = make_uint2(h, pat[h2]);
+                    blk[h2] = bloom_block_of_hash(sampled, h);
+                    vm[h2] = __ballot_sync(KBBQ_FULL, valid && !known);
+                    kn[h2] = __ballot_sync(KBBQ_FULL, known);
+                }
+                coop_probe_pair(sampled.words, sampled.patterns, blk[0], pat[0], vm[0], blk[1], pat[1], vm[1], m[0], m[1]);
+                if (lane == 0) {
+                    Pm[j0 >> 5] = m[0] | kn[0];
+                    if (j0 + 32 < nk) Pm[(j0 >> 5) + 1] = m[1] | kn[1];
+                }
             }
         } else
         for (int j0 = 0; j0 < nk; j0 += 32) {
