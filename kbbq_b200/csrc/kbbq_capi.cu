@@ -1644,12 +1644,14 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         const size_t smem = (shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0) + (mode == INS_STAGED ? st.smem() : 0);
         const int threads = KBBQ_WARPS_PER_BLOCK * 32;
 #define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S, PF><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers, known, b->d_ins_bits)
-        // `sampled` beyond the L2: two queries in flight per warp (QMODE 2; KBBQ_P2_DEEP=0 switches it off).
+        // KBBQ_P2_DEEP=1 (measurement): two queries in flight per warp (QMODE 2).  It wins 7 % in pass 3's scan, which is
+        // latency bound at 40 % issue utilisation; this kernel is at 60 % and spills at 64 registers with 64 probes in flight:
+        // 43.8 -> 50.0 ms on the config-3 shape, so it stays off here.
         // KBBQ_PREFETCH=1 (measurement): prefetch the blocks of all of a read's k-mers into the L2 before probing.  Measured
         // on the config-3 shape it LOSES -- 44 -> 68 ms here, 37 -> 53 ms in pass 3's scan -- so it stays off.
         const bool big = ctx->filt[KBBQ_FILTER_SAMPLED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4;
         const char* deep_env = getenv("KBBQ_P2_DEEP");
-        const int qmode = !shared_hash ? 0 : (big && getenv("KBBQ_PREFETCH")) ? 1 : (deep_env ? atoi(deep_env) != 0 : big) ? 2 : 0;
+        const int qmode = !shared_hash ? 0 : (big && getenv("KBBQ_PREFETCH")) ? 1 : (deep_env && atoi(deep_env) != 0) ? 2 : 0;
         if (qmode == 2) {
             constexpr int PF = 2;
             if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, true);

@@ -11,7 +11,9 @@
 //       evaluates f(t, key) -> bool valid for t in [0,count), count <= 32, and returns the mask of t for which the
 //       k-mer is valid AND present in the trusted filter (Bloom::query, bloom.hh:398);
 //   template<class F> uint32_t map32(F f)
-//       returns the mask of t in [0,32) for which f(t) is true.
+//       returns the mask of t in [0,32) for which f(t) is true;
+//   template<class F> void par(int n, F f)
+//       runs f(i) for every i in [0,n), in any order (one lane each on the device): the per-word loops.
 // On the device those are one lane per t and a __ballot_sync; tests/emu provides serial stand-ins so the logic can be
 // exercised without a GPU.
 //
@@ -370,8 +372,12 @@ struct ErrCaller {
     KBBQ_HD void revcomp(const SeqRef& src, const SeqRef& dst) {
         const int len = src.len;
         const int nw = (len + 31) >> 5;
-        KBBQ_NOUNROLL
-        for (int wd = 0; wd < nw; ++wd) {
+        q.par(nw + 1, [&](int wd) {
+            if (wd == nw) {
+                dst.w[nw] = 0;
+                dst.nm[nw] = 0;
+                return;
+            }
             // dst bases [32wd, 32wd+32) = complement of src bases len-1-32wd down to len-32-32wd
             const int hi = len - 1 - 32 * wd;
             int lo = hi - 31, cnt = 32;
@@ -383,14 +389,11 @@ struct ErrCaller {
 #if defined(__CUDA_ARCH__)
             nr = __brev(n) >> (32 - cnt);
 #else
-            KBBQ_NOUNROLL
             for (int b = 0; b < cnt; ++b) nr |= ((n >> b) & 1u) << (cnt - 1 - b);
 #endif
             dst.w[wd] = ~v & kmask(cnt);
             dst.nm[wd] = nr;
-        }
-        dst.w[nw] = 0;
-        dst.nm[nw] = 0;
+        });
     }
 
     // One invocation of get_errors on `cur` (length cur.len), whose base 0 is base `base` of the top-level read.
@@ -402,8 +405,7 @@ struct ErrCaller {
         bad_suffix = KBBQ_NPOS;
         if (len < k) return;  // the reference is undefined here (bloom.cc:30 / readutils.cc:207 underflow)
         const int nw = (len + 31) >> 5;
-        KBBQ_NOUNROLL
-        for (int w = 0; w <= nw; ++w) sc.O_nm[w] = cur.nm[w];
+        q.par(nw + 1, [&](int w) { sc.O_nm[w] = cur.nm[w]; });
         bool multiple = false;
         memo_reset();
         if (!prescanned) scan(cur, sc.T_orig);
@@ -510,15 +512,16 @@ struct ErrCaller {
             // call's own coordinates: a window's weight is two popcounts instead of a 20-step loop per base
             uint32_t* F = sc.F;
             uint32_t* FQ = sc.FQ;
-            KBBQ_NOUNROLL
-            for (int w = 0; w < nw; ++w) {
-                const int cnt = len - 32 * w < 32 ? len - 32 * w : 32;
-                const uint32_t e = extract_n(sc.E, base + 32 * w, cnt) & ~sc.O_nm[w];
+            q.par(nw + 1, [&](int w) {
+                uint32_t e = 0, eq = 0;
+                if (w < nw) {
+                    const int cnt = len - 32 * w < 32 ? len - 32 * w : 32;
+                    e = extract_n(sc.E, base + 32 * w, cnt) & ~sc.O_nm[w];
+                    eq = e & extract_n(sc.QL, base + 32 * w, cnt);
+                }
                 F[w] = e;
-                FQ[w] = e & extract_n(sc.QL, base + 32 * w, cnt);
-            }
-            F[nw] = 0;
-            FQ[nw] = 0;
+                FQ[w] = eq;
+            });
             KBBQ_NOUNROLL
             for (int w = 0; w < nw; ++w) {
                 uint32_t m = 0;

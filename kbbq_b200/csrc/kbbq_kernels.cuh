@@ -1033,6 +1033,17 @@ struct DevQuery {
         return 0;
 #endif
     }
+    // fn(i) for i in [0, n), one lane each: per-word loops of the error caller (a read is a handful of 32-base words)
+    // become one step of the warp instead of a chain of dependent shared-memory round trips
+    template <class F>
+    KBBQ_HD void par(int n, F fn) {
+#if defined(__CUDA_ARCH__)
+        for (int i = (int)(threadIdx.x & 31); i < n; i += 32) fn(i);
+        __syncwarp();
+#else
+        (void)n; (void)fn;
+#endif
+    }
 };
 
 // Writes read.errors (err_out, kbbq_batch word layout) and, per read, the base get_errors left modified (mod_out, see

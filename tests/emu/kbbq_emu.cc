@@ -58,6 +58,10 @@ struct HostQueryRef {
     uint32_t query(int count, F fn) { return h->query(count, fn); }
     template <class F>
     uint32_t map32(F fn) { return h->map32(fn); }
+    template <class F>
+    void par(int n, F fn) {  // the device runs fn(i) for i in [0,n) on different lanes; any order must do
+        for (int i = n - 1; i >= 0; --i) fn(i);
+    }
 };
 BloomView make_view(uint64_t* words, const uint64_t* patterns, uint64_t* inserted, uint64_t n_blocks, uint32_t s0, uint32_t s1) {
     BloomView v;
