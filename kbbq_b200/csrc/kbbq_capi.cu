@@ -246,6 +246,8 @@ struct kbbq_dbatch {
     uint32_t part_read[5] = {0, 0, 0, 0, 0};   // read boundaries of the pieces
     uint64_t part_word[5] = {0, 0, 0, 0, 0};   // ... and their word offsets (from the host's word_off at upload)
     cudaEvent_t qual_ready = nullptr;  // recorded on the copy stream after d_qual's upload
+    cudaEvent_t qmask_ready = nullptr; // kbbq_batch_upload_async with host masks: recorded on the copy stream after d_qmask's upload
+    bool qmask_waited = true;
     bool qual_waited = true;           // false until `stream` has been made to wait for qual_ready
     bool all_on_copy = false;          // kbbq_batch_upload_stream: every array is ready with qual_ready, not before
     BatchView view() const {
@@ -298,6 +300,17 @@ int need_quals(kbbq_ctx* ctx, kbbq_dbatch* b) {
     if (!b->qual_waited) {
         CU(cudaStreamWaitEvent(ctx->stream, b->qual_ready, 0));
         b->qual_waited = true;
+    }
+    return KBBQ_OK;
+}
+
+// pass 2 reads the quality MASKS only: made by the host they travel right behind what pass 1 needs and ahead of the
+// qualities; made on the device (or on a streamed batch) they are ready when the qualities are
+int need_qmask(kbbq_ctx* ctx, kbbq_dbatch* b) {
+    if (b->qmask_needs_quals || b->all_on_copy) return need_quals(ctx, b);
+    if (!b->qmask_waited) {
+        CU(cudaStreamWaitEvent(ctx->stream, b->qmask_ready, 0));
+        b->qmask_waited = true;
     }
     return KBBQ_OK;
 }
@@ -1317,6 +1330,7 @@ void kbbq_batch_free(kbbq_ctx* ctx, kbbq_dbatch* b) {
         if (ctx && !b->qual_waited) cudaStreamWaitEvent(st, b->qual_ready, 0);  // d_qual is freed in `st`'s order
         cudaEventDestroy(b->qual_ready);
     }
+    if (b->qmask_ready) cudaEventDestroy(b->qmask_ready);  // recorded before qual_ready on the same stream
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
     delete b;
@@ -1388,7 +1402,8 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, i
     PUT(b->d_nmask + h->n_words, (const void*)nullptr, 4);
     PUT(b->d_bases, h->bases, h->n_words * 8);
     PUT(b->d_nmask, h->nmask, h->n_words * 4);
-    if (h->qmask) PUT(b->d_qmask, h->qmask, (size_t)h->n_words * 8);  // early: all pass 2 needs of the qualities
+    const bool qmask_behind = mode == 1 && h->qmask && h->n_words;  // pass 1 does not read the masks: they follow on the copy stream
+    if (h->qmask && !qmask_behind) PUT(b->d_qmask, h->qmask, (size_t)h->n_words * 8);
     PUT(b->d_word_off, h->word_off, ((size_t)n + 1) * 4);
     PUT(b->d_len, h->len, (size_t)n * 4);
     PUT(b->d_rg, h->rg, (size_t)n * 2);
@@ -1412,6 +1427,12 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, i
             if (e2 == cudaSuccess) e2 = cudaEventRecord(small_done, ctx->stream);
             if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(ctx->copy_stream, small_done, 0);
             if (small_done) cudaEventDestroy(small_done);
+        }
+        if (e2 == cudaSuccess && qmask_behind) {  // the masks first (all pass 2 needs of the qualities), then the qualities
+            e2 = cudaMemcpyAsync(b->d_qmask, h->qmask, (size_t)h->n_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&b->qmask_ready, cudaEventDisableTiming);
+            if (e2 == cudaSuccess) e2 = cudaEventRecord(b->qmask_ready, ctx->copy_stream);
+            b->qmask_waited = false;
         }
         if (e2 == cudaSuccess && !h->n_words) e2 = cudaMemsetAsync(b->d_qual, 0, 32, ctx->copy_stream);
         if (e2 == cudaSuccess && h->n_words)
@@ -1621,8 +1642,7 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     }
     if (err_bits) CU(cudaMemsetAsync(b->d_err_bits, 0, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
-    if (b->qmask_needs_quals || b->all_on_copy)  // pass 2 reads the quality MASKS only; they are already there when the host brought them
-        if (int rc = need_quals(ctx, b)) return rc;
+    if (int rc = need_qmask(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {
         mark_kernel(ctx, "pass2_trusted_kernel");

@@ -1,6 +1,11 @@
 // kbbq_host_api.cc -- see kbbq_host_api.hh.
 #include "kbbq_host_api.hh"
+#include "fast_deflate.hh"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -432,22 +437,63 @@ static void parallel_for(size_t n, int nt, F f) {  // f(begin, end, thread index
         if (e) std::rethrow_exception(e);
 }
 
-static bool read_file(const std::string& filename, std::vector<uint8_t>& raw) {
-    FILE* f = fopen(filename.c_str(), "rb");
-    if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    const long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (sz < 0) { fclose(f); return false; }
-    raw.resize((size_t)sz);
-    const size_t got = sz ? fread(raw.data(), 1, (size_t)sz, f) : 0;
-    fclose(f);
-    return got == (size_t)sz;
+}  // namespace htsiter (reopened below)
+
+kbbq::Bytes& kbbq::Bytes::operator=(Bytes&& o) noexcept {
+    if (this != &o) {
+        release();
+        mapped_ = o.mapped_;
+        heap_ = std::move(o.heap_);
+        vec_ = std::move(o.vec_);
+        n_ = o.n_;
+        p_ = mapped_ ? o.p_ : !vec_.empty() ? vec_.data() : heap_.data();
+        o.p_ = nullptr;
+        o.n_ = 0;
+        o.mapped_ = false;
+    }
+    return *this;
 }
+void kbbq::Bytes::release() {
+    if (mapped_ && p_) munmap(const_cast<uint8_t*>(p_), n_);
+    p_ = nullptr;
+    n_ = 0;
+    mapped_ = false;
+}
+bool kbbq::Bytes::map_file(const std::string& path, Bytes& out) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size <= 0) { close(fd); return false; }
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return false;
+    madvise(m, (size_t)st.st_size, MADV_WILLNEED);
+    out.release();
+    out.p_ = (const uint8_t*)m;
+    out.n_ = (size_t)st.st_size;
+    out.mapped_ = true;
+    return true;
+}
+kbbq::Bytes kbbq::Bytes::uninitialised(size_t n) {
+    Bytes b;
+    b.heap_.resize(n);
+    b.p_ = b.heap_.data();
+    b.n_ = n;
+    return b;
+}
+kbbq::Bytes kbbq::Bytes::from(std::vector<uint8_t>&& v) {
+    Bytes b;
+    b.vec_ = std::move(v);
+    b.p_ = b.vec_.data();
+    b.n_ = b.vec_.size();
+    return b;
+}
+
+namespace htsiter {
 
 struct BgzfBlock { size_t cdata, clen, out_off; uint32_t isize; };
 // member boundaries of a BGZF file, or false when some member is not a BGZF block (then zlib reads it serially)
-static bool bgzf_index(const std::vector<uint8_t>& raw, std::vector<BgzfBlock>& blocks, size_t& total) {
+static bool bgzf_index(const kbbq::Bytes& raw, std::vector<BgzfBlock>& blocks, size_t& total) {
     size_t o = 0;
     total = 0;
     while (o < raw.size()) {
@@ -472,15 +518,15 @@ static bool bgzf_index(const std::vector<uint8_t>& raw, std::vector<BgzfBlock>& 
     return !blocks.empty();
 }
 
-static std::vector<uint8_t> read_all_decompressed(const std::string& filename, int nthreads) {
-    std::vector<uint8_t> data;
-    std::vector<uint8_t> raw;
-    if (filename != "-" && read_file(filename, raw)) {
-        if (raw.size() < 2 || raw[0] != 0x1f || raw[1] != 0x8b) return raw;  // not compressed
+static kbbq::Bytes read_all_decompressed(const std::string& filename, int nthreads) {
+    kbbq::Bytes raw;
+    if (filename != "-" && kbbq::Bytes::map_file(filename, raw)) {
+        if (raw.size() < 2 || raw[0] != 0x1f || raw[1] != 0x8b) return raw;  // not compressed: parsed where it lies
         std::vector<BgzfBlock> blocks;
         size_t total = 0;
         if (bgzf_index(raw, blocks, total)) {
-            data.resize(total);
+            kbbq::Bytes data = kbbq::Bytes::uninitialised(total);  // every byte is written by the pool below
+            uint8_t* out = data.writable();
             std::vector<char> bad((size_t)pool_size(nthreads), 0);
             parallel_for(blocks.size(), pool_size(nthreads), [&](size_t lo, size_t hi, int t) {
                 z_stream zs;
@@ -491,7 +537,7 @@ static std::vector<uint8_t> read_all_decompressed(const std::string& filename, i
                     if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
                     zs.next_in = (Bytef*)&raw[b.cdata];
                     zs.avail_in = (uInt)b.clen;
-                    zs.next_out = &data[b.out_off];
+                    zs.next_out = out + b.out_off;
                     zs.avail_out = b.isize;
                     const int rc = inflate(&zs, Z_FINISH);
                     inflateEnd(&zs);
@@ -503,15 +549,16 @@ static std::vector<uint8_t> read_all_decompressed(const std::string& filename, i
             return data;
         }
     }
-    // plain gzip (or stdin): one serial stream through zlib
+    // plain gzip, or something that cannot be mapped (a pipe, standard input): one serial stream through zlib, which
+    // passes uncompressed bytes through unchanged
     gzFile gz = filename == "-" ? gzdopen(0, "rb") : gzopen(filename.c_str(), "rb");
     if (!gz) throw std::runtime_error("Error opening file " + filename);
     gzbuffer(gz, 1 << 22);
-    std::vector<uint8_t> buf(1 << 24);
+    std::vector<uint8_t> data, buf(1 << 24);
     int got;
     while ((got = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.insert(data.end(), buf.begin(), buf.begin() + got);
     gzclose(gz);
-    return data;
+    return kbbq::Bytes::from(std::move(data));
 }
 
 // Read groups are numbered in order of first appearance in the file (readutils.cc:99-102).  Parsers working on
@@ -673,7 +720,7 @@ static size_t next_record_start(const char* base, size_t size, size_t from) {
 
 static std::shared_ptr<kbbq::ReadStore> load_fastq(const std::string& filename, int nthreads) {
     PhaseTimer pt_;
-    const std::vector<uint8_t> text = read_all_decompressed(filename, nthreads);
+    const kbbq::Bytes text = read_all_decompressed(filename, nthreads);
     pt_.mark("fastq: read + decompress");
     const char* base = (const char*)text.data();
     const size_t size = text.size();
@@ -740,12 +787,15 @@ static std::shared_ptr<kbbq::ReadStore> load_fastq(const std::string& filename, 
 
 FastqFile::FastqFile(std::string filename, int nthreads) : StoreFile(load_fastq(filename, nthreads), nthreads) {}
 
-StoreFile::~StoreFile() {
-    if (out_) {
-        flush_pending(true);
-        FILE* f = (FILE*)out_;
-        if (f == stdout) fflush(f); else fclose(f);
-    }
+StoreFile::~StoreFile() { close_out(); }
+int StoreFile::close_out() {
+    if (!out_) return 0;
+    int rc = flush_pending(true);
+    FILE* f = (FILE*)out_;
+    out_ = nullptr;
+    if (f == stdout) { if (fflush(f) != 0) rc = -1; }
+    else if (fclose(f) != 0) rc = -1;
+    return rc;
 }
 int StoreFile::next() {
     if (cur_ >= store_->n()) return -1;
@@ -783,26 +833,47 @@ int StoreFile::open_out(std::string filename) {
 
 // ---- BGZF: gzip members of <= 64 KiB with the "BC" extra field, closed by the empty EOF block --------------------
 static const size_t kBgzfInput = 0xff00;
+// The deflate stream inside a block: this repo's own encoder (fast_deflate.hh: long matches + one dynamic Huffman code
+// per block, ~3x zlib's level 1 at its ratio) unless KBBQ_BGZF_LEVEL asks for zlib: 0..9 = that zlib level (htslib's
+// bgzf_open(.., "w") compresses at zlib's default, 6), "huff" = this encoder without matching.
+struct BgzfMode { int zlib_level; int min_match; };  // zlib_level < 0: fast_deflate with min_match
+static BgzfMode bgzf_mode() {
+    static const BgzfMode mode = [] {
+        const char* e = getenv("KBBQ_BGZF_LEVEL");
+        if (e && *e >= '0' && *e <= '9') return BgzfMode{*e - '0', 0};
+        if (e && !strcmp(e, "huff")) return BgzfMode{-1, 1 << 30};
+        return BgzfMode{-1, 8};
+    }();
+    return mode;
+}
 static bool bgzf_block(const char* in, size_t n, std::string& out) {
-    z_stream zs;
-    std::memset(&zs, 0, sizeof zs);
-    // htslib's bgzf_open(.., "w") compresses at zlib's default level; KBBQ_BGZF_LEVEL=0..9 overrides (1 is ~3x faster)
-    static const int level = [] { const char* e = getenv("KBBQ_BGZF_LEVEL"); return e && *e >= '0' && *e <= '9' ? *e - '0' : Z_DEFAULT_COMPRESSION; }();
-    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    const BgzfMode mode = bgzf_mode();
     const size_t start = out.size();
-    out.resize(start + 18 + deflateBound(&zs, n) + 8);
-    unsigned char* o = (unsigned char*)&out[start];
+    size_t clen = 0;
     static const unsigned char head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    if (mode.zlib_level < 0) {
+        const size_t cap = kbbq::fdeflate::bound(n);
+        out.resize(start + 18 + cap + 8);
+        clen = kbbq::fdeflate::compress((const uint8_t*)in, n, (uint8_t*)&out[start] + 18, cap, mode.min_match);
+        if (clen == 0) return false;
+    } else {
+        z_stream zs;
+        std::memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, mode.zlib_level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+        out.resize(start + 18 + deflateBound(&zs, n) + 8);
+        zs.next_in = (Bytef*)in;
+        zs.avail_in = (uInt)n;
+        zs.next_out = (Bytef*)&out[start] + 18;
+        zs.avail_out = (uInt)(out.size() - start - 18 - 8);
+        const int rc = deflate(&zs, Z_FINISH);
+        clen = zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END) return false;
+    }
+    unsigned char* o = (unsigned char*)&out[start];
     std::memcpy(o, head, 16);
-    zs.next_in = (Bytef*)in;
-    zs.avail_in = (uInt)n;
-    zs.next_out = o + 18;
-    zs.avail_out = (uInt)(out.size() - start - 18 - 8);
-    const int rc = deflate(&zs, Z_FINISH);
-    const size_t clen = zs.total_out;
-    deflateEnd(&zs);
-    if (rc != Z_STREAM_END) return false;
     const size_t bsize = 18 + clen + 8;
+    if (bsize > 65536) return false;
     o[16] = (unsigned char)((bsize - 1) & 0xff);
     o[17] = (unsigned char)((bsize - 1) >> 8);
     const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)in, (uInt)n), isize = (uint32_t)n;
@@ -1015,7 +1086,7 @@ static std::shared_ptr<kbbq::ReadStore> load_bam(const std::string& filename, bo
     PhaseTimer pt_;
     rs->bam_raw = read_all_decompressed(filename, nthreads);
     pt_.mark("bam: read + decompress");
-    const std::vector<uint8_t>& d = rs->bam_raw;
+    const kbbq::Bytes& d = rs->bam_raw;
     if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) throw std::runtime_error("Error opening file " + filename);
     size_t p = 4;
     int32_t l_text, n_ref;
@@ -1030,7 +1101,7 @@ static std::shared_ptr<kbbq::ReadStore> load_bam(const std::string& filename, bo
         std::memcpy(&l_ref, &d[p], 4); p += 4;
         rs->ref_len.push_back(l_ref);
     }
-    rs->bam_header.assign(d.begin(), d.begin() + p);
+    rs->bam_header.assign(d.data(), d.data() + p);
     // record boundaries and column offsets: one cheap serial walk over the block_size chain
     rs->name_off.push_back(0); rs->comment_off.push_back(0); rs->off.push_back(0);
     while (p + 4 <= d.size()) {

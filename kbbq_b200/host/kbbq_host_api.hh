@@ -35,6 +35,14 @@ public:
     Column() = default;
     Column(const Column&) = delete;
     Column& operator=(const Column&) = delete;
+    Column(Column&& o) noexcept : p_(std::move(o.p_)), n_(o.n_), cap_(o.cap_) { o.n_ = o.cap_ = 0; }
+    Column& operator=(Column&& o) noexcept {
+        p_ = std::move(o.p_);
+        n_ = o.n_;
+        cap_ = o.cap_;
+        o.n_ = o.cap_ = 0;
+        return *this;
+    }
     void resize(size_t n) {
         if (n > cap_) {
             T* p = static_cast<T*>(::operator new(n * sizeof(T)));
@@ -57,6 +65,34 @@ private:
     size_t n_ = 0, cap_ = 0;
 };
 
+// The decompressed input: a read-only mapping of the file itself when it is plain (no copy, pages come straight from
+// the page cache as the parser threads touch them), else heap memory filled by the inflater threads.
+class Bytes {
+public:
+    Bytes() = default;
+    Bytes(const Bytes&) = delete;
+    Bytes& operator=(const Bytes&) = delete;
+    Bytes(Bytes&& o) noexcept { *this = std::move(o); }
+    Bytes& operator=(Bytes&& o) noexcept;
+    ~Bytes() { release(); }
+    static bool map_file(const std::string& path, Bytes& out);  // false: not a regular file, or the mapping failed
+    static Bytes uninitialised(size_t n);
+    static Bytes from(std::vector<uint8_t>&& v);
+    const uint8_t* data() const { return p_; }
+    uint8_t* writable() { return mapped_ ? nullptr : const_cast<uint8_t*>(p_); }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    const uint8_t& operator[](size_t i) const { return p_[i]; }
+
+private:
+    void release();
+    const uint8_t* p_ = nullptr;
+    size_t n_ = 0;
+    bool mapped_ = false;
+    Column<uint8_t> heap_;
+    std::vector<uint8_t> vec_;
+};
+
 // Everything parsed from the input, kept for all passes: the reference's per-record kseq_t / CReadData, columnar.
 struct ReadStore {
     std::string path;
@@ -69,7 +105,8 @@ struct ReadStore {
     uint32_t max_len = 0;
     // BAM input only: the header as it was read, the whole uncompressed stream, and where each record's body (core +
     // data, without its block_size field) sits in it; reference lengths from the header
-    std::vector<uint8_t> bam_header, bam_raw;
+    std::vector<uint8_t> bam_header;
+    Bytes bam_raw;
     std::vector<uint64_t> bam_rec_off;
     std::vector<uint32_t> bam_rec_len;
     std::vector<uint64_t> ref_len;
@@ -279,6 +316,9 @@ public:
     const kbbq::ReadStore& store() const override { return *store_; }
     // mirror-only: write every record with new qualities (layout of kbbq_batch.qual per batch), in input order
     int write_all(const kbbq::Session& s, const std::vector<kbbq::Pinned<uint8_t>>& newq);
+    // mirror-only: finish the output now (last block, BGZF end-of-file marker, flush) instead of in the destructor;
+    // 0, or -1 when the stream reports an error
+    int close_out();
 
 protected:
     StoreFile(std::shared_ptr<kbbq::ReadStore> st, int nthreads) : store_(std::move(st)), nthreads_(nthreads) {}

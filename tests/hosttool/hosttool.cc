@@ -4,11 +4,17 @@
 //   hosttool rewrite FILE QUALS OUT [set_oq] [use_oq]
 //        QUALS holds one line of new qualities (+33, read orientation) per record; every record is passed through
 //        HTSFile::next / recalibrate / write exactly as recalibrate_and_write's generic loop does
+//   hosttool deflate FILE OUT BLOCK MINMATCH
+//        the sink's own DEFLATE encoder (fast_deflate.hh) on FILE cut into BLOCK-byte pieces; OUT = per piece a
+//        little-endian u32 stream length followed by the raw stream
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <memory>
+#include <vector>
 
+#include "../../kbbq_b200/host/fast_deflate.hh"
 #include "../../kbbq_b200/host/kbbq_host_api.hh"
 
 int main(int argc, char** argv) {
@@ -19,6 +25,25 @@ int main(int argc, char** argv) {
     for (int i = 3; i < argc; ++i) {
         if (!strcmp(argv[i], "set_oq")) set_oq = true;
         if (!strcmp(argv[i], "use_oq")) use_oq = true;
+    }
+    if (mode == "deflate") {
+        if (argc < 6) return 2;
+        std::ifstream in(fn, std::ios::binary);
+        const std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        std::ofstream out(argv[3], std::ios::binary);
+        const size_t block = (size_t)atol(argv[4]);
+        const int min_match = atoi(argv[5]);
+        std::vector<uint8_t> z(kbbq::fdeflate::bound(block));
+        size_t p = 0;
+        do {  // an empty file is one empty piece
+            const size_t n = std::min(block, data.size() - p);
+            const uint32_t c = (uint32_t)kbbq::fdeflate::compress((const uint8_t*)data.data() + p, n, z.data(), z.size(), min_match);
+            if (c == 0) return 6;
+            out.write((const char*)&c, 4);
+            out.write((const char*)z.data(), c);
+            p += n;
+        } while (p < data.size());
+        return 0;
     }
     try {
         std::unique_ptr<htsiter::StoreFile> f;

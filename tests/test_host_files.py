@@ -195,3 +195,72 @@ def test_cli_error_paths_without_a_gpu(tmp_path):
         assert rc == 1 and "no CPU path" in err
     else:
         assert rc == 1 and "--genomelen must be specified" in err
+
+
+def _inflate_pieces(blob):
+    import zlib
+    out, p = [], 0
+    while p < len(blob):
+        n = int.from_bytes(blob[p:p + 4], "little")
+        d = zlib.decompressobj(-15)
+        piece = d.decompress(blob[p + 4:p + 4 + n]) + d.flush()
+        assert d.eof and d.unused_data == b""  # one complete final block, nothing after it
+        out.append(piece)
+        p += 4 + n
+    return b"".join(out)
+
+
+def _deflate_cases():
+    rng = np.random.default_rng(5)
+    fib = [1, 1]
+    while len(fib) < 40:
+        fib.append(fib[-1] + fib[-2])
+    deep = b"".join(bytes([i]) * min(f, 40000) for i, f in enumerate(fib[:24]))  # Fibonacci counts: plain Huffman depth > 15
+    rec = b"".join(b"@SRR1234567.%d %d length=100\n" % (i, i) + bytes(rng.choice(list(b"ACGT"), 100).tolist()) + b"\n+\n"
+                   + bytes(rng.choice(list(b"#,:FI"), 100, p=[.01, .04, .1, .35, .5]).tolist()) + b"\n" for i in range(3000))
+    return {
+        "empty": b"", "one": b"A", "two": b"AB", "same": b"x" * 200000, "random": rng.bytes(150000),
+        "short_edges": b"".join(bytes(rng.integers(65, 70, n).tolist()) for n in (15, 16, 31, 32, 33)),
+        "deep": bytes(rng.permutation(np.frombuffer(deep, dtype=np.uint8)).tolist()), "fastq": rec,
+        "periodic": (b"ACGTTGCA" * 9 + b"N") * 3000, "far": rng.bytes(40000) * 3,
+        "bam_like": rng.integers(0, 16, 120000).astype(np.uint8).tobytes() + bytes(200) + rng.integers(0, 4, 9000).astype(np.uint8).tobytes(),
+    }
+
+
+@pytest.mark.parametrize("min_match", [8, 20, 1 << 30])
+@pytest.mark.parametrize("block", [65280, 65535, 4096, 37])
+def test_sink_deflate_encoder_round_trips_through_zlib(tool, tmp_path, block, min_match):
+    """fast_deflate.cc against zlib's inflater: every shape of block (empty, one symbol, incompressible -> stored,
+    code depths beyond the 15-bit limit, matches at every distance up to the window, the last bytes of a block)."""
+    for name, data in _deflate_cases().items():
+        if block == 37 and len(data) > 40000:
+            data = data[:40000]
+        (tmp_path / "in").write_bytes(data)
+        subprocess.run([tool, "deflate", str(tmp_path / "in"), str(tmp_path / "out"), str(block), str(min_match)], check=True)
+        blob = (tmp_path / "out").read_bytes()
+        assert _inflate_pieces(blob) == data, name
+        if name in ("same", "periodic") and block >= 4096 and min_match <= 20:
+            assert len(blob) < len(data) // 20, name  # matches are found and used
+        if name == "random":
+            assert len(blob) <= len(data) + 9 * (len(data) // block + 1), name  # never worse than stored blocks
+        if name == "fastq" and block >= 65280:
+            assert len(blob) < 0.5 * len(data)
+
+
+@pytest.mark.parametrize("level", [None, "huff", "1", "6"])
+def test_bgzf_writer_modes_all_inflate_to_the_same_stream(tool, tmp_path, level):
+    want = gzip.open(os.path.join(GOLD, "cli_bam_out.bam.gz")).read()
+    _, wr = _records(want)
+    (tmp_path / "q.txt").write_bytes(b"\n".join(_read_orientation_quals(r) for r in wr) + b"\n")
+    env = dict(os.environ)
+    env.pop("KBBQ_BGZF_LEVEL", None)
+    if level:
+        env["KBBQ_BGZF_LEVEL"] = level
+    subprocess.run([tool, "rewrite", os.path.join(GOLD, "cli_in.bam"), str(tmp_path / "q.txt"), str(tmp_path / "o.bam"), "set_oq"], check=True, env=env)
+    raw = (tmp_path / "o.bam").read_bytes()
+    assert gzip.decompress(raw) == want
+    p = 0
+    while p < len(raw):  # every member is a BGZF block whose BSIZE field is its length
+        assert raw[p:p + 4] == b"\x1f\x8b\x08\x04" and raw[p + 12:p + 14] == b"BC"
+        p += int.from_bytes(raw[p + 16:p + 18], "little") + 1
+    assert p == len(raw)
