@@ -1464,15 +1464,36 @@ static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, i
         const uint32_t km1 = (uint32_t)ctx->k - 1;
         bool uniform = n > 0;
         const uint32_t wpr0 = n ? (h->len[0] + 31) / 32 : 0;
-        for (uint32_t r = 0; r < n; ++r) {
-            const uint32_t l = h->len[r];
-            longest = std::max(longest, l);
-            slots += l > km1 ? l - km1 : 0;
-            uniform = uniform && (l + 31) / 32 == wpr0 && h->word_off[r] == r * wpr0;
+        // pass 1 cannot be launched before this returns: large batches are checked by a few threads
+        const int nt = (int)std::min<uint32_t>((uint32_t)std::min(host_threads(), 8), n / (1u << 18) + 1);
+        struct Part { unsigned long long slots = 0; uint32_t longest = 0, biggest_rg = 0; bool uniform = true; };
+        std::vector<Part> parts((size_t)nt);
+        auto check = [&](int t) {
+            Part pt;
+            const uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
+            for (uint32_t r = lo; r < hi; ++r) {
+                const uint32_t l = h->len[r];
+                pt.longest = std::max(pt.longest, l);
+                pt.slots += l > km1 ? l - km1 : 0;
+                pt.uniform = pt.uniform && (l + 31) / 32 == wpr0 && h->word_off[r] == r * wpr0;
+            }
+            if (h->rg)
+                for (uint32_t r = lo; r < hi; ++r) pt.biggest_rg = std::max<uint32_t>(pt.biggest_rg, h->rg[r]);
+            parts[(size_t)t] = pt;
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(check, t);
+            check(0);
+            for (auto& t : th) t.join();
+        }
+        for (const Part& pt : parts) {
+            slots += pt.slots;
+            longest = std::max(longest, pt.longest);
+            biggest_rg = std::max(biggest_rg, pt.biggest_rg);
+            uniform = uniform && pt.uniform;
         }
         b->uniform_wpr = uniform && wpr0 ? wpr0 : 0;
-        if (h->rg)
-            for (uint32_t r = 0; r < n; ++r) biggest_rg = std::max<uint32_t>(biggest_rg, h->rg[r]);
         b->n_slots = slots;
         const char* bad = longest > h->max_len ? "len[r] exceeds max_len"
                           : (n && biggest_rg >= (uint32_t)ctx->n_rg) ? "read group id >= n_rg" : nullptr;

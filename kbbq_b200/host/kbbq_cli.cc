@@ -144,18 +144,31 @@ int main(int argc, char* argv[]) {
             return 1;
         }
         const int n_rg = (int)std::max<size_t>(1, readutils::CReadData::rg_to_int.size());
+        // --gpus N with N > 0 names the devices without asking the driver (the first CUDA call blocks until the runtime is
+        // up, and the packing below should run under that start-up, not behind it); the count is checked afterwards
         std::vector<int> devices;
-        {
-            const int have = kbbq_device_count();
+        auto check_count = [&](int have) {
             const int want = ngpus == 0 ? have : ngpus;
             if (want > have && have > 0) {
                 std::cerr << put_now << " Error: " << want << " GPUs requested, " << have << " present." << std::endl;
-                return 1;
+                return false;
             }
-            for (int d = 0; d < std::max(1, want); ++d) devices.push_back(d);
+            return true;
+        };
+        if (ngpus == 0) {
+            const int have = kbbq_device_count();
+            if (!check_count(have)) return 1;
+            for (int d = 0; d < std::max(1, have); ++d) devices.push_back(d);
+        } else {
+            for (int d = 0; d < ngpus; ++d) devices.push_back(d);
         }
-        kbbq::Session session(k, n_rg, (int)std::max<uint32_t>(1, store.max_len), devices);
+        // the contexts come up in the background (CUDA's start-up outlasts the parsing); packing needs none of them
+        kbbq::Session session(k, n_rg, (int)std::max<uint32_t>(1, store.max_len), devices, true);
         covariateutils::CCovariateData data;
+        session.prepack(store);
+        timer.mark("first batches packed");
+        if (ngpus != 0 && !check_count(kbbq_device_count())) return 1;
+        session.contexts();
         timer.mark("GPU context");
 
         if (fixedinput == "") {

@@ -60,33 +60,50 @@ template class Pinned<uint8_t>;
 
 Session::Session(int k, int n_rg, int max_cycle, int device) : Session(k, n_rg, max_cycle, std::vector<int>{device}) {}
 
-Session::Session(int k, int n_rg, int max_cycle, const std::vector<int>& devices) : devices_(devices), k_(k) {
+Session::Session(int k, int n_rg, int max_cycle, const std::vector<int>& devices, bool background) : devices_(devices), k_(k) {
     if (devices.empty()) throw std::invalid_argument("a Session needs at least one device");
-    try {
-        for (int d : devices) {
-            kbbq_ctx* c = nullptr;
-            CK(kbbq_ctx_create(d, k, n_rg, max_cycle, &c));
-            ctx_.push_back(c);
+    streaming_.assign(devices.size(), false);
+    auto create = [this, k, n_rg, max_cycle] {
+        try {
+            for (int d : devices_) {
+                kbbq_ctx* c = nullptr;
+                CK(kbbq_ctx_create(d, k, n_rg, max_cycle, &c));
+                ctx_.push_back(c);
+            }
+        } catch (...) {
+            for (kbbq_ctx* c : ctx_) kbbq_ctx_destroy(c);
+            ctx_.clear();
+            throw;
         }
-    } catch (...) {
-        for (kbbq_ctx* c : ctx_) kbbq_ctx_destroy(c);
-        throw;
+    };
+    if (background) {
+        ready_ = std::async(std::launch::async, create).share();
+    } else {
+        create();
+        std::promise<void> done;
+        done.set_value();
+        ready_ = done.get_future().share();
     }
-    streaming_.assign(ctx_.size(), false);
     if (!g_current) g_current = this;
 }
+void Session::wait_contexts() const {
+    std::shared_future<void> f = ready_;  // a copy per caller: get() on one object from several threads is not allowed
+    f.get();                              // rethrows what the creation threw, every time
+}
 Session::~Session() {
+    try { wait_contexts(); } catch (...) {}
     for (SessionBatch& b : batches_)
         if (b.dev) kbbq_batch_free(ctx_[b.gpu], b.dev);
     for (kbbq_ctx* c : ctx_) kbbq_ctx_destroy(c);
     if (g_current == this) g_current = nullptr;
 }
 
-// Pack reads [sb.lo, sb.hi) of the store into the kbbq_batch layout.  With `pinned_copy` the arrays are the batch's own
-// pinned members (kept for re-streaming); otherwise thread-local scratch that lives until the next call on this thread.
-void Session::pack(const ReadStore& rs, SessionBatch& sb, bool pinned_copy, kbbq_batch& hb, std::vector<uint16_t>*) {
+// Pack reads [sb.lo, sb.hi) of the store into the kbbq_batch layout: into the batch's own pinned members (kept for
+// re-streaming; needs a context), into its ordinary pre_* members (prepack), or into thread-local scratch that lives
+// until the next call on this thread.
+void Session::pack(const ReadStore& rs, SessionBatch& sb, PackTo to, kbbq_batch& hb) {
     const size_t m = sb.hi - sb.lo;
-    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max<size_t>(1, ctx_.size())));
+    const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max<size_t>(1, devices_.size())));
     std::vector<uint64_t> off(m + 1);
     for (size_t i = 0; i <= m; ++i) off[i] = rs.off[sb.lo + i] - rs.off[sb.lo];
     uint64_t nw = 0;
@@ -103,10 +120,14 @@ void Session::pack(const ReadStore& rs, SessionBatch& sb, bool pinned_copy, kbbq
     uint32_t *nmask, *len;
     uint8_t* qual;
     const size_t nw1 = std::max<uint64_t>(nw, 1);
-    if (pinned_copy) {
+    if (to == kPinned) {
         sb.bases.resize(nw1); sb.nmask.resize(nw1); sb.qual.resize(nw1 * 32); sb.len.resize(std::max<size_t>(m, 1)); sb.qmask.resize(nw1 * 2);
         bases = sb.bases.data(); nmask = sb.nmask.data(); qual = sb.qual.data(); len = sb.len.data();
         sb.has_host_copy = true;
+    } else if (to == kOwned) {
+        sb.pre_bases.resize(nw1); sb.pre_nmask.resize(nw1); sb.pre_qual.resize(nw1 * 32); sb.pre_len.resize(std::max<size_t>(m, 1));
+        bases = sb.pre_bases.data(); nmask = sb.pre_nmask.data(); qual = sb.pre_qual.data(); len = sb.pre_len.data();
+        sb.prepacked = true;
     } else {
         t_bases.resize(nw1); t_nmask.resize(nw1); t_qual.resize(nw1 * 32); t_len.resize(std::max<size_t>(m, 1));
         bases = t_bases.data(); nmask = t_nmask.data(); qual = t_qual.data(); len = t_len.data();
@@ -120,7 +141,7 @@ void Session::pack(const ReadStore& rs, SessionBatch& sb, bool pinned_copy, kbbq
     hb.bases = bases; hb.nmask = nmask; hb.qual = qual; hb.word_off = sb.word_off.data();
     hb.len = len; hb.rg = rs.rg.data() + sb.lo; hb.second = rs.second.data() + sb.lo;
     hb.qmask = nullptr;  // resident batches: derived on the device (the upload is synchronous anyway)
-    if (pinned_copy) {   // streamed batches bring the masks, so that pass 2 never waits for more than its own upload
+    if (to == kPinned) {  // streamed batches bring the masks, so that pass 2 never waits for more than its own upload
         CK(kbbq_quality_masks(nw, qual, sb.qmask.data(), nt));
         hb.qmask = sb.qmask.data();
     }
@@ -132,10 +153,10 @@ static void host_batch_of(const ReadStore& rs, const SessionBatch& sb, kbbq_batc
     hb.len = sb.len.data(); hb.rg = rs.rg.data() + sb.lo; hb.second = rs.second.data() + sb.lo; hb.qmask = sb.qmask.data();
 }
 
-void Session::ensure_resident(const ReadStore& rs) {
-    if (resident_ == &rs) return;
-    if (resident_) throw std::runtime_error("a Session holds one input at a time");
-    const size_t n = rs.n(), G = ctx_.size();
+void Session::cut_batches(const ReadStore& rs) {
+    if (cut_for_ == &rs) return;
+    if (cut_for_) throw std::runtime_error("a Session holds one input at a time");
+    const size_t n = rs.n(), G = devices_.size();
     // at most 2 M reads per batch keeps word offsets well inside 32 bits; several GPUs each get a share of a small input
     size_t per_batch = 1u << 21;
     if (G > 1) per_batch = std::max<size_t>(1, std::min(per_batch, (n + G - 1) / G));
@@ -147,6 +168,39 @@ void Session::ensure_resident(const ReadStore& rs) {
         batches_.push_back(std::move(sb));
         if (n == 0) break;
     }
+    cut_for_ = &rs;
+}
+
+void Session::prepack(const ReadStore& rs) {
+    if (resident_ == &rs) return;
+    cut_batches(rs);
+    const size_t G = devices_.size();
+    std::vector<std::exception_ptr> err(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            try {
+                for (SessionBatch& sb : batches_) {
+                    if ((size_t)sb.gpu != g) continue;
+                    kbbq_batch hb;
+                    if (!sb.prepacked) pack(rs, sb, kOwned, hb);
+                    break;  // the first batch of this GPU only: the others reuse one scratch buffer as they are uploaded
+                }
+            } catch (...) {
+                err[g] = std::current_exception();
+            }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : err)
+        if (e) std::rethrow_exception(e);
+}
+
+void Session::ensure_resident(const ReadStore& rs) {
+    if (resident_ == &rs) return;
+    if (resident_) throw std::runtime_error("a Session holds one input at a time");
+    cut_batches(rs);
+    wait_contexts();
+    const size_t G = ctx_.size();
     // what a GPU's share would take resident (inputs, flags, new qualities), against what it has left beside the filters
     // and the staging arrays of one batch's inserts
     std::vector<uint64_t> need(G, 0), biggest(G, 0);
@@ -177,8 +231,19 @@ void Session::ensure_resident(const ReadStore& rs) {
                 for (SessionBatch& sb : batches_) {
                     if ((size_t)sb.gpu != g) continue;
                     kbbq_batch hb;
-                    pack(rs, sb, streaming_[g], hb, nullptr);
+                    if (sb.prepacked && !streaming_[g]) {  // packed while the contexts were being created
+                        hb.n_reads = (uint32_t)(sb.hi - sb.lo); hb.max_len = sb.max_len; hb.n_words = sb.n_words;
+                        hb.bases = sb.pre_bases.data(); hb.nmask = sb.pre_nmask.data(); hb.qual = sb.pre_qual.data();
+                        hb.word_off = sb.word_off.data(); hb.len = sb.pre_len.data();
+                        hb.rg = rs.rg.data() + sb.lo; hb.second = rs.second.data() + sb.lo; hb.qmask = nullptr;
+                    } else {
+                        pack(rs, sb, streaming_[g] ? kPinned : kScratch, hb);
+                    }
                     if (!streaming_[g]) CK(kbbq_batch_upload(ctx_[g], &hb, &sb.dev));
+                    if (sb.prepacked) {
+                        sb.pre_bases = Column<uint64_t>(); sb.pre_nmask = Column<uint32_t>(); sb.pre_len = Column<uint32_t>(); sb.pre_qual = Column<uint8_t>();
+                        sb.prepacked = false;
+                    }
                 }
             } catch (...) {
                 err[g] = std::current_exception();
@@ -248,6 +313,7 @@ void Session::for_each_batch(const std::function<void(kbbq_ctx*, kbbq_dbatch*, S
 }
 
 void Session::merge_filter(int which) {
+    wait_contexts();
     if (ctx_.size() > 1) CK(kbbq_bloom_or_allreduce_local(ctx_.data(), (int)ctx_.size(), which));
 }
 
@@ -257,9 +323,9 @@ kbbq_dbatch* Session::upload_range(const ReadStore& rs, size_t lo, size_t hi, in
     sb.hi = hi;
     sb.gpu = g;
     kbbq_batch hb;
-    pack(rs, sb, false, hb, nullptr);
+    pack(rs, sb, kScratch, hb);
     kbbq_dbatch* d = nullptr;
-    CK(kbbq_batch_upload(ctx_[g], &hb, &d));
+    CK(kbbq_batch_upload(ctx(g), &hb, &d));
     return d;
 }
 

@@ -10,6 +10,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <future>
 #include <memory>
 #include <cstring>
 #include <functional>
@@ -148,6 +149,11 @@ struct SessionBatch {
     Pinned<uint32_t> nmask, len, qmask;
     Pinned<uint8_t> qual;
     bool has_host_copy = false;
+    // packed ahead of the upload (Session::prepack), ordinary memory: the contexts may not exist yet
+    Column<uint64_t> pre_bases;
+    Column<uint32_t> pre_nmask, pre_len;
+    Column<uint8_t> pre_qual;
+    bool prepacked = false;
 };
 
 // The GPU contexts of one run plus the batches of one input.
@@ -162,13 +168,18 @@ struct SessionBatch {
 class Session {
 public:
     Session(int k, int n_rg, int max_cycle, int device = 0);
-    Session(int k, int n_rg, int max_cycle, const std::vector<int>& devices);
+    // background = true: the contexts are created by a side thread (CUDA's start-up takes hundreds of ms) and the
+    // constructor returns at once; whatever needs a context waits for it, and reports its failure.  prepack() does not.
+    Session(int k, int n_rg, int max_cycle, const std::vector<int>& devices, bool background = false);
     ~Session();
     Session(const Session&) = delete;
-    int n_gpus() const { return (int)ctx_.size(); }
-    kbbq_ctx* ctx(int g = 0) const { return ctx_[g]; }
-    const std::vector<kbbq_ctx*>& contexts() const { return ctx_; }
+    int n_gpus() const { return (int)devices_.size(); }
+    kbbq_ctx* ctx(int g = 0) const { wait_contexts(); return ctx_[g]; }
+    const std::vector<kbbq_ctx*>& contexts() const { wait_contexts(); return ctx_; }
     int k() const { return k_; }
+    // Host-only head start for ensure_resident: cuts the store into batches and packs every GPU's first batch into
+    // ordinary memory, touching no context -- what a caller does while the contexts are still being created.
+    void prepack(const ReadStore& rs);
     // pack the store into batches once (uploading those that stay resident); later calls are no-ops
     void ensure_resident(const ReadStore& rs);
     std::vector<SessionBatch>& batches() { return batches_; }
@@ -186,7 +197,12 @@ public:
     int next_filter_slot() { return next_slot_++; }
 
 private:
-    void pack(const ReadStore& rs, SessionBatch& sb, bool pinned_copy, kbbq_batch& hb, std::vector<uint16_t>* rg_tmp);
+    enum PackTo { kScratch, kPinned, kOwned };  // thread-local scratch / the batch's pinned members / its pre_* members
+    void pack(const ReadStore& rs, SessionBatch& sb, PackTo to, kbbq_batch& hb);
+    void cut_batches(const ReadStore& rs);
+    void wait_contexts() const;
+    mutable std::shared_future<void> ready_;
+    const ReadStore* cut_for_ = nullptr;
     std::vector<kbbq_ctx*> ctx_;
     std::vector<int> devices_;
     std::vector<bool> streaming_;
