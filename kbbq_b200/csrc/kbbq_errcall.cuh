@@ -164,11 +164,13 @@ struct ErrCaller {
         int p;            // position, -1 = empty
         bool mirrored;    // which working sequence
         uint32_t first;   // bit c: first k-mer with base c trusted
-        uint64_t run_in;  // per base c, 16 bits at 16c: trusted streak over the k-mers containing p (>= 1), 0 = not walked yet
+        uint32_t run_in;  // per base c, 8 bits at 8c: trusted streak over the k-mers containing p (1 .. k), 0 = not walked yet
     };
     // four small counters in one register (indexed arrays would live in local memory once loops are not unrolled)
     static KBBQ_HD int get16(uint64_t v, int i) { return (int)((v >> (16 * i)) & 0xFFFFu); }
     static KBBQ_HD uint64_t set16(uint64_t v, int i, int x) { return (v & ~(0xFFFFull << (16 * i))) | ((uint64_t)(unsigned)x << (16 * i)); }
+    static KBBQ_HD int get8(uint32_t v, int i) { return (int)((v >> (8 * i)) & 0xFFu); }
+    static KBBQ_HD uint32_t set8(uint32_t v, int i, int x) { return (v & ~(0xFFu << (8 * i))) | ((uint32_t)x << (8 * i)); }
     Memo memo;
 
     KBBQ_HD void memo_reset() { memo.p = -1; }
@@ -178,21 +180,18 @@ struct ErrCaller {
         const uint32_t m0 = kmers_mask(s, p - k + 1, 0, ncand, p, 0, cpack);
         memo.p = p;
         memo.mirrored = T_mirrored;
-        memo.first = 0;
         memo.run_in = 0;
-        KBBQ_NOUNROLL
-        for (int t = 0; t < ncand; ++t) {
-            const int c = (int)((cpack >> (2 * t)) & 3u);
-            if ((m0 >> t) & 1u) memo.first |= 1u << c;
-        }
+        // bit t of m0 (test order) -> bit c of first (base code); m0 has no bit at or above ncand
+        memo.first = ((m0 & 1u) << (cpack & 3u)) | (((m0 >> 1) & 1u) << ((cpack >> 2) & 3u)) | (((m0 >> 2) & 1u) << ((cpack >> 4) & 3u)) |
+                     (((m0 >> 3) & 1u) << ((cpack >> 6) & 3u));
         return memo.first;
     }
     // trusted streak over the k-mers that contain p (there are nin of them) with base c at p, first one known trusted
     KBBQ_HD int run_containing(const SeqRef& s, int p, int nin, int c) {
-        int r = get16(memo.run_in, c);
+        int r = get8(memo.run_in, c);
         if (r == 0) {
             r = 1 + trusted_run(s, p - k + 2, p - k + 1 + nin, p, c);
-            memo.run_in = set16(memo.run_in, c, r);
+            memo.run_in = set8(memo.run_in, c, r);
         }
         return r;
     }
@@ -281,9 +280,9 @@ struct ErrCaller {
             }
         }
         // otherwise try pulling the anchor back by up to k/2: first k-mers of every (position, base) pair in bulk
-        int ni = 0;  // positions i = k/2-1 .. 0 that satisfy anchor > i+k-1 form a prefix of that descending walk
-        KBBQ_NOUNROLL
-        for (int i = k / 2 - 1; i >= 0 && anchor > i + k - 1; --i) ++ni;
+        // positions i = k/2-1 .. 0 while anchor > i+k-1 (bloom.cc:228): the test only gets easier as i falls, so the walk
+        // covers all k/2 positions or stops at once
+        const int ni = anchor > k / 2 - 1 + k - 1 ? k / 2 : 0;
         const int npairs = 4 * ni;
         const int need = k / 2 + 2;  // k-mers ending at m .. m+k/2+1 must all be trusted
         const int jmax = s.len - k + 1;

@@ -1,0 +1,9 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests/test_cli_gpu.py tests/test_gpu_parity.py tests/test_full_size.py -m gpu -q -x ) > gpurun_out/r2_c17_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2_c17_pytest.log
+VAR_GENOME=64000000 VAR_COVERAGE=30 VAR_ITERS=4 timeout 600 python tools/p3_variants.py main > gpurun_out/r2_c17_variants_c3.txt 2>&1
+timeout 300 python tools/p3_variants.py main > gpurun_out/r2_c17_variants_c2.txt 2>&1
+timeout 600 python tools/cli_timing.py 3 > gpurun_out/r2_c17_cli_timing.txt 2>&1
+echo done
