@@ -316,6 +316,8 @@ int main(int argc, char* argv[]) {
             std::cerr.flush();
             _exit(0);
         }
+        file.reset();
+        timer.mark("parsed input released");
     } catch (const std::exception& e) {
         std::cerr << put_now << " Error: " << e.what() << std::endl;
         return 1;

@@ -21,6 +21,20 @@
 
 namespace kbbq {
 
+void* big_alloc(size_t bytes) {
+    const size_t huge = (size_t)2 << 20;
+    void* p = nullptr;
+    if (bytes >= 2 * huge) {
+        const size_t rounded = (bytes + huge - 1) & ~(huge - 1);
+        if (posix_memalign(&p, huge, rounded) != 0) p = nullptr;
+        if (p) madvise(p, rounded, MADV_HUGEPAGE);
+    } else {
+        p = std::malloc(std::max<size_t>(bytes, 1));
+    }
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+
 void throw_last(int rc) {
     const std::string msg = kbbq_last_error();
     if (rc == KBBQ_ENOMEM) throw std::bad_alloc();
@@ -92,9 +106,21 @@ void Session::wait_contexts() const {
 }
 Session::~Session() {
     try { wait_contexts(); } catch (...) {}
+    const bool timing = getenv("KBBQ_HOST_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::cerr << "[host] session teardown: " << what << " " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " ms" << std::endl;
+        t0 = t1;
+    };
     for (SessionBatch& b : batches_)
         if (b.dev) kbbq_batch_free(ctx_[b.gpu], b.dev);
+    mark("batches freed");
     for (kbbq_ctx* c : ctx_) kbbq_ctx_destroy(c);
+    mark("contexts destroyed");
+    batches_.clear();
+    mark("host copies released");
     if (g_current == this) g_current = nullptr;
 }
 

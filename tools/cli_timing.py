@@ -21,10 +21,11 @@ def main():
             rs = api.synth_host(bench.synth_params(G, 1000), 0, n, n_threads=os.cpu_count() or 1)
             fq, out = os.path.join(d, label + ".fq"), os.path.join(d, "out.gz")
             bench.write_fastq(fq, rs)
-            for extra in ({}, {"KBBQ_CLEAN_EXIT": "1"}):
+            for extra in ({}, {"KBBQ_CLEAN_EXIT": "1"}, {"KBBQ_BGZF_LEVEL": "huff"}):
                 for i in range(runs):
                     env = dict(os.environ, KBBQ_HOST_TIMING="1", **extra)
-                    env.pop("KBBQ_BGZF_LEVEL", None)
+                    if "KBBQ_BGZF_LEVEL" not in extra:
+                        env.pop("KBBQ_BGZF_LEVEL", None)
                     t0 = time.perf_counter()
                     with open(out, "wb") as fo:
                         r = subprocess.run([cli, "--seed", "7", "-k", "32", "-g", str(G), "-c", str(cov), fq], stdout=fo, stderr=subprocess.PIPE, env=env)
