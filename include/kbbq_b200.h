@@ -205,9 +205,11 @@ int kbbq_covariates_upload(kbbq_ctx* ctx, const uint64_t* rgc, const uint64_t* q
 
 /* ---- batches -------------------------------------------------------------------------------------------------------- */
 int kbbq_batch_upload(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
-/* Same, but the quality array (3/4 of the bytes) is copied on a side stream and may still be in flight on return:
- * pass 1 does not read it and overlaps the copy; passes 2-4 wait for it on the device.  host->qual must stay valid and
- * unmodified until kbbq_sync() has returned (with pinned memory the copy is truly asynchronous). */
+/* Same, but the quality masks (when the host brings them) and the quality array -- 3/4 of the bytes -- are copied on a
+ * side stream behind everything else and may still be in flight on return: pass 1 reads neither and overlaps the copies,
+ * pass 2 waits on the device for the masks, passes 3-4 for the qualities.  host->qmask and host->qual must stay valid
+ * and unmodified until kbbq_batch_wait() or kbbq_sync() has returned (with pinned memory the copies are truly
+ * asynchronous). */
 int kbbq_batch_upload_async(kbbq_ctx* ctx, const kbbq_batch* host, kbbq_dbatch** out);
 /* Same, but EVERY array travels on the side stream and nothing is waited for: the call returns as soon as the copies
  * are queued, the passes wait for them on the device, and the upload of the next batch overlaps the passes of this one

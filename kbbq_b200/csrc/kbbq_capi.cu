@@ -1733,7 +1733,11 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
     if (!b || b->k != ctx->k) return fail(KBBQ_EINVAL, "batch was uploaded for another k");
     if (!b->d_err_bits) CU(cudaMallocAsync(&b->d_err_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
     if (!b->d_mod) CU(cudaMallocAsync(&b->d_mod, std::max<size_t>(b->n_reads, 1) * 4, ctx->stream));
-    if (int rc = need_quals(ctx, b)) return rc;
+    // the scan reads bases and N masks only: after kbbq_batch_upload_async it runs while the last of the qualities are
+    // still crossing the link, and the wait for them sits between the scan and the repairs (a streamed batch has
+    // everything behind one event)
+    if (b->all_on_copy)
+        if (int rc = need_quals(ctx, b)) return rc;
     pass_begin(ctx);
     if (b->n_reads) {
         if (!b->d_tflags) CU(cudaMallocAsync(&b->d_tflags, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
@@ -1757,6 +1761,7 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
             pass3_scan_kernel<false, false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
         if (int rc = check_launch(ctx, "pass3_scan_kernel")) return rc;
+        if (int rc = need_quals(ctx, b)) return rc;
         mark_kernel(ctx, "pass3_repair_kernel");
         pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
             b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1);
