@@ -89,6 +89,9 @@ int kbbq_device_warmup(int device);
 int kbbq_host_alloc(size_t bytes, void** out);
 void kbbq_host_free(void* p);
 int kbbq_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes);
+/* Give back everything this process holds on `device` (cached pool memory, the primary context).  Optional; every
+ * kbbq_ctx of the device must have been destroyed and every pinned array freed. */
+int kbbq_device_reset(int device);
 
 /* ---- host-only helpers (no GPU needed) ------------------------------------------------------------------------ */
 /* bloom::Bloom ctor geometry; KBBQ_EINVAL where the reference throws (bloom.cc:18-21) */

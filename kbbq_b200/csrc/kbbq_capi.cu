@@ -560,6 +560,11 @@ int kbbq_host_alloc(size_t bytes, void** out) {
 void kbbq_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
+int kbbq_device_reset(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return fail(KBBQ_ECUDA, "no such device");
+    CU(cudaDeviceReset());
+    return KBBQ_OK;
+}
 int kbbq_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes) {
     if (cudaSetDevice(device) != cudaSuccess) return fail(KBBQ_ECUDA, "no such device");
     size_t f = 0, t = 0;

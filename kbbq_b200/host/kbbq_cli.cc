@@ -312,6 +312,14 @@ int main(int argc, char* argv[]) {
         // Everything is written.  What is left is handing back gigabytes of parsed input, pinned buffers and the CUDA
         // contexts one destructor at a time, which the kernel does in one sweep at process exit anyway
         // (KBBQ_CLEAN_EXIT=1 runs the destructors, for leak checkers).
+        if (const char* em = getenv("KBBQ_EXIT_MODE")) {  // measurement: what the kernel's teardown at exit is made of
+            const int mode = atoi(em);
+            if (mode & 1) { file.reset(); timer.mark("exit probe: parsed input released"); }
+            if (mode & 2) { session.release(); timer.mark("exit probe: batches and contexts released"); }
+            if (mode & 4) { for (int d : devices) kbbq_device_reset(d); timer.mark("exit probe: devices reset"); }
+            std::cerr.flush();
+            _exit(0);
+        }
         if (!getenv("KBBQ_CLEAN_EXIT")) {
             std::cerr.flush();
             _exit(0);

@@ -104,7 +104,8 @@ void Session::wait_contexts() const {
     std::shared_future<void> f = ready_;  // a copy per caller: get() on one object from several threads is not allowed
     f.get();                              // rethrows what the creation threw, every time
 }
-Session::~Session() {
+Session::~Session() { release(); }
+void Session::release() {
     try { wait_contexts(); } catch (...) {}
     const bool timing = getenv("KBBQ_HOST_TIMING") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
@@ -118,6 +119,7 @@ Session::~Session() {
         if (b.dev) kbbq_batch_free(ctx_[b.gpu], b.dev);
     mark("batches freed");
     for (kbbq_ctx* c : ctx_) kbbq_ctx_destroy(c);
+    ctx_.clear();
     mark("contexts destroyed");
     batches_.clear();
     mark("host copies released");

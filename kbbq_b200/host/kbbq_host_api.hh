@@ -179,6 +179,7 @@ public:
     Session(int k, int n_rg, int max_cycle, const std::vector<int>& devices, bool background = false);
     ~Session();
     Session(const Session&) = delete;
+    void release();  // frees the batches and destroys the contexts now (what the destructor does)
     int n_gpus() const { return (int)devices_.size(); }
     kbbq_ctx* ctx(int g = 0) const { wait_contexts(); return ctx_[g]; }
     const std::vector<kbbq_ctx*>& contexts() const { wait_contexts(); return ctx_; }

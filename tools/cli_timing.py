@@ -21,7 +21,10 @@ def main():
             rs = api.synth_host(bench.synth_params(G, 1000), 0, n, n_threads=os.cpu_count() or 1)
             fq, out = os.path.join(d, label + ".fq"), os.path.join(d, "out.gz")
             bench.write_fastq(fq, rs)
-            for extra in ({}, {"KBBQ_CLEAN_EXIT": "1"}, {"KBBQ_BGZF_LEVEL": "huff"}):
+            variants = ({}, {"KBBQ_CLEAN_EXIT": "1"}, {"KBBQ_BGZF_LEVEL": "huff"})
+            if os.environ.get("CLI_TIMING_EXIT_MODES"):  # what the teardown at exit is made of (KBBQ_EXIT_MODE bits: 1 host, 2 contexts, 4 reset)
+                variants = ({},) + tuple({"KBBQ_EXIT_MODE": m} for m in os.environ["CLI_TIMING_EXIT_MODES"].split(","))
+            for extra in variants:
                 for i in range(runs):
                     env = dict(os.environ, KBBQ_HOST_TIMING="1", **extra)
                     if "KBBQ_BGZF_LEVEL" not in extra:
