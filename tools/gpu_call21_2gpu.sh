@@ -6,4 +6,5 @@ mkdir -p gpurun_out
 echo "pytest rc=$?" >> gpurun_out/r2_c21_pytest.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_c21_bench_n2.json 2> gpurun_out/r2_c21_bench_n2.err
 echo "bench n2 rc=$?" >> gpurun_out/r2_c21_bench_n2.err
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --no-file-leg > gpurun_out/r2_c21_bench_c3.json 2> gpurun_out/r2_c21_bench_c3.err
 echo done
