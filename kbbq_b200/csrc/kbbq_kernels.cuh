@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t coop_probe_impl(const unsigned long long* __
 #pragma unroll
         for (int i = 0; i < ROUNDS_AT_ONCE; ++i) {  // issue every load of the group before using any
             const int src = 8 * (r0 + i) + grp;
-            const uint64_t b = __shfl_sync(KBBQ_FULL, blk, src);
+            const uint64_t b = __shfl_sync(KBBQ_FULL, (uint32_t)blk, src);  // a block number is a 32-bit hash reduced (bloom_block)
             const uint32_t p = __shfl_sync(KBBQ_FULL, pat, src);
             v[i] = (vmask >> src) & 1u;
             x[i] = make_uint4(0, 0, 0, 0);
@@ -155,7 +155,7 @@ __device__ __forceinline__ void coop_probe_pair(const unsigned long long* __rest
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int src = 8 * (i & 3) + grp;
-        const uint64_t b = __shfl_sync(KBBQ_FULL, i < 4 ? blkA : blkB, src);
+        const uint64_t b = __shfl_sync(KBBQ_FULL, (uint32_t)(i < 4 ? blkA : blkB), src);
         pn[i] = __shfl_sync(KBBQ_FULL, i < 4 ? patA : patB, src);
         v[i] = ((i < 4 ? vmaskA : vmaskB) >> src) & 1u;
         x[i] = make_uint4(0, 0, 0, 0);
@@ -1007,7 +1007,10 @@ __device__ __noinline__ uint32_t probe_ballot(const BloomView* f, bool valid, ui
 __device__ __noinline__ uint32_t probe_coop_ballot(const BloomView* f, bool valid, uint64_t key) {
     const uint32_t vmask = __ballot_sync(KBBQ_FULL, valid);
     if (vmask == 0) return 0;
-    return coop_probe_impl<2>(f->words, f->patterns, valid ? bloom_block(*f, key) : 0, valid ? bloom_pattern(*f, key) : 0, vmask);
+#ifndef KBBQ_P3R_COOP_ROUNDS
+#define KBBQ_P3R_COOP_ROUNDS 2
+#endif
+    return coop_probe_impl<KBBQ_P3R_COOP_ROUNDS>(f->words, f->patterns, valid ? bloom_block(*f, key) : 0, valid ? bloom_pattern(*f, key) : 0, vmask);
 }
 struct DevQuery {
     const BloomView* f;  // in shared memory: a kernel parameter has no address an out-of-line function could take
