@@ -32,7 +32,9 @@ extern "C" {
 #define KBBQ_FILTER_SAMPLED 0 /* `subsampled` in kbbq.cc:265 */
 #define KBBQ_FILTER_TRUSTED 1 /* `trusted`    in kbbq.cc:266 */
 #define KBBQ_DEFAULT_BLOOM_SEED 0xA5A5A5A55A5A5A5AULL /* bloom.hh:389 */
-#define KBBQ_ABI_MAX_READ_LEN 512
+/* longest read a batch may hold.  Reads of up to 512 bases run from statically sized shared-memory scratch; a batch with
+ * a longer read is routed to slower instantiations whose scratch is sized for it at launch. */
+#define KBBQ_ABI_MAX_READ_LEN 65535
 
 typedef struct kbbq_ctx kbbq_ctx;       /* one GPU: stream, filters, count tables, model tables */
 typedef struct kbbq_dbatch kbbq_dbatch; /* a read batch resident in device memory */

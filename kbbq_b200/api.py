@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("KBBQ_B200_LIB", os.path.join(_HERE, "libkbbq_b200.so"
 FILTER_SAMPLED = 0
 FILTER_TRUSTED = 1
 DEFAULT_BLOOM_SEED = 0xA5A5A5A55A5A5A5A
-MAX_READ_LEN = 512
+MAX_READ_LEN = 65535
 NQ = 94
 
 

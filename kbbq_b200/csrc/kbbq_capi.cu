@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(256) synth_reads_kernel(SynthSpec s, unsigned 
 namespace {
 int synth_spec(const kbbq_synth_params* p, SynthSpec& s) {
     if (!p) return fail(KBBQ_EINVAL, "null synth parameters");
-    if (p->read_len < 1 || p->read_len > KBBQ_MAX_READ_LEN || p->genome_len < p->read_len || p->n_rg < 1 || p->n_rg > 65535 ||
+    if (p->read_len < 1 || p->read_len > KBBQ_ABI_MAX_READ_LEN || p->genome_len < p->read_len || p->n_rg < 1 || p->n_rg > 65535 ||
         !(p->err_scale >= 0))
         return fail(KBBQ_EINVAL, "bad synth parameters");
     s.seed = p->seed; s.genome_seed = p->genome_seed; s.genome_len = p->genome_len; s.read_len = p->read_len; s.n_rg = p->n_rg;
@@ -637,7 +637,7 @@ int kbbq_pack_size(uint64_t n, const uint64_t* off, uint64_t* n_words, uint32_t*
     uint32_t ml = 0;
     for (uint64_t r = 0; r < n; ++r) {
         const uint64_t len = off[r + 1] - off[r];
-        if (len > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
+        if (len > KBBQ_ABI_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
         words += (len + 31) / 32;
         ml = std::max<uint32_t>(ml, (uint32_t)len);
     }
@@ -652,7 +652,7 @@ int kbbq_pack_reads(uint64_t n, const char* seq, const uint64_t* off, const uint
     uint64_t words = 0;
     for (uint64_t r = 0; r < n; ++r) {
         const uint64_t l = off[r + 1] - off[r];
-        if (l > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
+        if (l > KBBQ_ABI_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
         word_off[r] = (uint32_t)words;
         len[r] = (uint32_t)l;
         words += (l + 31) / 32;
@@ -734,7 +734,10 @@ int kbbq_ctx_create(int device, int k, int n_rg, int max_cycle, kbbq_ctx** out) 
     if (!out) return fail(KBBQ_EINVAL, "null output");
     if (k < 1 || k > KBBQ_MAX_K) return fail(KBBQ_EINVAL, "Error: k must be <= 32 and > 0.");
     if (n_rg < 1 || n_rg > 65535) return fail(KBBQ_EINVAL, "n_rg out of range");
-    if (max_cycle < 1 || max_cycle > KBBQ_MAX_READ_LEN) return fail(KBBQ_EINVAL, "max_cycle out of range");
+    if (max_cycle < 1 || max_cycle > KBBQ_ABI_MAX_READ_LEN) return fail(KBBQ_EINVAL, "max_cycle out of range");
+    // the kernels index the model and count tables with 32-bit offsets
+    if ((unsigned long long)n_rg * KBBQ_NQ * 2ull * (unsigned long long)max_cycle >= (1ull << 31))
+        return fail(KBBQ_ERANGE, "n_rg x max_cycle too large for the model tables");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -1360,7 +1363,7 @@ int kbbq_batch_wait(kbbq_ctx* ctx, const kbbq_dbatch* b) {
 static int batch_upload(kbbq_ctx* ctx, const kbbq_batch* h, kbbq_dbatch** out, int mode) {
     if (int rc = use(ctx)) return rc;
     if (!h || !out) return fail(KBBQ_EINVAL, "null argument");
-    if (h->max_len > KBBQ_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
+    if (h->max_len > KBBQ_ABI_MAX_READ_LEN) return fail(KBBQ_ERANGE, "read longer than KBBQ_ABI_MAX_READ_LEN");
     if ((int)h->max_len > ctx->max_cycle) return fail(KBBQ_ERANGE, "read longer than the context's max_cycle");
     const uint32_t n = h->n_reads;
     kbbq_dbatch* b = new (std::nothrow) kbbq_dbatch();
@@ -1685,11 +1688,24 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
         const bool use_known = getenv("KBBQ_NO_KNOWN_BITS") == nullptr;
         const uint32_t* known = use_known && b->d_sample_bits && b->sample_epoch == ctx->epoch[KBBQ_FILTER_SAMPLED] ? b->d_sample_bits : nullptr;
         if (use_known && !b->d_ins_bits) CU(cudaMallocAsync(&b->d_ins_bits, std::max<size_t>(b->n_words, 1) * 4, ctx->stream));
-        const bool shared_hash = sv.salt0 == tv.salt0 && sv.salt1 == tv.salt1 && !getenv("KBBQ_P2_SEPARATE_HASH");
+        // a batch with a read beyond KBBQ_MAX_READ_LEN (the statically sized masks): masks in dynamic shared memory, no
+        // parked hashes (8 bytes per k-mer and warp would not fit)
+        const bool long_batch = b->max_len > KBBQ_MAX_READ_LEN;
+        const int maxw = ((int)b->max_len + 31) / 32;
+        const bool shared_hash = !long_batch && sv.salt0 == tv.salt0 && sv.salt1 == tv.salt1 && !getenv("KBBQ_P2_SEPARATE_HASH");
         const int max_kmers = std::max(1, (int)b->max_len - ctx->k + 1);
-        const size_t smem = (shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0) + (mode == INS_STAGED ? st.smem() : 0);
+        const size_t smem = (shared_hash ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2) : 0) + (mode == INS_STAGED ? st.smem() : 0) +
+                            (long_batch ? (size_t)KBBQ_WARPS_PER_BLOCK * 2 * (maxw + 1) * sizeof(uint32_t) : 0);
+        if (smem > 200 * 1024) return fail(KBBQ_ERANGE, "read too long for pass 2's shared-memory masks");
         const int threads = KBBQ_WARPS_PER_BLOCK * 32;
-#define P2_LAUNCH(M, S) pass2_trusted_kernel<M, S, PF><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo, sink, max_kmers, known, b->d_ins_bits)
+#define P2_LAUNCH_L(M, S, L)                                                                                                         \
+    do {                                                                                                                            \
+        if (smem > 48 * 1024)                                                                                                       \
+            CU(cudaFuncSetAttribute(pass2_trusted_kernel<M, S, PF, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        pass2_trusted_kernel<M, S, PF, L><<<grid, threads, smem, ctx->stream>>>(b->view(), sv, tv, ctx->k, ctx->d_thresholds, eo,   \
+                                                                               sink, max_kmers, known, b->d_ins_bits, maxw);        \
+    } while (0)
+#define P2_LAUNCH(M, S) P2_LAUNCH_L(M, S, false)
         // KBBQ_P2_DEEP=1 (measurement): two queries in flight per warp (QMODE 2).  It wins 7 % in pass 3's scan, which is
         // latency bound at 40 % issue utilisation; this kernel is at 60 % and spills at 64 registers with 64 probes in flight:
         // 43.8 -> 50.0 ms on the config-3 shape, so it stays off here.
@@ -1713,6 +1729,11 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
             if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, true);
             else if (mode == INS_TEST_FIRST) P2_LAUNCH(INS_TEST_FIRST, true);
             else P2_LAUNCH(INS_DIRECT, true);
+        } else if (long_batch) {
+            constexpr int PF = 0;
+            if (mode == INS_STAGED) P2_LAUNCH_L(INS_STAGED, false, true);
+            else if (mode == INS_TEST_FIRST) P2_LAUNCH_L(INS_TEST_FIRST, false, true);
+            else P2_LAUNCH_L(INS_DIRECT, false, true);
         } else {
             constexpr int PF = 0;
             if (mode == INS_STAGED) P2_LAUNCH(INS_STAGED, false);
@@ -1720,6 +1741,7 @@ int kbbq_pass2_find_trusted(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_
             else P2_LAUNCH(INS_DIRECT, false);
         }
 #undef P2_LAUNCH
+#undef P2_LAUNCH_L
         if (int rc = check_launch(ctx, "pass2_trusted_kernel")) return rc;
         if (mode == INS_STAGED) {
             if (int rc = staging_apply(ctx, KBBQ_FILTER_TRUSTED, st)) return rc;
@@ -1756,7 +1778,7 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         // KBBQ_PREFETCH=1 (measurement; off because it loses, see pass 2).
         const bool big = ctx->filt[KBBQ_FILTER_TRUSTED].geom.table_bits / 8 > (size_t)ctx->l2_bytes * 3 / 4;
         const char* deep_env = getenv("KBBQ_SCAN_DEEP");
-        if (big && getenv("KBBQ_PREFETCH"))
+        if (big && getenv("KBBQ_PREFETCH") && b->max_len <= KBBQ_MAX_READ_LEN)
             pass3_scan_kernel<true, false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers * sizeof(uint2), ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, known, max_kmers);
         else if (deep_env ? atoi(deep_env) != 0 : big)
@@ -1768,8 +1790,20 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         if (int rc = check_launch(ctx, "pass3_scan_kernel")) return rc;
         if (int rc = need_quals(ctx, b)) return rc;
         mark_kernel(ctx, "pass3_repair_kernel");
-        pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-            b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1);
+        if (b->max_len <= KBBQ_MAX_READ_LEN) {
+            pass3_repair_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1, KBBQ_MAXW);
+        } else {  // long reads: the scratch is cut from dynamic shared memory, as many warps per block as fit
+            const int maxw = ((int)b->max_len + 31) / 32;
+            const size_t per_warp = ErrScratchDyn::bytes(maxw);
+            const int warps = (int)std::max<size_t>(1, std::min<size_t>(KBBQ_WARPS_PER_BLOCK, (200 * 1024) / per_warp));
+            const size_t smem = per_warp * warps;
+            if (smem > 220 * 1024) return fail(KBBQ_ERANGE, "read too long for the error caller's shared-memory scratch");
+            CU(cudaFuncSetAttribute(pass3_repair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long blocks = std::max(1ll, std::min(((long long)b->n_reads + warps - 1) / warps, (long long)ctx->sm_count * 4));
+            pass3_repair_kernel<true><<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(
+                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1, maxw);
+        }
         if (int rc = check_launch(ctx, "pass3_repair_kernel")) return rc;
         mark_kernel(ctx, "covariate_count_kernel");
         if (int rc = launch_count(ctx, b, b->d_err_bits, b->d_mod, b->n_reads)) return rc;

@@ -60,21 +60,37 @@ struct ErrScratch {
     uint32_t FQ[KBBQ_MAXW + 1];     // ... and those of them with qual <= 6
 };
 
+// The same scratch with its arrays somewhere else: reads longer than KBBQ_MAX_READ_LEN get theirs cut from dynamic shared
+// memory sized for the batch's longest read (pass3_repair_kernel<true>); every array holds maxw + 1 words.
+struct ErrScratchDyn {
+    unsigned long long *P_w, *A_w, *C_w;
+    uint32_t *P_nm, *A_nm, *C_nm, *O_nm, *T_orig, *T_cur, *E, *QL, *F, *FQ;
+    static KBBQ_HD size_t bytes(int maxw) { return (size_t)(maxw + 1) * (3 * 8 + 10 * 4); }
+    KBBQ_HD void carve(void* base, int maxw) {
+        const size_t n = (size_t)maxw + 1;
+        unsigned long long* w = static_cast<unsigned long long*>(base);
+        P_w = w; A_w = w + n; C_w = w + 2 * n;
+        uint32_t* u = reinterpret_cast<uint32_t*>(w + 3 * n);
+        P_nm = u; A_nm = u + n; C_nm = u + 2 * n; O_nm = u + 3 * n; T_orig = u + 4 * n; T_cur = u + 5 * n;
+        E = u + 6 * n; QL = u + 7 * n; F = u + 8 * n; FQ = u + 9 * n;
+    }
+};
+
 struct ErrResult {
     int mod_idx;   // ref quirk: the all-trusted early return after correct_one leaves the corrected base in seq
     int mod_base;  // (readutils.cc:263-265 vs 568); -1 when seq ends up equal to the input
 };
 
-template <class Q>
+template <class Q, class SC = ErrScratch>
 struct ErrCaller {
     Q q;  // held by value: on the device it is one pointer, and nothing here may force the caller's state into memory
     const int k;
     const uint8_t* qual;  // qualities of the top-level read (only correct_one's tie-break reads them)
-    ErrScratch& sc;
+    SC& sc;
     const uint32_t* T = nullptr;  // cached trusted flags of the running call's sequence (see cached_run)
     bool T_mirrored = false;
     const bool has_n;  // false: the read holds no non-ACGT base (nor does anything derived from it): key building skips the N masks
-    KBBQ_HD ErrCaller(Q q_, int k_, const uint8_t* qual_, ErrScratch& sc_, bool has_n_ = true)
+    KBBQ_HD ErrCaller(Q q_, int k_, const uint8_t* qual_, SC& sc_, bool has_n_ = true)
         : q(q_), k(k_), qual(qual_), sc(sc_), has_n(has_n_) {}
 
     // THE probe routine.  Lane t asks about the k-mer of s starting at j0 + t*stride with base p replaced:

@@ -493,27 +493,31 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
         const unsigned long long so = b.slot_off[r];
         // the sampled positions first (a bit test and a ballot per 32 slots), then keys for those only, 32 at a time:
         // at alpha = 7/30 a 150-base read has 28 of them -- one dense round instead of four quarter-full ones
-        int total = 0;
-        for (int j0 = 0; j0 < nk; j0 += 32) {
-            const int j = j0 + lane;
-            bool hit = false;
-            if (j < nk) {
-                const unsigned long long slot = so + (unsigned)j;
-                hit = (__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u;
+        // (a read longer than the list goes through in pieces of KBBQ_MAX_READ_LEN slots)
+        for (int c0 = 0; c0 < nk; c0 += KBBQ_MAX_READ_LEN) {
+            const int c1 = nk - c0 < KBBQ_MAX_READ_LEN ? nk : c0 + KBBQ_MAX_READ_LEN;
+            int total = 0;
+            for (int j0 = c0; j0 < c1; j0 += 32) {
+                const int j = j0 + lane;
+                bool hit = false;
+                if (j < c1) {
+                    const unsigned long long slot = so + (unsigned)j;
+                    hit = (__ldg(sample_bits + (slot >> 5)) >> (slot & 31)) & 1u;
+                }
+                const uint32_t m = __ballot_sync(KBBQ_FULL, hit);
+                if (hit) pos[total + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(j - c0);
+                total += __popc(m);
             }
-            const uint32_t m = __ballot_sync(KBBQ_FULL, hit);
-            if (hit) pos[total + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
-            total += __popc(m);
+            __syncwarp();
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                uint64_t key = 0;
+                const bool ins = t < total && kmer_key(s, c0 + (int)pos[t], k, 0, -1, key);  // an invalid k-mer still consumed its draw
+                if (MODE == INS_STAGED) inserted += warp_stage_insert(f, sink, sstate, sovf, ins, key);
+                else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(f, ins, key, stage);
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        for (int t0 = 0; t0 < total; t0 += 32) {
-            const int t = t0 + lane;
-            uint64_t key = 0;
-            const bool ins = t < total && kmer_key(s, (int)pos[t], k, 0, -1, key);  // an invalid k-mer still consumed its draw
-            if (MODE == INS_STAGED) inserted += warp_stage_insert(f, sink, sstate, sovf, ins, key);
-            else inserted += warp_bloom_insert<MODE == INS_TEST_FIRST>(f, ins, key, stage);
-        }
-        __syncwarp();
     }
     if (MODE == INS_STAGED) block_stage_close(sink, sstate);
     if (lane == 0 && inserted) atomicAdd(f.inserted, inserted);
@@ -529,22 +533,30 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
 // QMODE (with SHARED_HASH; `sampled` lives in HBM): 0 = one 32-k-mer query at a time; 2 = two at a time, all 64 block loads
 // in flight together (coop_probe_pair); 1 = hash every k-mer and prefetch its block first, probe afterwards (prefetch_l2:
 // measured, loses, kept as a dead end).
-template <int MODE, bool SHARED_HASH, int QMODE>
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P2_MIN_BLOCKS)
+// LONG: a batch whose longest read exceeds KBBQ_MAX_READ_LEN (maxw > KBBQ_MAXW words): the presence and error masks
+// then live at the end of the dynamic shared memory, maxw + 1 words each per warp (launched without SHARED_HASH).
+template <int MODE, bool SHARED_HASH, int QMODE, bool LONG = false>
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, LONG ? 1 : KBBQ_P2_MIN_BLOCKS)
 pass2_trusted_kernel(BatchView b, BloomView sampled, BloomView trusted, int k, const int* __restrict__ thresholds,
                      uint32_t* __restrict__ err_out, StageSink sink, int max_kmers, const uint32_t* __restrict__ known_bits,
-                     uint32_t* __restrict__ ins_out) {
+                     uint32_t* __restrict__ ins_out, int maxw) {
     extern __shared__ uint2 p2_hash[];  // [warps][max_kmers]: .x = hash_ap8(key, salt0), .y = pattern (0xFFFFFFFF: invalid k-mer)
     __shared__ int thr[KBBQ_MAX_K + 1];
-    __shared__ uint32_t Pm_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
-    __shared__ uint32_t Em_all[KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
+    __shared__ uint32_t Pm_all[LONG ? 1 : KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
+    __shared__ uint32_t Em_all[LONG ? 1 : KBBQ_WARPS_PER_BLOCK][KBBQ_MAXW + 1];
     __shared__ InsertStage stage_all[KBBQ_WARPS_PER_BLOCK];
     InsertStage& stage = stage_all[threadIdx.x >> 5];
     if (threadIdx.x <= k) thr[threadIdx.x] = thresholds[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t* Pm = Pm_all[wib];
-    uint32_t* Em = Em_all[wib];
+    uint32_t* Pm = Pm_all[LONG ? 0 : wib];
+    uint32_t* Em = Em_all[LONG ? 0 : wib];
+    if (LONG) {  // behind the hashes (none: no SHARED_HASH) and the staging state
+        uint32_t* masks = reinterpret_cast<uint32_t*>(p2_hash + (SHARED_HASH ? (size_t)KBBQ_WARPS_PER_BLOCK * max_kmers : 0)) +
+                          (MODE == INS_STAGED ? 3 * (size_t)sink.n_buckets : 0);
+        Pm = masks + (size_t)wib * 2 * (maxw + 1);
+        Em = Pm + (maxw + 1);
+    }
     uint2* HP = p2_hash + (size_t)wib * (SHARED_HASH ? max_kmers : 0);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long inserted = 0;
@@ -986,7 +998,7 @@ pass3_scan_kernel(BatchView b, BloomView trusted, int k, uint32_t* __restrict__ 
         }
         // fewer than k bases (out of contract in the reference, bloom.cc:30): untouched, like a clean read
         if (all_trusted || nk <= 0) {
-            if (lane < nw) err_out[wo + lane] = 0u;
+            for (int w = lane; w < nw; w += 32) err_out[wo + w] = 0u;
             if (lane == 0) mod_out[r] = 0xFFFFFFFFu;
         } else if (lane == 0) {
             repair_list[atomicAdd(repair_count, 1u)] = r;
@@ -1054,18 +1066,14 @@ struct DevQuery {
 #ifndef KBBQ_P3R_MIN_BLOCKS
 #define KBBQ_P3R_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3R_MIN_BLOCKS)
-pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
-                    uint32_t* __restrict__ mod_out, const uint32_t* __restrict__ repair_list,
-                    const unsigned int* __restrict__ repair_count, unsigned int* __restrict__ work_counter) {
-    __shared__ ErrScratch scratch[KBBQ_WARPS_PER_BLOCK];
-    __shared__ BloomView filter;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    ErrScratch& sc = scratch[wib];
-    if (threadIdx.x == 0) filter = trusted;
-    __syncthreads();
-    DevQuery q{&filter};
-    const uint32_t n_list = *repair_count;
+// LONG: a batch whose longest read exceeds KBBQ_MAX_READ_LEN.  The scratch then comes from dynamic shared memory,
+// ErrScratchDyn::bytes(maxw) per warp, and the block has as many warps as fit (the launch decides: 8 down to 1).
+template <bool LONG, class SC>
+__device__ __forceinline__ void repair_reads(SC& sc, const BatchView& b, DevQuery q, int k, const uint32_t* __restrict__ tflags,
+                                             uint32_t* __restrict__ err_out, uint32_t* __restrict__ mod_out,
+                                             const uint32_t* __restrict__ repair_list, uint32_t n_list,
+                                             unsigned int* __restrict__ work_counter) {
+    const int lane = threadIdx.x & 31;
     for (;;) {
         // reads differ a lot in cost (a single repair to ~1000 probes): pull, don't stride
         uint32_t idx = 0;
@@ -1077,23 +1085,51 @@ pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __res
         const uint32_t wo = b.word_off[r];
         const int nw = (len + 31) >> 5;
         const uint8_t* qual = b.qual + (size_t)wo * 32;
-        if (lane <= nw) {
-            sc.P_w[lane] = lane < nw ? b.bases[wo + lane] : 0ull;
-            sc.P_nm[lane] = lane < nw ? b.nmask[wo + lane] : 0u;
-            sc.E[lane] = 0;
-            sc.T_orig[lane] = 32 * lane < len - k + 1 ? tflags[wo + lane] : 0u;  // the scan wrote one word per 32 k-mers
+        bool any_n = false;
+        for (int w = lane; w <= nw; w += 32) {  // one trip for reads of up to 31 words
+            sc.P_w[w] = w < nw ? b.bases[wo + w] : 0ull;
+            const uint32_t nm = w < nw ? b.nmask[wo + w] : 0u;
+            sc.P_nm[w] = nm;
+            any_n = any_n || nm != 0u;
+            sc.E[w] = 0;
+            sc.T_orig[w] = 32 * w < len - k + 1 ? tflags[wo + w] : 0u;  // the scan wrote one word per 32 k-mers
             // low-quality flags for the overcorrection half weight (bits past the read's end cleared)
-            const int left = len - 32 * lane;
-            sc.QL[lane] = lane < nw ? b.qmask[wo + lane].y & (left >= 32 ? ~0u : ((1u << left) - 1u)) : 0u;
+            const int left = len - 32 * w;
+            sc.QL[w] = w < nw ? b.qmask[wo + w].y & (left >= 32 ? ~0u : ((1u << left) - 1u)) : 0u;
+            if (!LONG) break;
         }
         __syncwarp();
-        const bool has_n = __any_sync(KBBQ_FULL, lane < nw && sc.P_nm[lane] != 0u);
-        ErrCaller<DevQuery> ec(q, k, qual, sc, has_n);
+        const bool has_n = __any_sync(KBBQ_FULL, any_n);
+        ErrCaller<DevQuery, SC> ec(q, k, qual, sc, has_n);
         const ErrResult res = ec.run(len, true);
         __syncwarp();
-        if (lane < nw) err_out[wo + lane] = sc.E[lane];
+        for (int w = lane; w < nw; w += 32) {
+            err_out[wo + w] = sc.E[w];
+            if (!LONG) break;
+        }
         if (lane == 0) mod_out[r] = res.mod_idx >= 0 ? (uint32_t)(4 * res.mod_idx + res.mod_base) : 0xFFFFFFFFu;
         __syncwarp();
+    }
+}
+template <bool LONG>
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, LONG ? 1 : KBBQ_P3R_MIN_BLOCKS)
+pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
+                    uint32_t* __restrict__ mod_out, const uint32_t* __restrict__ repair_list,
+                    const unsigned int* __restrict__ repair_count, unsigned int* __restrict__ work_counter, int maxw) {
+    extern __shared__ __align__(16) unsigned char repair_dyn[];  // LONG: [warps of the block][ErrScratchDyn::bytes(maxw)]
+    __shared__ ErrScratch scratch[LONG ? 1 : KBBQ_WARPS_PER_BLOCK];
+    __shared__ BloomView filter;
+    const int wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) filter = trusted;
+    __syncthreads();
+    DevQuery q{&filter};
+    const uint32_t n_list = *repair_count;
+    if constexpr (LONG) {
+        ErrScratchDyn sc;
+        sc.carve(repair_dyn + (size_t)wib * ErrScratchDyn::bytes(maxw), maxw);
+        repair_reads<true>(sc, b, q, k, tflags, err_out, mod_out, repair_list, n_list, work_counter);
+    } else {
+        repair_reads<false>(scratch[wib], b, q, k, tflags, err_out, mod_out, repair_list, n_list, work_counter);
     }
 }
 

@@ -6,6 +6,7 @@
 // exercised by the `-m gpu` tests.
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../kbbq_b200/csrc/kbbq_core.cuh"
 #include "../../kbbq_b200/csrc/kbbq_errcall.cuh"
@@ -107,7 +108,8 @@ void emu_pass2(uint32_t n, const uint64_t* bases, const uint32_t* nmask, const u
         const uint32_t wo = word_off[r];
         CSeq s{(const unsigned long long*)bases + wo, nmask + wo, L};
         const uint8_t* q = qual + (size_t)wo * 32;
-        uint32_t Pm[KBBQ_MAXW + 1] = {0}, Em[KBBQ_MAXW + 1] = {0};
+        std::vector<uint32_t> Pm_v((size_t)(L + 31) / 32 + 2, 0), Em_v((size_t)(L + 31) / 32 + 2, 0);
+        uint32_t *Pm = Pm_v.data(), *Em = Em_v.data();
         for (int j = 0; j < nk; ++j) {
             uint64_t key;
             if (kmer_key(s, j, k, 0, -1, key) && contains_host(sv, key)) bit_set(Pm, j);
@@ -136,16 +138,30 @@ uint64_t emu_get_errors(uint32_t n, const uint64_t* bases, const uint32_t* nmask
         const int L = (int)len[r];
         const uint32_t wo = word_off[r];
         const int nw = (L + 31) >> 5;
-        ErrScratch sc;
-        std::memset(&sc, 0, sizeof sc);
-        for (int w = 0; w < nw; ++w) { sc.P_w[w] = bases[wo + w]; sc.P_nm[w] = nmask[wo + w]; }
-        for (int i = 0; i < L; ++i)
-            if (qual[(size_t)wo * 32 + i] <= 6) bit_set(sc.QL, i);
         bool has_n = false;  // as the kernel: key building skips the N masks of reads without N
-        for (int w = 0; w < nw; ++w) has_n = has_n || sc.P_nm[w] != 0;
-        ErrCaller<HostQueryRef> ec(HostQueryRef{&q}, k, qual + (size_t)wo * 32, sc, has_n);
-        const ErrResult res = ec.run(L);
-        for (int w = 0; w < nw; ++w) err_bits[wo + w] = sc.E[w];
+        for (int w = 0; w < nw; ++w) has_n = has_n || nmask[wo + w] != 0;
+        auto fill = [&](auto& sc) {
+            for (int w = 0; w < nw; ++w) { sc.P_w[w] = bases[wo + w]; sc.P_nm[w] = nmask[wo + w]; }
+            for (int i = 0; i < L; ++i)
+                if (qual[(size_t)wo * 32 + i] <= 6) bit_set(sc.QL, i);
+        };
+        ErrResult res;
+        if (L <= KBBQ_MAX_READ_LEN) {  // the statically sized scratch of pass3_repair_kernel<false>
+            ErrScratch sc;
+            std::memset(&sc, 0, sizeof sc);
+            fill(sc);
+            ErrCaller<HostQueryRef> ec(HostQueryRef{&q}, k, qual + (size_t)wo * 32, sc, has_n);
+            res = ec.run(L);
+            for (int w = 0; w < nw; ++w) err_bits[wo + w] = sc.E[w];
+        } else {  // ... and the one cut from a buffer sized for the read, as pass3_repair_kernel<true> does
+            std::vector<unsigned long long> buf(ErrScratchDyn::bytes(nw) / 8 + 1, 0);
+            ErrScratchDyn sc;
+            sc.carve(buf.data(), nw);
+            fill(sc);
+            ErrCaller<HostQueryRef, ErrScratchDyn> ec(HostQueryRef{&q}, k, qual + (size_t)wo * 32, sc, has_n);
+            res = ec.run(L);
+            for (int w = 0; w < nw; ++w) err_bits[wo + w] = sc.E[w];
+        }
         mod_idx[r] = res.mod_idx;
         mod_base[r] = res.mod_base;
     }

@@ -185,16 +185,45 @@ def test_pipeline_with_many_distinct_qualities():
     common.compare(common.run_gpu(rs, k, G, cov, 31337), common.run_port(rs, k, G, cov, 31337))
 
 
-def test_maximum_read_length_and_one_base_more():
-    """512-base reads (KBBQ_ABI_MAX_READ_LEN: 16 words, two rounds of the 256-base groups) go through every pass;
-    513 bases are refused with KBBQ_ERANGE."""
+def test_longest_reads_of_the_static_scratch():
+    """512-base reads (KBBQ_MAX_READ_LEN: 16 words, the largest the statically sized shared-memory scratch holds) go
+    through every pass."""
     G, cov, L, k = 50000, 30, 512, 32
     rs = synth.make_reads(G, cov, L, seed=23, err_scale=2.0, ragged=True, min_len=400, n_rg=2)
     common.compare(common.run_gpu(rs, k, G, cov, 7), common.run_port(rs, k, G, cov, 7))
-    long_rs = synth.make_reads(2000, 10, 513, seed=1)
-    with pytest.raises(api.KbbqError) as e:
-        api.PackedBatch(long_rs)
-    assert e.value.code == -5  # KBBQ_ERANGE
+
+
+@pytest.mark.parametrize("k,cov,L,kw", [
+    (32, 14, 513, dict(err_scale=2.0, ragged=True, min_len=505)),                      # one base more: 17 words
+    (32, 12, 700, dict(err_scale=3.0, ragged=True, min_len=300, n_frac=0.001, n_rg=2)),  # mixed with short reads
+    (25, 16, 3000, dict(err_scale=0.7, ragged=True, min_len=100)),                     # ~94 words, several chunks of pass 1's list
+    (21, 14, 20000, dict(err_scale=0.5, ragged=True, min_len=9000)),                    # the repair kernel down to one warp per block
+])
+def test_reads_beyond_512_bases_take_the_long_path(k, cov, L, kw):
+    """The reference has no read-length limit (readutils.cc:64-104).  A batch with a read of more than 512 bases is
+    routed to the kernels' LONG instantiations (masks and error-calling scratch in dynamic shared memory sized for the
+    batch, the position list of pass 1 in pieces); every intermediate must still be the port's."""
+    G = 60000
+    rs = synth.make_reads(G, cov, L, seed=200 + k, **kw)
+    assert int(np.diff(rs.off).max()) > 512
+    common.compare(common.run_gpu(rs, k, G, cov, 77), common.run_port(rs, k, G, cov, 77))
+
+
+def test_long_reads_with_every_insert_mode(monkeypatch):
+    G, cov, L, k = 40000, 16, 900, 32
+    rs = synth.make_reads(G, cov, L, seed=9, err_scale=0.7, ragged=True, min_len=200)
+    want = common.run_port(rs, k, G, cov, 5)
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("KBBQ_INSERT_MODE", mode)
+        monkeypatch.setenv("KBBQ_STAGE_SHIFT", "4")
+        common.compare(common.run_gpu(rs, k, G, cov, 5), want, what=f"insert mode {mode}: ")
+
+
+def test_the_longest_read_the_abi_takes():
+    """65535 bases: one warp per block in the repair kernel, 2049 words of every mask."""
+    G, k = 200000, 32
+    rs = synth.make_reads(G, 1, 65535, seed=4, n_reads=6, err_scale=0.3)
+    common.compare(common.run_gpu(rs, k, G, 2, 3), common.run_port(rs, k, G, 2, 3))
 
 
 def test_empty_batch_and_reads_shorter_than_k():

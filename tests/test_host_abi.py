@@ -110,10 +110,12 @@ def test_pack_roundtrip_and_limits():
         assert np.array_equal(pb.qual[wo * 32: wo * 32 + L], rs.qual[b0:b0 + L])
     flags = (np.arange(rs.total_bases) % 3 == 0).astype(np.uint8)
     assert np.array_equal(pb.unpack_bits(pb.pack_bits(flags), rs.total_bases), flags)
-    long = synth.make_reads(5000, 1, 600, seed=1, n_reads=2)
+    long = synth.make_reads(5000, 1, 600, seed=1, n_reads=2)  # beyond 512 bases: packed like any other read
+    assert api.PackedBatch(long).max_len == 600
+    too_long = synth.make_reads(70000, 1, 65536, seed=1, n_reads=1)
     with pytest.raises(api.KbbqError) as e:
-        api.PackedBatch(long)
-    assert e.value.code == -5
+        api.PackedBatch(too_long)
+    assert e.value.code == -5  # KBBQ_ERANGE: longer than KBBQ_ABI_MAX_READ_LEN
     empty = rs.subset(0, 0)
     assert api.PackedBatch(empty).n_words == 0
 
@@ -172,6 +174,8 @@ def test_canonical_kmers_with_substitution():
     (31, 14, 150, dict(ragged=True, min_len=62, n_frac=0.003)),
     (32, 20, 64, dict(err_scale=3.0)),       # len == 2k: shortest reads every k-mer helper still accepts
     (16, 30, 250, dict(err_scale=6.0)),      # long, error-rich reads: recursion on bad prefixes/suffixes
+    (32, 12, 700, dict(err_scale=3.0, ragged=True, min_len=300, n_frac=0.001)),  # beyond 512 bases: the dynamically sized scratch
+    (25, 16, 3000, dict(err_scale=0.7, ragged=True, min_len=100)),               # ... and ~94 words per read
 ])
 def test_emulated_kernel_logic_matches_port(k, cov, L, kw):
     E = _emu()

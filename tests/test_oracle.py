@@ -80,6 +80,8 @@ needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built 
     (31, 30, 150, dict(err_scale=4.0)),
     (32, 25, 130, dict(ragged=True, min_len=64, n_frac=0.001)),
     (11, 20, 60, dict(err_scale=2.0)),
+    (32, 12, 700, dict(err_scale=3.0, ragged=True, min_len=300, n_frac=0.001)),  # reads beyond 512 bases (the GPU's long-read path)
+    (25, 16, 3000, dict(err_scale=0.7, ragged=True, min_len=100)),
 ])
 def test_port_matches_reference(k, cov, L, kw):
     G = 60000
