@@ -1615,12 +1615,17 @@ int kbbq_pass1_subsample(kbbq_ctx* ctx, const kbbq_dbatch* cb) {
             if (int rc = staging_begin(ctx, KBBQ_FILTER_SAMPLED, b->n_slots, grid, st)) return rc;
         const StageSink sink = st.sink;
         const BloomView fv = ctx->filt[KBBQ_FILTER_SAMPLED].view();
-        if (mode == INS_STAGED)
-            pass1_insert_kernel<INS_STAGED><<<grid, KBBQ_WARPS_PER_BLOCK * 32, st.smem(), ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
-        else if (mode == INS_TEST_FIRST)
-            pass1_insert_kernel<INS_TEST_FIRST><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
-        else
-            pass1_insert_kernel<INS_DIRECT><<<grid, KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink);
+#define P1_LAUNCH(M, L, SM) pass1_insert_kernel<M, L><<<grid, KBBQ_WARPS_PER_BLOCK * 32, SM, ctx->stream>>>(b->view(), fv, ctx->k, b->d_sample_bits, sink)
+        if (b->max_len > KBBQ_MAX_READ_LEN) {  // a read longer than the kernel's position list
+            if (mode == INS_STAGED) P1_LAUNCH(INS_STAGED, true, st.smem());
+            else if (mode == INS_TEST_FIRST) P1_LAUNCH(INS_TEST_FIRST, true, 0);
+            else P1_LAUNCH(INS_DIRECT, true, 0);
+        } else {
+            if (mode == INS_STAGED) P1_LAUNCH(INS_STAGED, false, st.smem());
+            else if (mode == INS_TEST_FIRST) P1_LAUNCH(INS_TEST_FIRST, false, 0);
+            else P1_LAUNCH(INS_DIRECT, false, 0);
+        }
+#undef P1_LAUNCH
         if (int rc = check_launch(ctx, "pass1_insert_kernel")) return rc;
         if (mode == INS_STAGED) {
             if (int rc = staging_apply(ctx, KBBQ_FILTER_SAMPLED, st)) return rc;
@@ -1791,17 +1796,17 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         if (int rc = need_quals(ctx, b)) return rc;
         mark_kernel(ctx, "pass3_repair_kernel");
         if (b->max_len <= KBBQ_MAX_READ_LEN) {
-            pass3_repair_kernel<false><<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
-                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1, KBBQ_MAXW);
+            pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1);
         } else {  // long reads: the scratch is cut from dynamic shared memory, as many warps per block as fit
             const int maxw = ((int)b->max_len + 31) / 32;
             const size_t per_warp = ErrScratchDyn::bytes(maxw);
             const int warps = (int)std::max<size_t>(1, std::min<size_t>(KBBQ_WARPS_PER_BLOCK, (200 * 1024) / per_warp));
             const size_t smem = per_warp * warps;
             if (smem > 220 * 1024) return fail(KBBQ_ERANGE, "read too long for the error caller's shared-memory scratch");
-            CU(cudaFuncSetAttribute(pass3_repair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(pass3_repair_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const long long blocks = std::max(1ll, std::min(((long long)b->n_reads + warps - 1) / warps, (long long)ctx->sm_count * 4));
-            pass3_repair_kernel<true><<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(
+            pass3_repair_long_kernel<<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1, maxw);
         }
         if (int rc = check_launch(ctx, "pass3_repair_kernel")) return rc;

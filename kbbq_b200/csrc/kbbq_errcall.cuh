@@ -61,7 +61,7 @@ struct ErrScratch {
 };
 
 // The same scratch with its arrays somewhere else: reads longer than KBBQ_MAX_READ_LEN get theirs cut from dynamic shared
-// memory sized for the batch's longest read (pass3_repair_kernel<true>); every array holds maxw + 1 words.
+// memory sized for the batch's longest read (pass3_repair_long_kernel); every array holds maxw + 1 words.
 struct ErrScratchDyn {
     unsigned long long *P_w, *A_w, *C_w;
     uint32_t *P_nm, *A_nm, *C_nm, *O_nm, *T_orig, *T_cur, *E, *QL, *F, *FQ;

@@ -469,7 +469,8 @@ __global__ void __launch_bounds__(128) rng_sample_kernel(uint64_t s0, uint64_t s
 }
 
 // ---- pass 1b: insert the sampled k-mers (recalibrateutils.cc:7-13) ---------------------------------------------------
-template <int MODE>
+// LONG: the batch holds a read of more than KBBQ_MAX_READ_LEN bases, whose sampled positions go through the list in pieces
+template <int MODE, bool LONG = false>
 __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel(BatchView b, BloomView f, int k,
                                                                                   const uint32_t* __restrict__ sample_bits,
                                                                                   StageSink sink) {
@@ -494,8 +495,8 @@ __global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32) pass1_insert_kernel
         // the sampled positions first (a bit test and a ballot per 32 slots), then keys for those only, 32 at a time:
         // at alpha = 7/30 a 150-base read has 28 of them -- one dense round instead of four quarter-full ones
         // (a read longer than the list goes through in pieces of KBBQ_MAX_READ_LEN slots)
-        for (int c0 = 0; c0 < nk; c0 += KBBQ_MAX_READ_LEN) {
-            const int c1 = nk - c0 < KBBQ_MAX_READ_LEN ? nk : c0 + KBBQ_MAX_READ_LEN;
+        for (int c0 = 0; c0 < (LONG ? nk : 1); c0 += KBBQ_MAX_READ_LEN) {
+            const int c1 = !LONG || nk - c0 < KBBQ_MAX_READ_LEN ? nk : c0 + KBBQ_MAX_READ_LEN;
             int total = 0;
             for (int j0 = c0; j0 < c1; j0 += 32) {
                 const int j = j0 + lane;
@@ -1066,14 +1067,18 @@ struct DevQuery {
 #ifndef KBBQ_P3R_MIN_BLOCKS
 #define KBBQ_P3R_MIN_BLOCKS 4
 #endif
-// LONG: a batch whose longest read exceeds KBBQ_MAX_READ_LEN.  The scratch then comes from dynamic shared memory,
-// ErrScratchDyn::bytes(maxw) per warp, and the block has as many warps as fit (the launch decides: 8 down to 1).
-template <bool LONG, class SC>
-__device__ __forceinline__ void repair_reads(SC& sc, const BatchView& b, DevQuery q, int k, const uint32_t* __restrict__ tflags,
-                                             uint32_t* __restrict__ err_out, uint32_t* __restrict__ mod_out,
-                                             const uint32_t* __restrict__ repair_list, uint32_t n_list,
-                                             unsigned int* __restrict__ work_counter) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, KBBQ_P3R_MIN_BLOCKS)
+pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
+                    uint32_t* __restrict__ mod_out, const uint32_t* __restrict__ repair_list,
+                    const unsigned int* __restrict__ repair_count, unsigned int* __restrict__ work_counter) {
+    __shared__ ErrScratch scratch[KBBQ_WARPS_PER_BLOCK];
+    __shared__ BloomView filter;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    ErrScratch& sc = scratch[wib];
+    if (threadIdx.x == 0) filter = trusted;
+    __syncthreads();
+    DevQuery q{&filter};
+    const uint32_t n_list = *repair_count;
     for (;;) {
         // reads differ a lot in cost (a single repair to ~1000 probes): pull, don't stride
         uint32_t idx = 0;
@@ -1085,51 +1090,71 @@ __device__ __forceinline__ void repair_reads(SC& sc, const BatchView& b, DevQuer
         const uint32_t wo = b.word_off[r];
         const int nw = (len + 31) >> 5;
         const uint8_t* qual = b.qual + (size_t)wo * 32;
+        if (lane <= nw) {
+            sc.P_w[lane] = lane < nw ? b.bases[wo + lane] : 0ull;
+            sc.P_nm[lane] = lane < nw ? b.nmask[wo + lane] : 0u;
+            sc.E[lane] = 0;
+            sc.T_orig[lane] = 32 * lane < len - k + 1 ? tflags[wo + lane] : 0u;  // the scan wrote one word per 32 k-mers
+            // low-quality flags for the overcorrection half weight (bits past the read's end cleared)
+            const int left = len - 32 * lane;
+            sc.QL[lane] = lane < nw ? b.qmask[wo + lane].y & (left >= 32 ? ~0u : ((1u << left) - 1u)) : 0u;
+        }
+        __syncwarp();
+        const bool has_n = __any_sync(KBBQ_FULL, lane < nw && sc.P_nm[lane] != 0u);
+        ErrCaller<DevQuery> ec(q, k, qual, sc, has_n);
+        const ErrResult res = ec.run(len, true);
+        __syncwarp();
+        if (lane < nw) err_out[wo + lane] = sc.E[lane];
+        if (lane == 0) mod_out[r] = res.mod_idx >= 0 ? (uint32_t)(4 * res.mod_idx + res.mod_base) : 0xFFFFFFFFu;
+        __syncwarp();
+    }
+}
+
+// The same for a batch whose longest read exceeds KBBQ_MAX_READ_LEN: the scratch is cut from dynamic shared memory,
+// ErrScratchDyn::bytes(maxw) per warp, the block has as many warps as fit (the launch decides: 8 down to 1), and the
+// per-word set-up walks the read 32 words at a time.  A slow path: 198 registers, one block per SM.
+__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, 1)
+pass3_repair_long_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
+                         uint32_t* __restrict__ mod_out, const uint32_t* __restrict__ repair_list,
+                         const unsigned int* __restrict__ repair_count, unsigned int* __restrict__ work_counter, int maxw) {
+    extern __shared__ __align__(16) unsigned char repair_dyn[];  // [warps of the block][ErrScratchDyn::bytes(maxw)]
+    __shared__ BloomView filter;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) filter = trusted;
+    __syncthreads();
+    DevQuery q{&filter};
+    ErrScratchDyn sc;
+    sc.carve(repair_dyn + (size_t)wib * ErrScratchDyn::bytes(maxw), maxw);
+    const uint32_t n_list = *repair_count;
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(work_counter, 1u);
+        idx = __shfl_sync(KBBQ_FULL, idx, 0);
+        if (idx >= n_list) break;
+        const uint32_t r = repair_list[idx];
+        const int len = (int)b.len[r];
+        const uint32_t wo = b.word_off[r];
+        const int nw = (len + 31) >> 5;
+        const uint8_t* qual = b.qual + (size_t)wo * 32;
         bool any_n = false;
-        for (int w = lane; w <= nw; w += 32) {  // one trip for reads of up to 31 words
+        for (int w = lane; w <= nw; w += 32) {
             sc.P_w[w] = w < nw ? b.bases[wo + w] : 0ull;
             const uint32_t nm = w < nw ? b.nmask[wo + w] : 0u;
             sc.P_nm[w] = nm;
             any_n = any_n || nm != 0u;
             sc.E[w] = 0;
-            sc.T_orig[w] = 32 * w < len - k + 1 ? tflags[wo + w] : 0u;  // the scan wrote one word per 32 k-mers
-            // low-quality flags for the overcorrection half weight (bits past the read's end cleared)
+            sc.T_orig[w] = 32 * w < len - k + 1 ? tflags[wo + w] : 0u;
             const int left = len - 32 * w;
             sc.QL[w] = w < nw ? b.qmask[wo + w].y & (left >= 32 ? ~0u : ((1u << left) - 1u)) : 0u;
-            if (!LONG) break;
         }
         __syncwarp();
         const bool has_n = __any_sync(KBBQ_FULL, any_n);
-        ErrCaller<DevQuery, SC> ec(q, k, qual, sc, has_n);
+        ErrCaller<DevQuery, ErrScratchDyn> ec(q, k, qual, sc, has_n);
         const ErrResult res = ec.run(len, true);
         __syncwarp();
-        for (int w = lane; w < nw; w += 32) {
-            err_out[wo + w] = sc.E[w];
-            if (!LONG) break;
-        }
+        for (int w = lane; w < nw; w += 32) err_out[wo + w] = sc.E[w];
         if (lane == 0) mod_out[r] = res.mod_idx >= 0 ? (uint32_t)(4 * res.mod_idx + res.mod_base) : 0xFFFFFFFFu;
         __syncwarp();
-    }
-}
-template <bool LONG>
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, LONG ? 1 : KBBQ_P3R_MIN_BLOCKS)
-pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
-                    uint32_t* __restrict__ mod_out, const uint32_t* __restrict__ repair_list,
-                    const unsigned int* __restrict__ repair_count, unsigned int* __restrict__ work_counter, int maxw) {
-    extern __shared__ __align__(16) unsigned char repair_dyn[];  // LONG: [warps of the block][ErrScratchDyn::bytes(maxw)]
-    __shared__ ErrScratch scratch[LONG ? 1 : KBBQ_WARPS_PER_BLOCK];
-    __shared__ BloomView filter;
-    const int wib = threadIdx.x >> 5;
-    if (threadIdx.x == 0) filter = trusted;
-    __syncthreads();
-    DevQuery q{&filter};
-    const uint32_t n_list = *repair_count;
-    if constexpr (LONG) {
-        ErrScratchDyn sc;
-        sc.carve(repair_dyn + (size_t)wib * ErrScratchDyn::bytes(maxw), maxw);
-        repair_reads<true>(sc, b, q, k, tflags, err_out, mod_out, repair_list, n_list, work_counter);
-    } else {
-        repair_reads<false>(scratch[wib], b, q, k, tflags, err_out, mod_out, repair_list, n_list, work_counter);
     }
 }
 

@@ -146,14 +146,14 @@ uint64_t emu_get_errors(uint32_t n, const uint64_t* bases, const uint32_t* nmask
                 if (qual[(size_t)wo * 32 + i] <= 6) bit_set(sc.QL, i);
         };
         ErrResult res;
-        if (L <= KBBQ_MAX_READ_LEN) {  // the statically sized scratch of pass3_repair_kernel<false>
+        if (L <= KBBQ_MAX_READ_LEN) {  // the statically sized scratch of pass3_repair_kernel
             ErrScratch sc;
             std::memset(&sc, 0, sizeof sc);
             fill(sc);
             ErrCaller<HostQueryRef> ec(HostQueryRef{&q}, k, qual + (size_t)wo * 32, sc, has_n);
             res = ec.run(L);
             for (int w = 0; w < nw; ++w) err_bits[wo + w] = sc.E[w];
-        } else {  // ... and the one cut from a buffer sized for the read, as pass3_repair_kernel<true> does
+        } else {  // ... and the one cut from a buffer sized for the read, as pass3_repair_long_kernel does
             std::vector<unsigned long long> buf(ErrScratchDyn::bytes(nw) / 8 + 1, 0);
             ErrScratchDyn sc;
             sc.carve(buf.data(), nw);

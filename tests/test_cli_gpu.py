@@ -70,6 +70,32 @@ def test_cli_against_live_reference_cli(tmp_path):
     assert got == gzip.open(tmp_path / "ref.gz").read()
 
 
+def test_cli_long_reads_against_live_reference_cli(tmp_path):
+    """Reads of up to 2500 bases (the reference has no length limit) through both binaries, sharded over two GPUs where
+    the box has them."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "kbbq_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/kbbq_ref not present")
+    import sys
+    sys.path.insert(0, ROOT)
+    from kbbq_b200 import synth
+
+    rs = synth.make_reads(60000, 16, 2500, seed=12, err_scale=0.7, ragged=True, min_len=90, n_rg=2)
+    fq = str(tmp_path / "long.fq")
+    synth.to_fastq(rs, fq)
+    args = ["-k", "32", "-g", "60000", "-c", "16", fq]
+    with open(tmp_path / "ref.gz", "wb") as fo:
+        r = subprocess.run([ref] + args, stdout=fo, stderr=subprocess.PIPE)
+    assert r.returncode == 0
+    want = gzip.open(tmp_path / "ref.gz").read()
+    got, _ = _run(["--seed", "2854027472"] + args, tmp_path)
+    assert got == want
+    import torch
+    if torch.cuda.device_count() >= 2:
+        got2, _ = _run(["--seed", "2854027472", "--gpus", "2"] + args, tmp_path)
+        assert got2 == want
+
+
 def _bam_records(data):
     """Split an uncompressed BAM stream into (header bytes, [record bytes])."""
     import struct
