@@ -1,6 +1,7 @@
 // kbbq_capi.cu -- implementation of include/kbbq_b200.h: contexts, device memory, kernel launches.
 // No CPU fallback lives here: every pass entry point launches the sm_100a kernels or fails with KBBQ_ECUDA.
 #include "../../include/kbbq_b200.h"
+#include "kbbq_long.h"
 
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
@@ -1798,16 +1799,10 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         if (b->max_len <= KBBQ_MAX_READ_LEN) {
             pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1);
-        } else {  // long reads: the scratch is cut from dynamic shared memory, as many warps per block as fit
-            const int maxw = ((int)b->max_len + 31) / 32;
-            const size_t per_warp = ErrScratchDyn::bytes(maxw);
-            const int warps = (int)std::max<size_t>(1, std::min<size_t>(KBBQ_WARPS_PER_BLOCK, (200 * 1024) / per_warp));
-            const size_t smem = per_warp * warps;
-            if (smem > 220 * 1024) return fail(KBBQ_ERANGE, "read too long for the error caller's shared-memory scratch");
-            CU(cudaFuncSetAttribute(pass3_repair_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const long long blocks = std::max(1ll, std::min(((long long)b->n_reads + warps - 1) / warps, (long long)ctx->sm_count * 4));
-            pass3_repair_long_kernel<<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(
-                b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1, maxw);
+        } else {  // long reads: kbbq_long.cu
+            const cudaError_t e = launch_repair_long(b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work,
+                                                     ctx->d_work + 1, b->max_len, ctx->sm_count, ctx->stream);
+            if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("pass3_repair_long_kernel: ") + cudaGetErrorString(e));
         }
         if (int rc = check_launch(ctx, "pass3_repair_kernel")) return rc;
         mark_kernel(ctx, "covariate_count_kernel");

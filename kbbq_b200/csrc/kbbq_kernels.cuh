@@ -10,74 +10,9 @@
 
 #include "kbbq_core.cuh"
 #include "kbbq_errcall.cuh"
+#include "kbbq_views.cuh"
 
 namespace kbbq {
-
-struct BatchView {
-    const unsigned long long* bases;
-    const uint32_t* nmask;
-    const uint8_t* qual;
-    const uint2* qmask;  // per word: .x = bases with qual <= 2, .y = bases with qual <= 6 (kbbq_batch::qmask)
-    const uint32_t* word_off;
-    const uint32_t* len;
-    const uint16_t* rg;
-    const uint8_t* second;
-    const unsigned long long* slot_off;  // exclusive prefix of max(0, len-k+1)
-    uint32_t n_reads;
-};
-
-struct CountView {  // covariate count tables, {errors,total} pairs of u64
-    unsigned long long* rgc;
-    unsigned long long* qc;
-    unsigned long long* cyc;
-    unsigned long long* dic;
-    int max_cycle;
-};
-
-struct ModelView {  // dq_t folded into lookup tables (readutils.cc:579-587)
-    const int16_t* base;  // [R][94]  meanq + rgdq + qscoredq
-    const int8_t* cy;     // [R][94][2][C]
-    const int8_t* di;     // [R][94][16]
-    int max_cycle;
-};
-
-// read-only view of a packed read in global memory, usable with kmer_key()
-struct CSeqRef {
-    const unsigned long long* w;
-    const uint32_t* nm;
-    int len;
-};
-
-#define KBBQ_WARPS_PER_BLOCK 8
-#define KBBQ_HP_INVALID 0xFFFFFFFFu  // (hash, pattern) parked in shared memory: pattern slot of a k-mer that holds a non-ACGT base
-#define KBBQ_HP_KNOWN 0xFFFFFFFEu    // ... of a k-mer known to be present (no probe)
-#define KBBQ_FULL 0xffffffffu
-
-// ---- filter probes ------------------------------------------------------------------------------------------------
-// 32 bytes in one LDG.E.256 (sm_100): a 64-byte block or pattern is two instructions
-__device__ __forceinline__ void ldg256(const unsigned long long* p, unsigned long long& a, unsigned long long& b,
-                                       unsigned long long& c, unsigned long long& d) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-}
-// Bring the line of a filter block into the L2 without holding a register for it.  A warp that probes one 32-k-mer
-// round at a time has 32 blocks in flight and spends its life waiting for DRAM (the scan moved 4.0 TB/s where the same
-// probes, unburdened, move 5.1); prefetching the blocks of ALL of a read's k-mers first puts ~120 in flight per warp
-// and turns the rounds that follow into L2 hits.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// pattern_blocked_bf::contains (bloom.hh:276-292): (block & pattern) == pattern over 512 bits, one lane per key
-__device__ __forceinline__ bool bloom_contains_dev(const BloomView& f, uint64_t key) {
-    const uint64_t blk = bloom_block(f, key);
-    const uint32_t pat = bloom_pattern(f, key);
-    const unsigned long long* B = f.words + blk * 8;
-    const unsigned long long* P = f.patterns + (uint64_t)pat * 8;
-    unsigned long long b0, b1, b2, b3, b4, b5, b6, b7, p0, p1, p2, p3, p4, p5, p6, p7;
-    ldg256(B, b0, b1, b2, b3);
-    ldg256(B + 4, b4, b5, b6, b7);
-    ldg256(P, p0, p1, p2, p3);
-    ldg256(P + 4, p4, p5, p6, p7);
-    const unsigned long long miss = (~b0 & p0) | (~b1 & p1) | (~b2 & p2) | (~b3 & p3) | (~b4 & p4) | (~b5 & p5) | (~b6 & p6) | (~b7 & p7);
-    return miss == 0;
-}
 
 // pattern_blocked_bf::insert (bloom.hh:255-267): block |= pattern.  OR is order independent, so atomicOr on the
 // non-zero 64-bit words gives the reference's bits whatever the interleaving.  The caller counts the insert.
@@ -1105,54 +1040,6 @@ pass3_repair_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __res
         const ErrResult res = ec.run(len, true);
         __syncwarp();
         if (lane < nw) err_out[wo + lane] = sc.E[lane];
-        if (lane == 0) mod_out[r] = res.mod_idx >= 0 ? (uint32_t)(4 * res.mod_idx + res.mod_base) : 0xFFFFFFFFu;
-        __syncwarp();
-    }
-}
-
-// The same for a batch whose longest read exceeds KBBQ_MAX_READ_LEN: the scratch is cut from dynamic shared memory,
-// ErrScratchDyn::bytes(maxw) per warp, the block has as many warps as fit (the launch decides: 8 down to 1), and the
-// per-word set-up walks the read 32 words at a time.  A slow path: 198 registers, one block per SM.
-__global__ void __launch_bounds__(KBBQ_WARPS_PER_BLOCK * 32, 1)
-pass3_repair_long_kernel(BatchView b, BloomView trusted, int k, const uint32_t* __restrict__ tflags, uint32_t* __restrict__ err_out,
-                         uint32_t* __restrict__ mod_out, const uint32_t* __restrict__ repair_list,
-                         const unsigned int* __restrict__ repair_count, unsigned int* __restrict__ work_counter, int maxw) {
-    extern __shared__ __align__(16) unsigned char repair_dyn[];  // [warps of the block][ErrScratchDyn::bytes(maxw)]
-    __shared__ BloomView filter;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (threadIdx.x == 0) filter = trusted;
-    __syncthreads();
-    DevQuery q{&filter};
-    ErrScratchDyn sc;
-    sc.carve(repair_dyn + (size_t)wib * ErrScratchDyn::bytes(maxw), maxw);
-    const uint32_t n_list = *repair_count;
-    for (;;) {
-        uint32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(work_counter, 1u);
-        idx = __shfl_sync(KBBQ_FULL, idx, 0);
-        if (idx >= n_list) break;
-        const uint32_t r = repair_list[idx];
-        const int len = (int)b.len[r];
-        const uint32_t wo = b.word_off[r];
-        const int nw = (len + 31) >> 5;
-        const uint8_t* qual = b.qual + (size_t)wo * 32;
-        bool any_n = false;
-        for (int w = lane; w <= nw; w += 32) {
-            sc.P_w[w] = w < nw ? b.bases[wo + w] : 0ull;
-            const uint32_t nm = w < nw ? b.nmask[wo + w] : 0u;
-            sc.P_nm[w] = nm;
-            any_n = any_n || nm != 0u;
-            sc.E[w] = 0;
-            sc.T_orig[w] = 32 * w < len - k + 1 ? tflags[wo + w] : 0u;
-            const int left = len - 32 * w;
-            sc.QL[w] = w < nw ? b.qmask[wo + w].y & (left >= 32 ? ~0u : ((1u << left) - 1u)) : 0u;
-        }
-        __syncwarp();
-        const bool has_n = __any_sync(KBBQ_FULL, any_n);
-        ErrCaller<DevQuery, ErrScratchDyn> ec(q, k, qual, sc, has_n);
-        const ErrResult res = ec.run(len, true);
-        __syncwarp();
-        for (int w = lane; w < nw; w += 32) err_out[wo + w] = sc.E[w];
         if (lane == 0) mod_out[r] = res.mod_idx >= 0 ? (uint32_t)(4 * res.mod_idx + res.mod_base) : 0xFFFFFFFFu;
         __syncwarp();
     }
