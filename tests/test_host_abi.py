@@ -234,6 +234,18 @@ def test_device_warmup_fails_loudly_without_a_gpu():
         assert L.kbbq_device_warmup(0) == -3 and b"no CPU path" in L.kbbq_last_error()
 
 
+def test_context_arguments_are_checked_before_any_device_is_touched():
+    """kbbq_ctx_create: k, read groups and the longest read are validated first -- also that the tables the kernels index
+    with 32-bit offsets stay below 2^31 entries (n_rg x 94 x 2 x max_cycle)."""
+    import ctypes as C
+    L = api.lib()
+    ctx = C.c_void_p()
+    assert L.kbbq_ctx_create(0, 33, 1, 100, C.byref(ctx)) == -1 and b"k must be" in L.kbbq_last_error()
+    assert L.kbbq_ctx_create(0, 32, 0, 100, C.byref(ctx)) == -1
+    assert L.kbbq_ctx_create(0, 32, 1, 65536, C.byref(ctx)) == -1  # longer than KBBQ_ABI_MAX_READ_LEN
+    assert L.kbbq_ctx_create(0, 32, 400, 65535, C.byref(ctx)) == -5 and b"too large" in L.kbbq_last_error()
+
+
 def test_header_is_plain_c(tmp_path):
     """The boundary is a C ABI: include/kbbq_b200.h must compile as C99 on its own, and a C program must link against
     the library and get the loud no-GPU failure (or a context) through it."""
