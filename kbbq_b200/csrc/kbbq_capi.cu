@@ -1799,10 +1799,27 @@ int kbbq_pass3_covariates(kbbq_ctx* ctx, const kbbq_dbatch* cb, uint32_t* err_bi
         if (b->max_len <= KBBQ_MAX_READ_LEN) {
             pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
                 b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work, ctx->d_work + 1);
-        } else {  // long reads: kbbq_long.cu
-            const cudaError_t e = launch_repair_long(b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, b->d_repair, ctx->d_work,
-                                                     ctx->d_work + 1, b->max_len, ctx->sm_count, ctx->stream);
-            if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("pass3_repair_long_kernel: ") + cudaGetErrorString(e));
+        } else {
+            // a batch with long reads (kbbq_long.cu): its repair list is split, the reads of up to KBBQ_MAX_READ_LEN bases
+            // go through the common kernel at full speed and only the long ones through the slow one
+            uint32_t* split = nullptr;
+            unsigned int* counts = nullptr;
+            CU(cudaMallocAsync(&split, (size_t)b->n_reads * 4, ctx->stream));
+            CU(cudaMallocAsync(&counts, 4 * sizeof(unsigned int), ctx->stream));
+            cudaError_t e = launch_split_repair_list(b->d_len, b->d_repair, ctx->d_work, b->n_reads, split, counts, ctx->sm_count, ctx->stream);
+            ++ctx->launches;
+            if (e == cudaSuccess) {
+                pass3_repair_kernel<<<read_grid(ctx, b->n_reads), KBBQ_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(
+                    b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, split, counts, counts + 1);
+                e = cudaGetLastError();
+                ++ctx->launches;
+            }
+            if (e == cudaSuccess)
+                e = launch_repair_long(b->view(), tv, ctx->k, b->d_tflags, b->d_err_bits, b->d_mod, split + (b->n_reads - 1), counts + 2,
+                                       counts + 3, b->max_len, ctx->sm_count, ctx->stream);
+            cudaFreeAsync(split, ctx->stream);
+            cudaFreeAsync(counts, ctx->stream);
+            if (e != cudaSuccess) return fail(KBBQ_ECUDA, std::string("pass 3 repairs of a long-read batch: ") + cudaGetErrorString(e));
         }
         if (int rc = check_launch(ctx, "pass3_repair_kernel")) return rc;
         mark_kernel(ctx, "covariate_count_kernel");

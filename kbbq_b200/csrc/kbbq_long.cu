@@ -50,7 +50,7 @@ pass3_repair_long_kernel(BatchView b, BloomView trusted, int k, const uint32_t* 
         if (lane == 0) idx = atomicAdd(work_counter, 1u);
         idx = __shfl_sync(KBBQ_FULL, idx, 0);
         if (idx >= n_list) break;
-        const uint32_t r = repair_list[idx];
+        const uint32_t r = repair_list[-(long long)idx];  // the long reads sit at the END of the split list, last first
         const int len = (int)b.len[r];
         const uint32_t wo = b.word_off[r];
         const int nw = (len + 31) >> 5;
@@ -77,6 +77,28 @@ pass3_repair_long_kernel(BatchView b, BloomView trusted, int k, const uint32_t* 
     }
 }
 
+
+// Splits the scan's repair list of a long batch: reads of up to KBBQ_MAX_READ_LEN bases to the front of `out` (they go
+// through the common repair kernel at its full speed), longer ones to its end; counts[0] / counts[2] = how many of each
+// (counts[1], counts[3]: the two kernels' work counters, zeroed by the caller).
+__global__ void __launch_bounds__(256) split_repair_list_kernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ list,
+                                                                const unsigned int* __restrict__ n_list, uint32_t n_reads,
+                                                                uint32_t* __restrict__ out, unsigned int* __restrict__ counts) {
+    const uint32_t n = *n_list;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t r = list[i];
+        if (len[r] <= KBBQ_MAX_READ_LEN) out[atomicAdd(counts, 1u)] = r;
+        else out[n_reads - 1 - atomicAdd(counts + 2, 1u)] = r;
+    }
+}
+cudaError_t launch_split_repair_list(const uint32_t* len, const uint32_t* list, const unsigned int* n_list, uint32_t n_reads,
+                                     uint32_t* out, unsigned int* counts, int sm_count, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)std::max(1ll, std::min(((long long)n_reads + 255) / 256, (long long)sm_count * 8));
+    split_repair_list_kernel<<<blocks, 256, 0, stream>>>(len, list, n_list, n_reads, out, counts);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_repair_long(const BatchView& b, const BloomView& trusted, int k, const uint32_t* tflags, uint32_t* err_out,
                                uint32_t* mod_out, const uint32_t* repair_list, const unsigned int* repair_count,
