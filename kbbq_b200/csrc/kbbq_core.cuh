@@ -30,7 +30,8 @@
 #define KBBQ_MAXQ 93           // KBBQ_MAXQ, covariateutils.hh:3
 #define KBBQ_NQ 94
 #define KBBQ_NUM_PATTERNS 65536  // pattern_blocked_bf::num_patterns, bloom.hh:185
-#define KBBQ_MAX_READ_LEN 512  // longest read the per-warp shared-memory scratch holds
+#define KBBQ_MAX_READ_LEN 512  // longest read the STATIC per-warp shared-memory scratch holds; batches with longer reads
+                               // (up to KBBQ_ABI_MAX_READ_LEN) take the LONG instantiations and kbbq_long.cu
 #define KBBQ_MAXW (KBBQ_MAX_READ_LEN / 32)
 
 namespace kbbq {

@@ -187,6 +187,10 @@ def test_cli_error_paths_without_a_gpu(tmp_path):
     (tmp_path / "many.fq").write_bytes(b"".join(b"@\n" + b"ACGT" * 9 + b"\n+\n" + b"I" * 36 + b"\n" for _ in range(6000)))
     r = subprocess.run([cli, "-g", "100", "many.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=tmp_path)
     assert r.returncode in (0, 1)  # never a signal
+    # a read beyond the ABI's 65 535 bases: refused while packing, with the limit named, whatever the box has
+    (tmp_path / "huge.fq").write_bytes(b"@r0\n" + b"ACGT" * 17500 + b"\n+\n" + b"I" * 70000 + b"\n")
+    rc, err = run("-g", "100000", "-c", "5", "huge.fq")
+    assert rc == 1 and "KBBQ_ABI_MAX_READ_LEN" in err
     from kbbq_b200 import api
     rc, err = run("tiny.fq")
     if api.lib().kbbq_device_count() == 0:  # the GPU context comes first: no device, no run
@@ -264,3 +268,32 @@ def test_bgzf_writer_modes_all_inflate_to_the_same_stream(tool, tmp_path, level)
         assert raw[p:p + 4] == b"\x1f\x8b\x08\x04" and raw[p + 12:p + 14] == b"BC"
         p += int.from_bytes(raw[p + 16:p + 18], "little") + 1
     assert p == len(raw)
+
+
+def test_sink_deflate_encoder_on_mixed_content(tool, tmp_path):
+    """2 MB of segments with very different statistics (random bytes, two-symbol runs, long repeats, zero runs, text with
+    a shifting alphabet) cut into small blocks, so that hundreds of differently shaped code tables are built and read back."""
+    rng = np.random.default_rng(11)
+    parts = []
+    while sum(len(p) for p in parts) < (2 << 20):
+        kind = int(rng.integers(0, 6))
+        n = int(rng.integers(1, 30000))
+        if kind == 0:
+            parts.append(rng.bytes(n))
+        elif kind == 1:
+            parts.append(bytes(rng.choice([65, 66], n, p=[0.97, 0.03]).astype(np.uint8).tolist()))
+        elif kind == 2:
+            motif = rng.bytes(int(rng.integers(1, 300)))
+            parts.append((motif * (n // len(motif) + 1))[:n])
+        elif kind == 3:
+            parts.append(bytes(n))
+        elif kind == 4:
+            lo = int(rng.integers(0, 200))
+            parts.append(bytes((rng.integers(0, int(rng.integers(2, 56)), n) + lo).astype(np.uint8).tolist()))
+        else:
+            parts.append(bytes(np.minimum(rng.geometric(0.05, n), 255).astype(np.uint8).tolist()))
+    data = b"".join(parts)
+    (tmp_path / "in").write_bytes(data)
+    for block, min_match in ((1000, 8), (4096, 12), (65280, 8), (65535, 258)):
+        subprocess.run([tool, "deflate", str(tmp_path / "in"), str(tmp_path / "out"), str(block), str(min_match)], check=True)
+        assert _inflate_pieces((tmp_path / "out").read_bytes()) == data, (block, min_match)
