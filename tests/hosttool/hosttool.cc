@@ -4,6 +4,10 @@
 //   hosttool rewrite FILE QUALS OUT [set_oq] [use_oq]
 //        QUALS holds one line of new qualities (+33, read orientation) per record; every record is passed through
 //        HTSFile::next / recalibrate / write exactly as recalibrate_and_write's generic loop does
+//   hosttool prepack FILE K NGPUS
+//        a background Session over NGPUS devices (its contexts come up, or fail, on a side thread) packs every GPU's first
+//        batch without touching a context: prints one line per batch (lo hi gpu n_words slots prepacked), then whether
+//        the contexts arrived
 //   hosttool deflate FILE OUT BLOCK MINMATCH
 //        the sink's own DEFLATE encoder (fast_deflate.hh) on FILE cut into BLOCK-byte pieces; OUT = per piece a
 //        little-endian u32 stream length followed by the raw stream
@@ -59,6 +63,22 @@ int main(int argc, char** argv) {
                 std::cout << r.name << '\t' << r.seq << '\t' << q << '\t' << readutils::CReadData::rg_to_int[r.rg] << '\t' << (int)r.second << '\n';
             }
             for (uint64_t l : f->store().ref_len) std::cout << "#ref\t" << l << '\n';
+        } else if (mode == "prepack") {
+            if (argc < 5) return 2;
+            const int k = atoi(argv[3]), ngpus = atoi(argv[4]);
+            std::vector<int> devices;
+            for (int d = 0; d < ngpus; ++d) devices.push_back(d);
+            const int n_rg = (int)std::max<size_t>(1, readutils::CReadData::rg_to_int.size());
+            kbbq::Session ses(k, n_rg, (int)std::max<uint32_t>(1, f->store().max_len), devices, true);
+            ses.prepack(f->store());
+            for (const kbbq::SessionBatch& b : ses.batches())
+                std::cout << b.lo << '\t' << b.hi << '\t' << b.gpu << '\t' << b.n_words << '\t' << b.slots << '\t' << (b.prepacked ? 1 : 0) << '\n';
+            try {
+                const size_t n_ctx = ses.contexts().size();
+                std::cout << "contexts\t" << n_ctx << '\n';
+            } catch (const std::exception& e) {
+                std::cout << "contexts\tfailed\t" << e.what() << '\n';
+            }
         } else if (mode == "rewrite") {
             std::ifstream qin(argv[3]);
             if (f->open_out(argv[4]) < 0) return 3;

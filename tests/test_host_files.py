@@ -297,3 +297,28 @@ def test_sink_deflate_encoder_on_mixed_content(tool, tmp_path):
     for block, min_match in ((1000, 8), (4096, 12), (65280, 8), (65535, 258)):
         subprocess.run([tool, "deflate", str(tmp_path / "in"), str(tmp_path / "out"), str(block), str(min_match)], check=True)
         assert _inflate_pieces((tmp_path / "out").read_bytes()) == data, (block, min_match)
+
+
+def test_session_packs_ahead_of_its_contexts(tool, tmp_path):
+    """kbbq::Session(background): the contexts are created on a side thread and Session::prepack cuts the input into
+    batches and packs every GPU's first batch without one -- on a box without a GPU the packing still happens and the
+    missing device is reported, loudly, only when a context is asked for."""
+    from kbbq_b200 import api, synth
+    rs = synth.make_reads(50000, 12, 120, seed=8, ragged=True, min_len=20, n_rg=2)
+    fq = tmp_path / "in.fq"
+    synth.to_fastq(rs, str(fq))
+    k, ngpus = 25, 3
+    out = subprocess.run([tool, "prepack", str(fq), str(k), str(ngpus)], capture_output=True, text=True, check=True).stdout.splitlines()
+    rows = [tuple(int(x) for x in ln.split("\t")) for ln in out if not ln.startswith("contexts")]
+    assert [r[2] for r in rows] == [i % ngpus for i in range(len(rows))]           # dealt round-robin
+    assert rows[0][0] == 0 and rows[-1][1] == rs.n and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    lens = np.diff(rs.off).astype(np.int64)
+    for lo, hi, _gpu, n_words, slots, prepacked in rows:
+        assert prepacked == 1                                                        # one batch per GPU here: all packed ahead
+        assert n_words == api.PackedBatch(rs.subset(lo, hi)).n_words
+        assert slots == int(np.maximum(lens[lo:hi] - k + 1, 0).sum())
+    ctx = [ln for ln in out if ln.startswith("contexts")][0].split("\t")
+    if api.lib().kbbq_device_count() >= ngpus:
+        assert ctx[1] == str(ngpus)
+    else:
+        assert ctx[1] == "failed"
